@@ -1,0 +1,193 @@
+/*
+ * jmme.h — C ABI of the JM (H.264 reference encoder, lencod) motion-estimation hot path.
+ *
+ * One header, two implementations:
+ *   libjmme_cuda.so   the product: hand-written sm_100a kernels (h264-jm-commentary_b200/csrc/)
+ *   libjmme_oracle.so the CPU oracle (oracle/), test infrastructure only
+ *
+ * Reference interface replaced: the mounted reference (/root/reference) holds only
+ * README.md:1-4 and exposes no interface.  JM itself reaches motion
+ * estimation through direct C calls; the entry points below carry the JM function each one
+ * stands in for (names recalled from the public JM distribution, [MEM] in SURVEY.md — they
+ * are NOT citations into /root/reference):
+ *
+ *   jmme_InitMotionSearchModule        Init_Motion_Search_Module / InitializeMotionSearch   (a1)
+ *   jmme_lambda_factor                 LAMBDA_FACTOR(lambda_motion)                         (a2)
+ *   jmme_set_reference                 UnifiedOneForthPix / getSubImagesLuma                (a12)
+ *   jmme_getSubImagesLuma              getSubImagesLuma (stand-alone leaf)                  (a12)
+ *   jmme_search_frame                  for every MB: PartitionMotionSearch -> BlockMotionSearch
+ *                                        -> SetupFastFullPelSearch / FastFullPelBlockMotionSearch
+ *                                        |  FullPelBlockMotionSearch -> SubPelBlockMotionSearch (a4-a10)
+ *   jmme_SetupFastFullPelSearch        SetupFastFullPelSearch (+SetupLargerBlocks), one MB  (a6)
+ *   jmme_FastFullPelBlockMotionSearch  FastFullPelBlockMotionSearch, one block              (a7)
+ *   jmme_FullPelBlockMotionSearch      FullPelBlockMotionSearch, one block                  (a8)
+ *   jmme_SubPelBlockMotionSearch       SubPelBlockMotionSearch, one block                   (a10)
+ *   jmme_SATD                          SATD / HadamardSAD4x4, batched                       (a11)
+ *
+ * The arithmetic conventions ("the frozen spec") are in DESIGN.md §2.  C89-includable.
+ */
+#ifndef JMME_H
+#define JMME_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JMME_ABI_VERSION     1
+#define JMME_BLOCKS_PER_MB   41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 */
+#define JMME_MAX_REFS        4
+#define JMME_MAX_SEARCH_RANGE 64
+#define JMME_MAX_GPUS        8
+
+/* error codes: 0 = OK, negative otherwise; the library never exits or aborts */
+#define JMME_OK               0
+#define JMME_ERR_PARAM       (-1)
+#define JMME_ERR_CUDA        (-2)
+#define JMME_ERR_NOMEM       (-3)
+#define JMME_ERR_UNSUPPORTED (-4)
+#define JMME_ERR_STATE       (-5)   /* e.g. search before every reference was set */
+#define JMME_ERR_NODEVICE    (-6)
+
+/* search_mode */
+#define JMME_SEARCH_FASTFULL 0      /* one window per MB/ref around the 16x16 predictor (a6,a7) */
+#define JMME_SEARCH_FULL     1      /* one window per block around its own predictor (a8)      */
+
+/* pred_policy: where the MV predictors (rate term + window centre) come from */
+#define JMME_PRED_ZERO       0      /* (0,0) everywhere                                         */
+#define JMME_PRED_PER_MB     1      /* caller passes one predictor per (ref, MB)                */
+#define JMME_PRED_PER_BLOCK  2      /* caller passes 41 predictors per (ref, MB)                */
+
+/* blocktypes 1..7 = 16x16,16x8,8x16,8x8,8x4,4x8,4x4 (JM blc_size); bit t of blocktype_mask */
+#define JMME_MASK_16x16      0x02
+#define JMME_MASK_ALL        0xFE
+
+typedef struct jmme_params {
+    int32_t width, height;       /* luma size; padded up to x16 by right/bottom replication      */
+    int32_t search_range;        /* R, 1..64; candidates = (2R+1)^2                              */
+    int32_t num_refs;            /* 1..JMME_MAX_REFS                                             */
+    int32_t blocktype_mask;      /* JMME_MASK_*                                                  */
+    int32_t lambda_factor;       /* Q16 lambda_motion; 0 = derive from qp and rdopt              */
+    int32_t qp;                  /* 0..51, used when lambda_factor == 0                          */
+    int32_t rdopt;               /* 0: (0,0) pre-test + 16x16 (0,0) bonus + integer lambda       */
+    int32_t use_hadamard;        /* sub-pel distortion: 1 = SATD, 0 = SAD                        */
+    int32_t subpel;              /* 0 = integer search only, 1 = half- then quarter-pel          */
+    int32_t search_mode;         /* JMME_SEARCH_*                                                */
+    int32_t pred_policy;         /* JMME_PRED_*                                                  */
+    int32_t satd_round;          /* 0: satd>>1 per 4x4 (Gen A), 1: (satd+1)>>1 (Gen B)           */
+    int32_t cost_domain;         /* 0: Gen A Q16 scale-down (only value implemented)             */
+    int32_t mb_row_begin;        /* stripe of MB rows searched by this context: [begin, end)     */
+    int32_t mb_row_end;          /* 0 = to the last row                                          */
+    int32_t n_gpus;              /* 0/1 = one device; >1 = split the stripe over device_ids      */
+    int32_t device_ids[JMME_MAX_GPUS];
+} jmme_params;
+
+/* One macroblock's result.  Block order: blocktype 1..7, raster order inside the MB
+ * (index bases 0,1,3,5,9,17,25).  mv in quarter-pel units.  cost = distortion + MV rate
+ * + reference rate of ref_idx.  Blocks whose blocktype is masked out: mv 0, cost INT32_MAX,
+ * ref_idx -1. */
+typedef struct jmme_mbresult {
+    int16_t mv[JMME_BLOCKS_PER_MB][2];
+    int32_t cost[JMME_BLOCKS_PER_MB];
+    int8_t  ref_idx[JMME_BLOCKS_PER_MB];
+    int8_t  reserved[3];
+} jmme_mbresult;
+
+typedef struct jmme_ctx jmme_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+void        jmme_default_params(jmme_params *p);
+int         jmme_create(jmme_ctx **out, const jmme_params *p);
+int         jmme_destroy(jmme_ctx *ctx);
+const char *jmme_strerror(int code);
+const char *jmme_last_error(const jmme_ctx *ctx);      /* detail of the last failure          */
+const char *jmme_backend(void);                        /* "cuda-sm_100a" or "cpu-oracle"      */
+int         jmme_abi_version(void);
+
+/* geometry helpers (valid after create) */
+int         jmme_mb_width(const jmme_ctx *ctx);
+int         jmme_mb_height(const jmme_ctx *ctx);
+int         jmme_pad(const jmme_ctx *ctx);             /* replication border of the ref planes */
+int         jmme_lambda_factor_of(const jmme_ctx *ctx);
+int         jmme_lambda_factor(int qp, int rdopt);     /* (int)(65536*lambda_motion + 0.5)     */
+
+/* ---- frame-level path (host buffers; copies happen inside the call) -------------------- */
+/* Upload reference `ref_idx`, replicate its borders and (when params.subpel) build the 16
+ * quarter-pel planes. */
+int jmme_set_reference(jmme_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
+
+/* Search every MB of the context's stripe against every reference.
+ *   pred         NULL for JMME_PRED_ZERO, else int16 [num_refs][mb_count][nb][2] in
+ *                quarter-pel units, nb = 1 (PER_MB) or 41 (PER_BLOCK); mb_count = whole frame
+ *   out          [mb_w*mb_h] (whole-frame indexing; only the stripe's rows are written)
+ *   out_per_ref  NULL or [num_refs][mb_w*mb_h]: per-reference winners, cost without reference
+ *                rate (JM all_mv / motion_cost) */
+int jmme_search_frame(jmme_ctx *ctx, const uint8_t *cur_luma, int stride,
+                      const int16_t *pred, jmme_mbresult *out, jmme_mbresult *out_per_ref);
+
+/* Copy one quarter-pel plane (xfrac,yfrac in 0..3) of reference ref_idx back to the host,
+ * padded size (W16+2*pad) x (H16+2*pad), for parity checks of (a12). */
+int jmme_get_subimage(jmme_ctx *ctx, int ref_idx, int xfrac, int yfrac,
+                      uint8_t *dst, int dst_stride);
+
+/* ---- device-resident variants (product library only; pointers are CUDA device pointers,
+ *      stream is a cudaStream_t passed as void*; asynchronous on that stream) -------------- */
+int jmme_set_reference_dev(jmme_ctx *ctx, int ref_idx, const void *d_luma, int stride, void *stream);
+int jmme_search_frame_dev(jmme_ctx *ctx, const void *d_cur_luma, int stride, const void *d_pred,
+                          void *d_out, void *d_out_per_ref, void *stream);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+long long jmme_launch_count(const jmme_ctx *ctx);
+
+/* ---- JM-named leaf entry points on plain arrays ----------------------------------------- */
+/* (a1) tables.  mvbits has 2*max_mvd+1 entries, index (v + max_mvd); refbits n_refbits;
+ * spiral_x/y (2R+1)^2 entries. Any pointer may be NULL. */
+int jmme_InitMotionSearchModule(int search_range, int max_mvd, int32_t *mvbits,
+                                int n_refbits, int32_t *refbits,
+                                int16_t *spiral_x, int16_t *spiral_y);
+
+/* (a12) 16 planes from one luma image; out[(yfrac*4+xfrac)] planes are contiguous, each
+ * (width+2*pad) x (height+2*pad) bytes; width/height must be multiples of 16. */
+int jmme_getSubImagesLuma(const uint8_t *luma, int width, int height, int stride, int pad,
+                          uint8_t *out_planes);
+
+/* (a11) n 4x4 difference blocks (raster, int16) -> n SATD values */
+int jmme_SATD(const int16_t *diff4x4, int n, int satd_round, int32_t *out);
+
+/* (a6) SAD surfaces of one MB: out[41][(2R+1)^2] in spiral order around centre (cx,cy)
+ * (integer pel), including the 16x16 (0,0) bonus when bonus != 0 (subtracted at MV (0,0)).
+ * ref_padded points at sample (0,0) of a plane with `pad` replicated pixels around it. */
+int jmme_SetupFastFullPelSearch(const uint8_t *cur_mb16x16, int cur_stride,
+                                const uint8_t *ref_padded, int ref_stride,
+                                int mb_x, int mb_y, int cx, int cy, int search_range,
+                                int bonus, int32_t *out_blocksad);
+
+/* (a7) argmin over one block's SAD surface with the MV rate term.  pretest00: test MV (0,0)
+ * first (JM !rdopt).  Returns the winning integer MV and cost. */
+int jmme_FastFullPelBlockMotionSearch(const int32_t *blocksad, int search_range,
+                                      int cx, int cy, int pred_x, int pred_y,
+                                      int lambda_factor, int pretest00,
+                                      int16_t *mv_x, int16_t *mv_y, int32_t *min_mcost);
+
+/* (a8) per-block full search.  block_x/block_y: luma position of the block, bw x bh size. */
+int jmme_FullPelBlockMotionSearch(const uint8_t *cur, int cur_stride,
+                                  const uint8_t *ref_padded, int ref_stride,
+                                  int block_x, int block_y, int bw, int bh,
+                                  int pred_x, int pred_y, int search_range,
+                                  int lambda_factor, int bonus,
+                                  int16_t *mv_x, int16_t *mv_y, int32_t *min_mcost);
+
+/* (a10) sub-pel refinement of one block.  planes: 16 padded planes as produced by
+ * jmme_getSubImagesLuma.  In: integer-pel MV*4 and its cost; out: quarter-pel MV and cost. */
+int jmme_SubPelBlockMotionSearch(const uint8_t *cur, int cur_stride,
+                                 const uint8_t *planes, int width, int height, int pad,
+                                 int block_x, int block_y, int bw, int bh,
+                                 int pred_x, int pred_y, int lambda_factor,
+                                 int use_hadamard, int satd_round, int bonus,
+                                 int16_t *mv_x, int16_t *mv_y, int32_t *min_mcost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JMME_H */

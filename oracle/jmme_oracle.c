@@ -1,0 +1,641 @@
+/*
+ * jmme_oracle.c — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * PARITY UNPINNED: the mounted reference (/root/reference) holds only README.md:1-4 — no JM
+ * sources, tests or golden vectors exist to pin this restatement against.
+ * What this file restates is therefore
+ *   [STD] the normative H.264 arithmetic (6-tap / bilinear luma interpolation §8.4.2.2.1,
+ *         se(v)/ue(v) code lengths), and
+ *   [MEM] the JM lencod encoder conventions recalled in SURVEY.md Appendix A (spiral scan,
+ *         strict-< tie-break, (0,0) pre-test, 16x16 bonus, Q16 lambda, SATD rounding),
+ *         frozen in DESIGN.md §2.
+ * Each function names the JM function (Gen A ‖ Gen B name) it follows;
+ * none of those files is present under /root/reference, so no file:line can be given.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library.  The product (libjmme_cuda.so) never links or calls it.
+ *
+ * Single-threaded, scalar, written for clarity.  Implements include/jmme.h.
+ */
+#include "jmme.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAX_MVD 4096                 /* |cand - pred| in quarter-pel units stays below this */
+#define MAX_PRED 2048                /* |pred| limit, quarter-pel                            */
+
+/* ---- block geometry (JM blc_size) -------------------------------------------- */
+static const int blc_w[8] = {0, 16, 16, 8, 8, 8, 4, 4};
+static const int blc_h[8] = {0, 16, 8, 16, 8, 4, 8, 4};
+static const int blk_base[8] = {0, 0, 1, 3, 5, 9, 17, 25};
+
+struct jmme_ctx {
+    jmme_params p;
+    int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor;
+    int n_planes;                    /* 16 with subpel, else 1 */
+    uint8_t *planes[JMME_MAX_REFS];  /* [n_planes] padded planes, contiguous */
+    int ref_set[JMME_MAX_REFS];
+    int32_t *mvbits;                 /* centred table, index v + MAX_MVD */
+    int16_t *spx, *spy;              /* spiral */
+    int ncand;
+    char err[256];
+};
+
+/* ---- (a1) Init_Motion_Search_Module ‖ InitializeMotionSearch ----------------------------- */
+static int se_bits(int v)            /* length of the signed Exp-Golomb code of v [STD 9.1] */
+{
+    int a = v < 0 ? -v : v, k = 0;
+    if (a == 0) return 1;
+    while ((1 << (k + 1)) <= a) k++;        /* k = floor(log2 |v|) */
+    return 2 * k + 3;
+}
+static int ue_bits(int r)            /* length of the unsigned Exp-Golomb code of r */
+{
+    int k = 0;
+    while ((1 << (k + 1)) <= r + 1) k++;
+    return 2 * k + 1;
+}
+static void build_spiral(int R, int16_t *x, int16_t *y)     /* SURVEY A.5 */
+{
+    int k = 0, l, i;
+    x[k] = 0; y[k] = 0; k++;
+    for (l = 1; l <= R; l++) {
+        for (i = -l + 1; i < l; i++) {
+            x[k] = (int16_t)i;  y[k] = (int16_t)-l; k++;
+            x[k] = (int16_t)i;  y[k] = (int16_t)l;  k++;
+        }
+        for (i = -l; i <= l; i++) {
+            x[k] = (int16_t)-l; y[k] = (int16_t)i;  k++;
+            x[k] = (int16_t)l;  y[k] = (int16_t)i;  k++;
+        }
+    }
+}
+
+int jmme_InitMotionSearchModule(int R, int max_mvd, int32_t *mvbits, int n_refbits,
+                                int32_t *refbits, int16_t *sx, int16_t *sy)
+{
+    int v;
+    if (R < 0 || max_mvd < 0 || n_refbits < 0) return JMME_ERR_PARAM;
+    if (mvbits) for (v = -max_mvd; v <= max_mvd; v++) mvbits[v + max_mvd] = se_bits(v);
+    if (refbits) for (v = 0; v < n_refbits; v++) refbits[v] = ue_bits(v);
+    if (sx && sy) build_spiral(R, sx, sy);
+    return JMME_OK;
+}
+
+/* ---- (a2) LAMBDA_FACTOR / WEIGHTED_COST / MV_COST / REF_COST ----------------------------- */
+static const int QP2QUANT[40] = {1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 6, 6, 7, 8, 9,
+                                 10, 11, 13, 14, 16, 18, 20, 23, 25, 29, 32, 36, 40, 45, 51, 57,
+                                 64, 72, 81, 91};
+static double lambda_motion(int qp, int rdopt)
+{
+    int q = qp - 12;
+    if (q < 0) q = 0;
+    if (q > 39) q = 39;
+    if (rdopt) return sqrt(0.85 * pow(2.0, (double)q / 3.0));
+    return (double)QP2QUANT[q];
+}
+int jmme_lambda_factor(int qp, int rdopt) { return (int)(65536.0 * lambda_motion(qp, rdopt) + 0.5); }
+
+static int weighted_cost(int f, int bits) { return (int)(((int64_t)f * bits) >> 16); }
+
+/* MV_COST(f,s,cx,cy,px,py) = WEIGHTED_COST(f, mvbits[(cx<<s)-px] + mvbits[(cy<<s)-py]) is written
+ * out at its call sites below (s = 2 for integer candidates, 0 for sub-pel ones). */
+static int ref_cost(const jmme_ctx *c, int ref)
+{
+    if (c->p.rdopt) return weighted_cost(c->lambda_factor, ue_bits(ref));
+    /* (int)(2*lambda*min(ref,1)); lambda is an integer when !rdopt */
+    return ref ? (int)((2 * (int64_t)c->lambda_factor) >> 16) : 0;
+}
+
+/* ---- (a12) UnifiedOneForthPix ‖ getSubImagesLuma [STD 8.4.2.2.1] ------------------------- */
+static int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* Builds n_planes (1 or 16) planes of (w+2pad) x (h+2pad); plane index yfrac*4+xfrac.
+ * Integer samples are edge-replicated without bound (a9: UMV clamp). */
+static int build_planes(const uint8_t *luma, int w_in, int h_in, int stride, int w, int h, int pad,
+                        int n_planes, uint8_t *out)
+{
+    int ps = w + 2 * pad, ph = h + 2 * pad, x, y;
+    size_t psz = (size_t)ps * ph;
+    /* working arrays carry a 3-sample apron so that every tap is in range */
+    int ap = 3, as = ps + 2 * ap, ah = ph + 2 * ap;
+    int *G = (int *)malloc(sizeof(int) * (size_t)as * ah);   /* integer samples            */
+    int *B1 = NULL, *H1 = NULL, *J1 = NULL;
+    uint8_t *Pb, *Ph, *Pj;
+    if (!G) return JMME_ERR_NOMEM;
+#define AT(A, xx, yy) A[(size_t)((yy) + ap) * as + ((xx) + ap)]
+    for (y = -ap; y < ph + ap; y++)
+        for (x = -ap; x < ps + ap; x++) {
+            int sx = clampi(x - pad, 0, w_in - 1), sy = clampi(y - pad, 0, h_in - 1);
+            AT(G, x, y) = luma[(size_t)sy * stride + sx];
+        }
+    for (y = 0; y < ph; y++)
+        for (x = 0; x < ps; x++) out[(size_t)y * ps + x] = (uint8_t)AT(G, x, y);
+    if (n_planes == 1) { free(G); return JMME_OK; }
+
+    B1 = (int *)malloc(sizeof(int) * (size_t)as * ah);       /* unrounded horizontal half  */
+    H1 = (int *)malloc(sizeof(int) * (size_t)as * ah);       /* unrounded vertical half    */
+    J1 = (int *)malloc(sizeof(int) * (size_t)as * ah);       /* unrounded centre           */
+    if (!B1 || !H1 || !J1) { free(G); free(B1); free(H1); free(J1); return JMME_ERR_NOMEM; }
+    /* samples beyond the apron are replicas of the border column/row, so clamping the tap
+     * coordinate to the apron is exact */
+#define GC(xx, yy) AT(G, clampi(xx, -ap, ps + ap - 1), clampi(yy, -ap, ph + ap - 1))
+    for (y = -ap; y < ph + ap; y++)
+        for (x = -ap; x < ps + ap; x++) {
+            AT(B1, x, y) = GC(x - 2, y) - 5 * GC(x - 1, y) + 20 * GC(x, y) + 20 * GC(x + 1, y)
+                           - 5 * GC(x + 2, y) + GC(x + 3, y);
+            AT(H1, x, y) = GC(x, y - 2) - 5 * GC(x, y - 1) + 20 * GC(x, y) + 20 * GC(x, y + 1)
+                           - 5 * GC(x, y + 2) + GC(x, y + 3);
+        }
+#define B1C(xx, yy) AT(B1, xx, clampi(yy, -ap, ph + ap - 1))
+    for (y = 0; y < ph + 1; y++)
+        for (x = 0; x < ps + 1; x++)
+            AT(J1, x, y) = B1C(x, y - 2) - 5 * B1C(x, y - 1) + 20 * B1C(x, y) + 20 * B1C(x, y + 1)
+                           - 5 * B1C(x, y + 2) + B1C(x, y + 3);
+#define PL(xf, yf) (out + psz * (size_t)((yf) * 4 + (xf)))
+#define Gs(xx, yy) AT(G, xx, yy)
+#define bs(xx, yy) clip255((AT(B1, xx, yy) + 16) >> 5)
+#define hs(xx, yy) clip255((AT(H1, xx, yy) + 16) >> 5)
+#define js(xx, yy) clip255((AT(J1, xx, yy) + 512) >> 10)
+    Pb = PL(2, 0); Ph = PL(0, 2); Pj = PL(2, 2);
+    for (y = 0; y < ph; y++)
+        for (x = 0; x < ps; x++) {
+            size_t o = (size_t)y * ps + x;
+            int g = Gs(x, y), b = bs(x, y), h = hs(x, y), j = js(x, y);
+            int gr = Gs(x + 1, y), gd = Gs(x, y + 1);       /* H and M of the standard       */
+            int m = hs(x + 1, y), s = bs(x, y + 1);
+            Pb[o] = (uint8_t)b; Ph[o] = (uint8_t)h; Pj[o] = (uint8_t)j;
+            PL(1, 0)[o] = (uint8_t)((g + b + 1) >> 1);      /* a */
+            PL(3, 0)[o] = (uint8_t)((gr + b + 1) >> 1);     /* c */
+            PL(0, 1)[o] = (uint8_t)((g + h + 1) >> 1);      /* d */
+            PL(0, 3)[o] = (uint8_t)((gd + h + 1) >> 1);     /* n */
+            PL(2, 1)[o] = (uint8_t)((b + j + 1) >> 1);      /* f */
+            PL(2, 3)[o] = (uint8_t)((j + s + 1) >> 1);      /* q */
+            PL(1, 2)[o] = (uint8_t)((h + j + 1) >> 1);      /* i */
+            PL(3, 2)[o] = (uint8_t)((j + m + 1) >> 1);      /* k */
+            PL(1, 1)[o] = (uint8_t)((b + h + 1) >> 1);      /* e */
+            PL(3, 1)[o] = (uint8_t)((b + m + 1) >> 1);      /* g */
+            PL(1, 3)[o] = (uint8_t)((h + s + 1) >> 1);      /* p */
+            PL(3, 3)[o] = (uint8_t)((m + s + 1) >> 1);      /* r */
+        }
+    free(G); free(B1); free(H1); free(J1);
+    return JMME_OK;
+}
+
+int jmme_getSubImagesLuma(const uint8_t *luma, int width, int height, int stride, int pad,
+                          uint8_t *out_planes)
+{
+    if (!luma || !out_planes || width <= 0 || height <= 0 || (width & 15) || (height & 15) ||
+        pad < 0 || stride < width)
+        return JMME_ERR_PARAM;
+    return build_planes(luma, width, height, stride, width, height, pad, 16, out_planes);
+}
+
+/* ---- (a11) SATD ‖ HadamardSAD4x4 --------------------------------------------------------- */
+static int satd4x4(const int *d, int satd_round)
+{
+    int m[16], t[16], i, s = 0;
+    for (i = 0; i < 4; i++) {                       /* rows */
+        int a = d[4 * i], b = d[4 * i + 1], c = d[4 * i + 2], e = d[4 * i + 3];
+        int s0 = a + e, s1 = b + c, d0 = a - e, d1 = b - c;
+        t[4 * i] = s0 + s1; t[4 * i + 1] = d0 + d1; t[4 * i + 2] = s0 - s1; t[4 * i + 3] = d0 - d1;
+    }
+    for (i = 0; i < 4; i++) {                       /* columns */
+        int a = t[i], b = t[4 + i], c = t[8 + i], e = t[12 + i];
+        int s0 = a + e, s1 = b + c, d0 = a - e, d1 = b - c;
+        m[i] = s0 + s1; m[4 + i] = d0 + d1; m[8 + i] = s0 - s1; m[12 + i] = d0 - d1;
+    }
+    for (i = 0; i < 16; i++) s += m[i] < 0 ? -m[i] : m[i];
+    return satd_round ? (s + 1) >> 1 : s >> 1;
+}
+int jmme_SATD(const int16_t *diff, int n, int satd_round, int32_t *out)
+{
+    int i, k, d[16];
+    if (!diff || !out || n < 0) return JMME_ERR_PARAM;
+    for (i = 0; i < n; i++) {
+        for (k = 0; k < 16; k++) d[k] = diff[16 * i + k];
+        out[i] = satd4x4(d, satd_round);
+    }
+    return JMME_OK;
+}
+
+/* ---- context ----------------------------------------------------------------------------- */
+static int set_err(jmme_ctx *c, int code, const char *msg)
+{
+    if (c) snprintf(c->err, sizeof c->err, "%s", msg);
+    return code;
+}
+void jmme_default_params(jmme_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->search_range = 32; p->num_refs = 1; p->blocktype_mask = JMME_MASK_ALL;
+    p->qp = 28; p->rdopt = 0; p->use_hadamard = 1; p->subpel = 0;
+    p->search_mode = JMME_SEARCH_FASTFULL; p->pred_policy = JMME_PRED_ZERO;
+}
+static int pad_for(int R) { return (2 * R + 16 + 15) & ~15; }
+
+int jmme_create(jmme_ctx **out, const jmme_params *p)
+{
+    jmme_ctx *c;
+    int v;
+    if (!out || !p) return JMME_ERR_PARAM;
+    *out = NULL;
+    if (p->width <= 0 || p->height <= 0 || p->search_range < 1 ||
+        p->search_range > JMME_MAX_SEARCH_RANGE || p->num_refs < 1 || p->num_refs > JMME_MAX_REFS ||
+        (p->blocktype_mask & ~JMME_MASK_ALL) || !(p->blocktype_mask & JMME_MASK_ALL) ||
+        p->qp < 0 || p->qp > 51 || p->lambda_factor < 0 ||
+        p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 2 ||
+        p->satd_round < 0 || p->satd_round > 1)
+        return JMME_ERR_PARAM;
+    if (p->cost_domain != 0) return JMME_ERR_UNSUPPORTED;
+    c = (jmme_ctx *)calloc(1, sizeof *c);
+    if (!c) return JMME_ERR_NOMEM;
+    c->p = *p;
+    c->w16 = (p->width + 15) & ~15; c->h16 = (p->height + 15) & ~15;
+    c->mb_w = c->w16 / 16; c->mb_h = c->h16 / 16;
+    if (c->p.mb_row_end == 0) c->p.mb_row_end = c->mb_h;
+    if (c->p.mb_row_begin < 0 || c->p.mb_row_end > c->mb_h || c->p.mb_row_begin >= c->p.mb_row_end) {
+        free(c); return JMME_ERR_PARAM;
+    }
+    c->pad = pad_for(p->search_range);
+    c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
+    c->lambda_factor = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
+    if (c->lambda_factor > (96 << 16)) { free(c); return JMME_ERR_PARAM; }
+    c->n_planes = p->subpel ? 16 : 1;
+    c->ncand = (2 * p->search_range + 1) * (2 * p->search_range + 1);
+    c->mvbits = (int32_t *)malloc(sizeof(int32_t) * (2 * MAX_MVD + 1));
+    c->spx = (int16_t *)malloc(sizeof(int16_t) * c->ncand);
+    c->spy = (int16_t *)malloc(sizeof(int16_t) * c->ncand);
+    if (!c->mvbits || !c->spx || !c->spy) { jmme_destroy(c); return JMME_ERR_NOMEM; }
+    for (v = -MAX_MVD; v <= MAX_MVD; v++) c->mvbits[v + MAX_MVD] = se_bits(v);
+    build_spiral(p->search_range, c->spx, c->spy);
+    *out = c;
+    return JMME_OK;
+}
+int jmme_destroy(jmme_ctx *c)
+{
+    int r;
+    if (!c) return JMME_OK;
+    for (r = 0; r < JMME_MAX_REFS; r++) free(c->planes[r]);
+    free(c->mvbits); free(c->spx); free(c->spy); free(c);
+    return JMME_OK;
+}
+const char *jmme_strerror(int code)
+{
+    switch (code) {
+    case JMME_OK: return "ok";
+    case JMME_ERR_PARAM: return "invalid parameter";
+    case JMME_ERR_CUDA: return "CUDA error";
+    case JMME_ERR_NOMEM: return "out of memory";
+    case JMME_ERR_UNSUPPORTED: return "unsupported configuration";
+    case JMME_ERR_STATE: return "invalid state (reference not set?)";
+    case JMME_ERR_NODEVICE: return "no CUDA device";
+    default: return "unknown error";
+    }
+}
+const char *jmme_last_error(const jmme_ctx *c) { return c ? c->err : ""; }
+const char *jmme_backend(void) { return "cpu-oracle"; }
+int jmme_abi_version(void) { return JMME_ABI_VERSION; }
+int jmme_mb_width(const jmme_ctx *c) { return c ? c->mb_w : 0; }
+int jmme_mb_height(const jmme_ctx *c) { return c ? c->mb_h : 0; }
+int jmme_pad(const jmme_ctx *c) { return c ? c->pad : 0; }
+int jmme_lambda_factor_of(const jmme_ctx *c) { return c ? c->lambda_factor : 0; }
+long long jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }
+
+int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
+{
+    size_t sz;
+    int rc;
+    if (!c || !luma || r < 0 || r >= c->p.num_refs || stride < c->p.width) return JMME_ERR_PARAM;
+    sz = (size_t)c->pstride * c->pheight * c->n_planes;
+    if (!c->planes[r]) c->planes[r] = (uint8_t *)malloc(sz);
+    if (!c->planes[r]) return set_err(c, JMME_ERR_NOMEM, "plane allocation failed");
+    rc = build_planes(luma, c->p.width, c->p.height, stride, c->w16, c->h16, c->pad, c->n_planes,
+                      c->planes[r]);
+    if (rc == JMME_OK) c->ref_set[r] = 1;
+    return rc;
+}
+int jmme_get_subimage(jmme_ctx *c, int r, int xf, int yf, uint8_t *dst, int dst_stride)
+{
+    int y;
+    const uint8_t *src;
+    if (!c || !dst || r < 0 || r >= c->p.num_refs || xf < 0 || xf > 3 || yf < 0 || yf > 3 ||
+        dst_stride < c->pstride)
+        return JMME_ERR_PARAM;
+    if (!c->ref_set[r]) return JMME_ERR_STATE;
+    if ((xf || yf) && c->n_planes != 16) return JMME_ERR_STATE;
+    src = c->planes[r] + (size_t)c->pstride * c->pheight * (yf * 4 + xf);
+    for (y = 0; y < c->pheight; y++) memcpy(dst + (size_t)y * dst_stride, src + (size_t)y * c->pstride, c->pstride);
+    return JMME_OK;
+}
+int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d, int s, void *st)
+{ (void)r; (void)d; (void)s; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
+int jmme_search_frame_dev(jmme_ctx *c, const void *a, int s, const void *b, void *o, void *o2, void *st)
+{ (void)a; (void)s; (void)b; (void)o; (void)o2; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
+
+/* ---- distortion -------------------------------------------------------------------------- */
+/* padded-plane sample fetch; (x,y) relative to sample (0,0) of the unpadded picture */
+static const uint8_t *plane_at(const uint8_t *base, int pstride, int pad, int x, int y)
+{
+    return base + (size_t)(y + pad) * pstride + (x + pad);
+}
+static int sad_block(const uint8_t *cur, int cs, const uint8_t *ref, int rs, int bw, int bh)
+{
+    int x, y, s = 0;
+    for (y = 0; y < bh; y++)
+        for (x = 0; x < bw; x++) {
+            int d = (int)cur[y * cs + x] - (int)ref[y * rs + x];
+            s += d < 0 ? -d : d;
+        }
+    return s;
+}
+/* distortion of a block at quarter-pel MV (qx,qy): SAD, or sum of 4x4 SATDs (a10/a11) */
+static int subpel_dist(const uint8_t *cur, int cs, const uint8_t *planes, int pstride, int pheight,
+                       int pad, int bx, int by, int bw, int bh, int qx, int qy, int hadamard,
+                       int satd_round)
+{
+    const uint8_t *pl = planes + (size_t)pstride * pheight * ((qy & 3) * 4 + (qx & 3));
+    const uint8_t *ref = plane_at(pl, pstride, pad, bx + (qx >> 2), by + (qy >> 2));
+    int x0, y0, x, y, s = 0, d[16];
+    if (!hadamard) return sad_block(cur, cs, ref, pstride, bw, bh);
+    for (y0 = 0; y0 < bh; y0 += 4)
+        for (x0 = 0; x0 < bw; x0 += 4) {
+            for (y = 0; y < 4; y++)
+                for (x = 0; x < 4; x++)
+                    d[4 * y + x] = (int)cur[(y0 + y) * cs + x0 + x] - (int)ref[(y0 + y) * pstride + x0 + x];
+            s += satd4x4(d, satd_round);
+        }
+    return s;
+}
+
+/* ---- (a6) SetupFastFullPelSearch + SetupLargerBlocks ------------------------------------- */
+/* 4x4 SADs at every spiral position, then 4x8/8x4 <- 4x4, 8x8 <- 8x4, 16x8/8x16 <- 8x8,
+ * 16x16 <- 16x8.  out[41][ncand]. */
+static void setup_fastfull(const uint8_t *cur, int cs, const uint8_t *ref00, int rs, int mbx, int mby,
+                           int cx, int cy, int ncand, const int16_t *spx, const int16_t *spy,
+                           int bonus, int32_t *out)
+{
+    int pos, b, i, j;
+    for (pos = 0; pos < ncand; pos++) {
+        int mx = cx + spx[pos], my = cy + spy[pos];
+        const uint8_t *r = ref00 + (size_t)(16 * mby + my) * rs + (16 * mbx + mx);
+        int s44[4][4], s84[4][2], s48[2][4], s88[2][2];
+        for (j = 0; j < 4; j++)
+            for (i = 0; i < 4; i++)
+                s44[j][i] = sad_block(cur + 4 * j * cs + 4 * i, cs, r + 4 * j * rs + 4 * i, rs, 4, 4);
+        for (j = 0; j < 4; j++) for (i = 0; i < 2; i++) s84[j][i] = s44[j][2 * i] + s44[j][2 * i + 1];
+        for (j = 0; j < 2; j++) for (i = 0; i < 4; i++) s48[j][i] = s44[2 * j][i] + s44[2 * j + 1][i];
+        for (j = 0; j < 2; j++) for (i = 0; i < 2; i++) s88[j][i] = s84[2 * j][i] + s84[2 * j + 1][i];
+#define O(blk) out[(size_t)(blk) * ncand + pos]
+        for (j = 0; j < 4; j++) for (i = 0; i < 4; i++) O(blk_base[7] + 4 * j + i) = s44[j][i];
+        for (j = 0; j < 2; j++) for (i = 0; i < 4; i++) O(blk_base[6] + 4 * j + i) = s48[j][i];
+        for (j = 0; j < 4; j++) for (i = 0; i < 2; i++) O(blk_base[5] + 2 * j + i) = s84[j][i];
+        for (j = 0; j < 2; j++) for (i = 0; i < 2; i++) O(blk_base[4] + 2 * j + i) = s88[j][i];
+        O(blk_base[3] + 0) = s88[0][0] + s88[1][0];           /* 8x16 left, right */
+        O(blk_base[3] + 1) = s88[0][1] + s88[1][1];
+        O(blk_base[2] + 0) = s88[0][0] + s88[0][1];           /* 16x8 top, bottom */
+        O(blk_base[2] + 1) = s88[1][0] + s88[1][1];
+        b = O(blk_base[2]) + O(blk_base[2] + 1);
+        if (mx == 0 && my == 0) b -= bonus;                   /* 16x16 (0,0) bias, SURVEY A.6 */
+        O(0) = b;
+#undef O
+    }
+}
+int jmme_SetupFastFullPelSearch(const uint8_t *cur, int cs, const uint8_t *ref, int rs, int mbx,
+                                int mby, int cx, int cy, int R, int bonus, int32_t *out)
+{
+    int n = (2 * R + 1) * (2 * R + 1);
+    int16_t *sx, *sy;
+    if (!cur || !ref || !out || R < 1 || R > JMME_MAX_SEARCH_RANGE) return JMME_ERR_PARAM;
+    sx = (int16_t *)malloc(2 * n); sy = (int16_t *)malloc(2 * n);
+    if (!sx || !sy) { free(sx); free(sy); return JMME_ERR_NOMEM; }
+    build_spiral(R, sx, sy);
+    setup_fastfull(cur, cs, ref, rs, mbx, mby, cx, cy, n, sx, sy, bonus, out);
+    free(sx); free(sy);
+    return JMME_OK;
+}
+
+/* ---- (a7) FastFullPelBlockMotionSearch ---------------------------------------------------- */
+static void fastfull_block(const int32_t *sad, int ncand, const int16_t *spx, const int16_t *spy,
+                           const int32_t *mvbits, int f, int cx, int cy, int px, int py, int pretest,
+                           int *best_pos, int *best_cost)
+{
+    int pos, min = INT_MAX, bp = 0;
+#define MVC(mx, my) weighted_cost(f, mvbits[4 * (mx) - px + MAX_MVD] + mvbits[4 * (my) - py + MAX_MVD])
+    if (pretest) {                                  /* MV (0,0) first when !rdopt */
+        for (pos = 0; pos < ncand; pos++)
+            if (cx + spx[pos] == 0 && cy + spy[pos] == 0) break;
+        if (pos < ncand) { min = sad[pos] + MVC(0, 0); bp = pos; }
+    }
+    for (pos = 0; pos < ncand; pos++) {
+        int c = sad[pos] + MVC(cx + spx[pos], cy + spy[pos]);
+        if (c < min) { min = c; bp = pos; }
+    }
+#undef MVC
+    *best_pos = bp; *best_cost = min;
+}
+int jmme_FastFullPelBlockMotionSearch(const int32_t *sad, int R, int cx, int cy, int px, int py, int f,
+                                      int pretest, int16_t *mvx, int16_t *mvy, int32_t *cost)
+{
+    int n = (2 * R + 1) * (2 * R + 1), bp, bc, v;
+    int16_t *sx, *sy;
+    int32_t *mvb;
+    if (!sad || !mvx || !mvy || !cost || R < 1 || R > JMME_MAX_SEARCH_RANGE) return JMME_ERR_PARAM;
+    if (abs(px) > MAX_PRED || abs(py) > MAX_PRED) return JMME_ERR_PARAM;
+    sx = (int16_t *)malloc(2 * n); sy = (int16_t *)malloc(2 * n);
+    mvb = (int32_t *)malloc(sizeof(int32_t) * (2 * MAX_MVD + 1));
+    if (!sx || !sy || !mvb) { free(sx); free(sy); free(mvb); return JMME_ERR_NOMEM; }
+    for (v = -MAX_MVD; v <= MAX_MVD; v++) mvb[v + MAX_MVD] = se_bits(v);
+    build_spiral(R, sx, sy);
+    fastfull_block(sad, n, sx, sy, mvb, f, cx, cy, px, py, pretest, &bp, &bc);
+    *mvx = (int16_t)(cx + sx[bp]); *mvy = (int16_t)(cy + sy[bp]); *cost = bc;
+    free(sx); free(sy); free(mvb);
+    return JMME_OK;
+}
+
+/* ---- (a8) FullPelBlockMotionSearch -------------------------------------------------------- */
+static void full_block(const uint8_t *cur, int cs, const uint8_t *ref00, int rs, int bx, int by, int bw,
+                       int bh, int cx, int cy, int px, int py, int ncand, const int16_t *spx,
+                       const int16_t *spy, const int32_t *mvbits, int f, int bonus, int *bmx, int *bmy,
+                       int *bcost)
+{
+    int pos, min = INT_MAX, mx0 = cx, my0 = cy;
+    for (pos = 0; pos < ncand; pos++) {
+        int mx = cx + spx[pos], my = cy + spy[pos];
+        int c = weighted_cost(f, mvbits[4 * mx - px + MAX_MVD] + mvbits[4 * my - py + MAX_MVD]);
+        c += sad_block(cur + (size_t)by * cs + bx, cs, ref00 + (size_t)(by + my) * rs + (bx + mx), rs, bw, bh);
+        if (mx == 0 && my == 0) c -= bonus;
+        if (c < min) { min = c; mx0 = mx; my0 = my; }
+    }
+    *bmx = mx0; *bmy = my0; *bcost = min;
+}
+int jmme_FullPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *ref, int rs, int bx, int by,
+                                  int bw, int bh, int px, int py, int R, int f, int bonus, int16_t *mvx,
+                                  int16_t *mvy, int32_t *cost)
+{
+    int n = (2 * R + 1) * (2 * R + 1), v, mx, my, mc, cx, cy;
+    int16_t *sx, *sy;
+    int32_t *mvb;
+    if (!cur || !ref || !mvx || !mvy || !cost || R < 1 || R > JMME_MAX_SEARCH_RANGE) return JMME_ERR_PARAM;
+    if (abs(px) > MAX_PRED || abs(py) > MAX_PRED) return JMME_ERR_PARAM;
+    sx = (int16_t *)malloc(2 * n); sy = (int16_t *)malloc(2 * n);
+    mvb = (int32_t *)malloc(sizeof(int32_t) * (2 * MAX_MVD + 1));
+    if (!sx || !sy || !mvb) { free(sx); free(sy); free(mvb); return JMME_ERR_NOMEM; }
+    for (v = -MAX_MVD; v <= MAX_MVD; v++) mvb[v + MAX_MVD] = se_bits(v);
+    build_spiral(R, sx, sy);
+    cx = clampi(px / 4, -R, R); cy = clampi(py / 4, -R, R);
+    full_block(cur, cs, ref, rs, bx, by, bw, bh, cx, cy, px, py, n, sx, sy, mvb, f, bonus, &mx, &my, &mc);
+    *mvx = (int16_t)mx; *mvy = (int16_t)my; *cost = mc;
+    free(sx); free(sy); free(mvb);
+    return JMME_OK;
+}
+
+/* ---- (a10) SubPelBlockMotionSearch -------------------------------------------------------- */
+/* In: integer MV (quarter-pel units, multiple of 4) and its integer-search cost.
+ * Half-pel: spiral positions (0 when hadamard else 1)..8, step 2; quarter-pel: positions 1..8,
+ * step 1, around the half-pel winner.  Strict <.  No early termination (result-neutral in JM
+ * except in combination with the (0,0) bonus; the frozen spec is the plain argmin). */
+static void subpel_block(const uint8_t *cur, int cs, const uint8_t *planes, int pstride, int pheight,
+                         int pad, int bx, int by, int bw, int bh, int px, int py, const int32_t *mvbits,
+                         int f, int hadamard, int satd_round, int bonus, const int16_t *spx,
+                         const int16_t *spy, int *mvx, int *mvy, int *cost)
+{
+    int pos, step, bmx = *mvx, bmy = *mvy, min = hadamard ? INT_MAX : *cost;
+    for (step = 2; step >= 1; step--) {
+        int ox = bmx, oy = bmy, best = 0;
+        for (pos = (step == 2 && hadamard) ? 0 : 1; pos < 9; pos++) {
+            int qx = ox + step * spx[pos], qy = oy + step * spy[pos];
+            int c = weighted_cost(f, mvbits[qx - px + MAX_MVD] + mvbits[qy - py + MAX_MVD]);
+            c += subpel_dist(cur + (size_t)by * cs + bx, cs, planes, pstride, pheight, pad, bx, by, bw, bh,
+                             qx, qy, hadamard, satd_round);
+            if (qx == 0 && qy == 0) c -= bonus;
+            if (c < min) { min = c; best = pos; }
+        }
+        bmx = ox + step * spx[best]; bmy = oy + step * spy[best];
+    }
+    *mvx = bmx; *mvy = bmy; *cost = min;
+}
+int jmme_SubPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *planes, int width, int height,
+                                 int pad, int bx, int by, int bw, int bh, int px, int py, int f,
+                                 int hadamard, int satd_round, int bonus, int16_t *mvx, int16_t *mvy,
+                                 int32_t *cost)
+{
+    int16_t sx[9], sy[9];
+    int32_t *mvb;
+    int v, x, y, c;
+    if (!cur || !planes || !mvx || !mvy || !cost) return JMME_ERR_PARAM;
+    if (abs(px) > MAX_PRED || abs(py) > MAX_PRED) return JMME_ERR_PARAM;
+    mvb = (int32_t *)malloc(sizeof(int32_t) * (2 * MAX_MVD + 1));
+    if (!mvb) return JMME_ERR_NOMEM;
+    for (v = -MAX_MVD; v <= MAX_MVD; v++) mvb[v + MAX_MVD] = se_bits(v);
+    build_spiral(1, sx, sy);
+    x = *mvx; y = *mvy; c = *cost;
+    subpel_block(cur, cs, planes, width + 2 * pad, height + 2 * pad, pad, bx, by, bw, bh, px, py, mvb, f,
+                 hadamard, satd_round, bonus, sx, sy, &x, &y, &c);
+    *mvx = (int16_t)x; *mvy = (int16_t)y; *cost = c;
+    free(mvb);
+    return JMME_OK;
+}
+
+/* ---- (a4,a5) PartitionMotionSearch / BlockMotionSearch over a frame ----------------------- */
+int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int16_t *pred,
+                      jmme_mbresult *out, jmme_mbresult *out_per_ref)
+{
+    int R, mbx, mby, r, t, x, y, rc = JMME_OK;
+    int nmb, npb, bonus_base;
+    uint8_t *cur;                    /* current picture padded to x16 by replication */
+    int32_t *bsad = NULL;
+    if (!c || !cur_in || !out || stride < c->p.width) return JMME_ERR_PARAM;
+    if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return set_err(c, JMME_ERR_PARAM, "pred required");
+    for (r = 0; r < c->p.num_refs; r++)
+        if (!c->ref_set[r]) return set_err(c, JMME_ERR_STATE, "reference not set");
+    R = c->p.search_range; nmb = c->mb_w * c->mb_h;
+    npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
+    if (pred) {
+        size_t i, n = (size_t)c->p.num_refs * nmb * npb * 2;
+        if (c->p.pred_policy != JMME_PRED_ZERO)
+            for (i = 0; i < n; i++)
+                if (pred[i] > MAX_PRED || pred[i] < -MAX_PRED) return set_err(c, JMME_ERR_PARAM, "pred out of range");
+    }
+    cur = (uint8_t *)malloc((size_t)c->w16 * c->h16);
+    if (c->p.search_mode == JMME_SEARCH_FASTFULL)
+        bsad = (int32_t *)malloc(sizeof(int32_t) * JMME_BLOCKS_PER_MB * (size_t)c->ncand);
+    if (!cur || (c->p.search_mode == JMME_SEARCH_FASTFULL && !bsad)) { free(cur); free(bsad); return JMME_ERR_NOMEM; }
+    for (y = 0; y < c->h16; y++)
+        for (x = 0; x < c->w16; x++)
+            cur[(size_t)y * c->w16 + x] = cur_in[(size_t)clampi(y, 0, c->p.height - 1) * stride + clampi(x, 0, c->p.width - 1)];
+    bonus_base = c->p.rdopt ? 0 : weighted_cost(c->lambda_factor, 16);
+
+    for (mby = c->p.mb_row_begin; mby < c->p.mb_row_end; mby++)
+        for (mbx = 0; mbx < c->mb_w; mbx++) {
+            int mb = mby * c->mb_w + mbx, b;
+            jmme_mbresult *o = &out[mb];
+            for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
+                o->mv[b][0] = o->mv[b][1] = 0; o->cost[b] = INT_MAX; o->ref_idx[b] = -1;
+            }
+            memset(o->reserved, 0, sizeof o->reserved);
+            for (r = 0; r < c->p.num_refs; r++) {
+                const uint8_t *pl0 = c->planes[r];               /* integer plane */
+                const uint8_t *ref00 = plane_at(pl0, c->pstride, c->pad, 0, 0);
+                const int16_t *pr = pred ? pred + ((size_t)r * nmb + mb) * npb * 2 : NULL;
+                int bonus = r == 0 ? bonus_base : 0;
+                jmme_mbresult *opr = out_per_ref ? &out_per_ref[(size_t)r * nmb + mb] : NULL;
+                int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
+                int cx = clampi(p16x / 4, -R, R), cy = clampi(p16y / 4, -R, R);
+                if (opr) {
+                    for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
+                        opr->mv[b][0] = opr->mv[b][1] = 0; opr->cost[b] = INT_MAX; opr->ref_idx[b] = -1;
+                    }
+                    memset(opr->reserved, 0, sizeof opr->reserved);
+                }
+                if (c->p.search_mode == JMME_SEARCH_FASTFULL)
+                    setup_fastfull(cur + (size_t)16 * mby * c->w16 + 16 * mbx, c->w16, ref00, c->pstride, mbx,
+                                   mby, cx, cy, c->ncand, c->spx, c->spy, bonus, bsad);
+                for (t = 1; t <= 7; t++) {
+                    int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh, j, i;
+                    if (!(c->p.blocktype_mask & (1 << t))) continue;
+                    for (j = 0; j < nby; j++)
+                        for (i = 0; i < nbx; i++) {
+                            int blk = blk_base[t] + j * nbx + i;
+                            int px = pr ? pr[(npb == 1 ? 0 : blk) * 2] : 0;
+                            int py = pr ? pr[(npb == 1 ? 0 : blk) * 2 + 1] : 0;
+                            int bx = 16 * mbx + i * bw, by = 16 * mby + j * bh;
+                            int mvx, mvy, cost, total;
+                            if (c->p.search_mode == JMME_SEARCH_FASTFULL) {
+                                int bp;
+                                fastfull_block(bsad + (size_t)blk * c->ncand, c->ncand, c->spx, c->spy, c->mvbits,
+                                               c->lambda_factor, cx, cy, px, py, !c->p.rdopt, &bp, &cost);
+                                mvx = cx + c->spx[bp]; mvy = cy + c->spy[bp];
+                            } else {
+                                int bcx = clampi(px / 4, -R, R), bcy = clampi(py / 4, -R, R);
+                                full_block(cur, c->w16, ref00, c->pstride, bx, by, bw, bh, bcx, bcy, px, py,
+                                           c->ncand, c->spx, c->spy, c->mvbits, c->lambda_factor,
+                                           t == 1 ? bonus : 0, &mvx, &mvy, &cost);
+                            }
+                            mvx *= 4; mvy *= 4;
+                            if (c->p.subpel)
+                                subpel_block(cur, c->w16, c->planes[r], c->pstride, c->pheight, c->pad, bx, by,
+                                             bw, bh, px, py, c->mvbits, c->lambda_factor, c->p.use_hadamard,
+                                             c->p.satd_round, t == 1 ? bonus : 0, c->spx, c->spy, &mvx, &mvy,
+                                             &cost);
+                            if (opr) {
+                                opr->mv[blk][0] = (int16_t)mvx; opr->mv[blk][1] = (int16_t)mvy;
+                                opr->cost[blk] = cost; opr->ref_idx[blk] = (int8_t)r;
+                            }
+                            total = cost + ref_cost(c, r);
+                            if (total < o->cost[blk]) {         /* lowest ref wins ties */
+                                o->mv[blk][0] = (int16_t)mvx; o->mv[blk][1] = (int16_t)mvy;
+                                o->cost[blk] = total; o->ref_idx[blk] = (int8_t)r;
+                            }
+                        }
+                }
+            }
+        }
+    free(cur); free(bsad);
+    return rc;
+}

@@ -1,0 +1,123 @@
+"""Independent numpy / pure-Python restatements used to cross-check the C oracle.
+Written sample-by-sample from the H.264 text (8.4.2.2.1) and from the definitions in DESIGN.md §2,
+deliberately NOT sharing structure with oracle/jmme_oracle.c."""
+import numpy as np
+
+
+def se_bits(v):
+    """Signed Exp-Golomb code length: codeNum = 2|v| - (v>0); length = 2*floor(log2(codeNum+1))+1."""
+    code = 2 * abs(v) - (1 if v > 0 else 0)
+    return 2 * ((code + 1).bit_length() - 1) + 1
+
+
+def ue_bits(v):
+    return 2 * ((v + 1).bit_length() - 1) + 1
+
+
+def spiral(R):
+    """JM spiral_search_x/y, written as 'sort by ring then by the ring's emission order'."""
+    pts = [(0, 0)]
+    for l in range(1, R + 1):
+        for i in range(-l + 1, l):
+            pts += [(i, -l), (i, l)]
+        for i in range(-l, l + 1):
+            pts += [(-l, i), (l, i)]
+    return pts
+
+
+def spiral_index_closed_form(dx, dy):
+    """SURVEY A.5 closed form."""
+    if dx == 0 and dy == 0:
+        return 0
+    l = max(abs(dx), abs(dy))
+    base = (2 * l - 1) ** 2
+    if abs(dy) == l and abs(dx) < l:
+        return base + 2 * (dx + l - 1) + (1 if dy > 0 else 0)
+    return base + 2 * (2 * l - 1) + 2 * (dy + l) + (1 if dx > 0 else 0)
+
+
+class Interp:
+    """Per-sample luma interpolation on an infinitely edge-replicated picture."""
+
+    def __init__(self, img):
+        self.img = np.asarray(img, dtype=np.int64)
+        self.H, self.W = self.img.shape
+
+    def G(self, x, y):
+        return int(self.img[min(max(y, 0), self.H - 1), min(max(x, 0), self.W - 1)])
+
+    @staticmethod
+    def tap(v):
+        return v[0] - 5 * v[1] + 20 * v[2] + 20 * v[3] - 5 * v[4] + v[5]
+
+    @staticmethod
+    def clip(v):
+        return min(max(v, 0), 255)
+
+    def b1(self, x, y):   # between G(x,y) and G(x+1,y)
+        return self.tap([self.G(x + i, y) for i in range(-2, 4)])
+
+    def h1(self, x, y):   # between G(x,y) and G(x,y+1)
+        return self.tap([self.G(x, y + i) for i in range(-2, 4)])
+
+    def b(self, x, y):
+        return self.clip((self.b1(x, y) + 16) >> 5)
+
+    def h(self, x, y):
+        return self.clip((self.h1(x, y) + 16) >> 5)
+
+    def j(self, x, y):
+        # horizontal 6-tap over vertical intermediates (the text allows either order)
+        return self.clip((self.tap([self.h1(x + i, y) for i in range(-2, 4)]) + 512) >> 10)
+
+    def sample(self, qx, qy):
+        """Sample at quarter-pel position (qx, qy) relative to picture sample (0,0)."""
+        x, y, fx, fy = qx >> 2, qy >> 2, qx & 3, qy & 3
+        G, b, h, j = self.G, self.b, self.h, self.j
+        avg = lambda p, q: (p + q + 1) >> 1                               # noqa: E731
+        table = {
+            (0, 0): lambda: G(x, y), (2, 0): lambda: b(x, y), (0, 2): lambda: h(x, y), (2, 2): lambda: j(x, y),
+            (1, 0): lambda: avg(G(x, y), b(x, y)), (3, 0): lambda: avg(b(x, y), G(x + 1, y)),
+            (0, 1): lambda: avg(G(x, y), h(x, y)), (0, 3): lambda: avg(h(x, y), G(x, y + 1)),
+            (2, 1): lambda: avg(b(x, y), j(x, y)), (2, 3): lambda: avg(j(x, y), b(x, y + 1)),
+            (1, 2): lambda: avg(h(x, y), j(x, y)), (3, 2): lambda: avg(j(x, y), h(x + 1, y)),
+            (1, 1): lambda: avg(b(x, y), h(x, y)), (3, 1): lambda: avg(b(x, y), h(x + 1, y)),
+            (1, 3): lambda: avg(h(x, y), b(x, y + 1)), (3, 3): lambda: avg(h(x + 1, y), b(x, y + 1)),
+        }
+        return table[(fx, fy)]()
+
+
+H4 = np.array([[1, 1, 1, 1], [1, 1, -1, -1], [1, -1, -1, 1], [1, -1, 1, -1]], dtype=np.int64)
+
+
+def satd4x4(d, satd_round=0):
+    d = np.asarray(d, dtype=np.int64).reshape(4, 4)
+    s = int(np.abs(H4 @ d @ H4.T).sum())
+    return (s + 1) >> 1 if satd_round else s >> 1
+
+
+def weighted_cost(f, bits):
+    return (f * bits) >> 16
+
+
+def padded(img, pad):
+    return np.pad(np.asarray(img), pad, mode="edge")
+
+
+def brute_search(cur, refp, pad, bx, by, bw, bh, cx, cy, px, py, R, f, bonus=0, pretest=False):
+    """Direct per-block search in spiral order with strict <.  Returns (mvx, mvy, cost, sad_surface)."""
+    blk = cur[by:by + bh, bx:bx + bw].astype(np.int64)
+    best = None
+    cands = spiral(R)
+    order = list(range(len(cands)))
+    if pretest:
+        order = [cands.index((-cx, -cy))] + order
+    for pos in order:
+        mx, my = cx + cands[pos][0], cy + cands[pos][1]
+        r = refp[pad + by + my: pad + by + my + bh, pad + bx + mx: pad + bx + mx + bw].astype(np.int64)
+        c = int(np.abs(blk - r).sum()) + weighted_cost(f, se_bits(4 * mx - px) + se_bits(4 * my - py))
+        if mx == 0 and my == 0:
+            c -= bonus
+        if best is None or c < best[2]:
+            best = (mx, my, c)
+    return best
