@@ -1,0 +1,432 @@
+// jmme_api.cu — the C ABI of include/jmme.h on top of the sm_100a kernels.
+//
+// Host side of the drop-in boundary: context life cycle, device memory, stream ordering, the
+// stripe (MB-row) partition, the single-process multi-GPU mode (one sub-context per device, MV
+// field gathered to the first device over NVLink peer copies) and parameter checking that
+// mirrors the oracle's error behaviour.  There is NO CPU fallback: every compute entry point
+// fails with JMME_ERR_NODEVICE / JMME_ERR_CUDA when no B200 is usable.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "jmme_dev.cuh"
+
+cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int K, cudaStream_t st);
+cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
+                               int n_planes, uint8_t *out, cudaStream_t st);
+cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stride, int w16, int h16, uint8_t *dst,
+                                cudaStream_t st);
+cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st);
+cudaError_t jmme_launch_select(const SearchParams &P, cudaStream_t st);
+
+struct jmme_ctx {
+    jmme_params p;
+    int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
+    int device, num_sms, K;
+    cudaStream_t stream;
+    uint8_t *d_raw;                       // staging for one raw luma picture (width x height)
+    uint8_t *d_planes[JMME_MAX_REFS];
+    bool ref_set[JMME_MAX_REFS];
+    uint8_t *d_cur16;
+    int16_t *d_pred;
+    uint16_t *d_spiral_key;
+    int16_t *d_spiral_xy;
+    BlkRes *d_res;
+    jmme_mbresult *d_out, *d_out_per_ref;
+    long long launches;
+    char err[256];
+    int n_sub;                            // >0: this is a multi-GPU parent, work lives in sub[]
+    jmme_ctx *sub[JMME_MAX_GPUS];
+    cudaEvent_t ev_done;
+};
+
+namespace {
+
+int fail(jmme_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        if (e != cudaSuccess)
+            snprintf(c->err, sizeof c->err, "%s: %s", what, cudaGetErrorString(e));
+        else
+            snprintf(c->err, sizeof c->err, "%s", what);
+    }
+    return code;
+}
+#define CU(c, call)                                                        \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) return fail(c, JMME_ERR_CUDA, #call, e_);   \
+    } while (0)
+
+int pad_for(int R) { return (2 * R + 16 + 15) & ~15; }
+
+// JM spiral order generated from its closed form: ring l = max(|dx|,|dy|), then the
+// top/bottom rows interleaved, then the left/right columns interleaved.
+int spiral_index(int dx, int dy)
+{
+    if (!dx && !dy) return 0;
+    int l = std::max(std::abs(dx), std::abs(dy)), base = (2 * l - 1) * (2 * l - 1);
+    if (std::abs(dy) == l && std::abs(dx) < l) return base + 2 * (dx + l - 1) + (dy > 0);
+    return base + 2 * (2 * l - 1) + 2 * (dy + l) + (dx > 0);
+}
+
+const int kQp2Quant[40] = {1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 23,
+                           25, 29, 32, 36, 40, 45, 51, 57, 64, 72, 81, 91};
+
+void free_device(jmme_ctx *c)
+{
+    if (c->device >= 0) cudaSetDevice(c->device);
+    cudaFree(c->d_raw);
+    for (int r = 0; r < JMME_MAX_REFS; r++) cudaFree(c->d_planes[r]);
+    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
+    cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+int validate(const jmme_params *p)
+{
+    if (p->width <= 0 || p->height <= 0 || p->search_range < 1 || p->search_range > JMME_MAX_SEARCH_RANGE ||
+        p->num_refs < 1 || p->num_refs > JMME_MAX_REFS || (p->blocktype_mask & ~JMME_MASK_ALL) ||
+        !(p->blocktype_mask & JMME_MASK_ALL) || p->qp < 0 || p->qp > 51 || p->lambda_factor < 0 ||
+        p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 2 || p->satd_round < 0 ||
+        p->satd_round > 1 || p->n_gpus < 0 || p->n_gpus > JMME_MAX_GPUS)
+        return JMME_ERR_PARAM;
+    if (p->cost_domain != 0) return JMME_ERR_UNSUPPORTED;
+    return JMME_OK;
+}
+
+int create_single(jmme_ctx **out, const jmme_params *p, int device)
+{
+    jmme_ctx *c = new (std::nothrow) jmme_ctx();
+    if (!c) return JMME_ERR_NOMEM;
+    memset(c, 0, sizeof *c);
+    c->p = *p;
+    c->device = device;
+    c->w16 = (p->width + 15) & ~15; c->h16 = (p->height + 15) & ~15;
+    c->mb_w = c->w16 / 16; c->mb_h = c->h16 / 16;
+    if (c->p.mb_row_end == 0) c->p.mb_row_end = c->mb_h;
+    if (c->p.mb_row_begin < 0 || c->p.mb_row_end > c->mb_h || c->p.mb_row_begin >= c->p.mb_row_end) {
+        delete c; return JMME_ERR_PARAM;
+    }
+    c->pad = pad_for(p->search_range);
+    c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
+    c->lambda_factor = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
+    if (c->lambda_factor > (96 << 16)) { delete c; return JMME_ERR_PARAM; }
+    c->n_planes = p->subpel ? 16 : 1;
+    c->ncols = 2 * p->search_range + 1; c->ncand = c->ncols * c->ncols;
+    const char *ek = getenv("JMME_K");
+    c->K = ek ? atoi(ek) : 3;
+    if (c->K < 2 || c->K > 5) c->K = 3;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device >= ndev) { delete c; return JMME_ERR_NODEVICE; }
+    int rc = JMME_OK;
+#define CUC(call)                                                                      \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) { rc = fail(c, JMME_ERR_CUDA, #call, e_); goto bad; }   \
+    } while (0)
+    {
+        const size_t n_mb = (size_t)c->mb_w * c->mb_h;
+        const size_t psz = (size_t)c->pstride * c->pheight;
+        std::vector<uint16_t> key(c->ncand);
+        std::vector<int16_t> xy(2 * (size_t)c->ncand);
+        const int R = p->search_range;
+        CUC(cudaSetDevice(device));
+        CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+        CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        CUC(cudaMalloc(&c->d_raw, (size_t)p->width * p->height));
+        for (int r = 0; r < p->num_refs; r++) CUC(cudaMalloc(&c->d_planes[r], psz * c->n_planes));
+        CUC(cudaMalloc(&c->d_cur16, (size_t)c->w16 * c->h16));
+        CUC(cudaMalloc(&c->d_pred, sizeof(int16_t) * 2 * JMME_NBLK * n_mb * p->num_refs));
+        CUC(cudaMalloc(&c->d_res, sizeof(BlkRes) * JMME_NBLK * n_mb * p->num_refs));
+        CUC(cudaMemset(c->d_res, 0, sizeof(BlkRes) * JMME_NBLK * n_mb * p->num_refs));
+        CUC(cudaMalloc(&c->d_out, sizeof(jmme_mbresult) * n_mb));
+        CUC(cudaMemset(c->d_out, 0, sizeof(jmme_mbresult) * n_mb));
+        CUC(cudaMalloc(&c->d_out_per_ref, sizeof(jmme_mbresult) * n_mb * p->num_refs));
+        CUC(cudaMalloc(&c->d_spiral_key, sizeof(uint16_t) * c->ncand));
+        CUC(cudaMalloc(&c->d_spiral_xy, sizeof(int16_t) * 2 * c->ncand));
+        for (int dy = -R; dy <= R; dy++)
+            for (int dx = -R; dx <= R; dx++) {
+                int k = spiral_index(dx, dy);
+                key[(size_t)(dy + R) * c->ncols + (dx + R)] = (uint16_t)(k + 1);
+                xy[2 * (size_t)k] = (int16_t)dx; xy[2 * (size_t)k + 1] = (int16_t)dy;
+            }
+        CUC(cudaMemcpy(c->d_spiral_key, key.data(), sizeof(uint16_t) * c->ncand, cudaMemcpyHostToDevice));
+        CUC(cudaMemcpy(c->d_spiral_xy, xy.data(), sizeof(int16_t) * 2 * c->ncand, cudaMemcpyHostToDevice));
+    }
+#undef CUC
+    *out = c;
+    return JMME_OK;
+bad:
+    free_device(c);
+    delete c;
+    return rc;
+}
+
+void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, int cur_stride, const int16_t *d_pred,
+                        jmme_mbresult *d_out, jmme_mbresult *d_out_per_ref)
+{
+    memset(&P, 0, sizeof P);
+    P.cur = cur; P.cur_stride = cur_stride;
+    for (int r = 0; r < c->p.num_refs; r++) P.planes[r] = c->d_planes[r];
+    P.pstride = c->pstride; P.pheight = c->pheight; P.pad = c->pad;
+    P.mb_w = c->mb_w; P.mb_h = c->mb_h; P.mb_row_begin = c->p.mb_row_begin; P.mb_row_end = c->p.mb_row_end;
+    P.R = c->p.search_range; P.ncols = c->ncols; P.num_refs = c->p.num_refs;
+    P.lambda_factor = c->lambda_factor; P.rdopt = c->p.rdopt; P.search_mode = c->p.search_mode;
+    P.pred_policy = c->p.pred_policy; P.blocktype_mask = c->p.blocktype_mask;
+    P.use_hadamard = c->p.use_hadamard; P.satd_round = c->p.satd_round; P.subpel = c->p.subpel;
+    P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
+    P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy;
+    P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
+}
+
+// enqueue the whole search on `st`; nothing is synchronised here
+int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t *d_pred, jmme_mbresult *d_out,
+                   jmme_mbresult *d_out_per_ref, cudaStream_t st)
+{
+    for (int r = 0; r < c->p.num_refs; r++)
+        if (!c->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
+    const uint8_t *cur = d_cur;
+    int cs = stride;
+    if (c->w16 != c->p.width || c->h16 != c->p.height || (stride & 3) || ((uintptr_t)d_cur & 3)) {
+        CU(c, jmme_launch_pad_cur(d_cur, c->p.width, c->p.height, stride, c->w16, c->h16, c->d_cur16, st));
+        c->launches++;
+        cur = c->d_cur16; cs = c->w16;
+    }
+    SearchParams P;
+    fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
+    CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
+    c->launches++;
+    if (c->p.subpel) {
+        CU(c, jmme_launch_subpel(P, st));
+        c->launches++;
+    }
+    CU(c, jmme_launch_select(P, st));
+    c->launches++;
+    return JMME_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void jmme_default_params(jmme_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->search_range = 32; p->num_refs = 1; p->blocktype_mask = JMME_MASK_ALL;
+    p->qp = 28; p->use_hadamard = 1;
+    p->search_mode = JMME_SEARCH_FASTFULL; p->pred_policy = JMME_PRED_ZERO;
+}
+
+int jmme_lambda_factor(int qp, int rdopt)
+{
+    int q = std::min(std::max(qp - 12, 0), 39);
+    double lambda = rdopt ? std::sqrt(0.85 * std::pow(2.0, q / 3.0)) : (double)kQp2Quant[q];
+    return (int)(65536.0 * lambda + 0.5);
+}
+
+int jmme_create(jmme_ctx **out, const jmme_params *p)
+{
+    if (!out || !p) return JMME_ERR_PARAM;
+    *out = nullptr;
+    int rc = validate(p);
+    if (rc != JMME_OK) return rc;
+    if (p->search_mode == JMME_SEARCH_FULL && p->pred_policy == JMME_PRED_PER_BLOCK)
+        return JMME_ERR_UNSUPPORTED;    // per-block windows: not built on the GPU
+    if (p->n_gpus <= 1) return create_single(out, p, p->device_ids[0]);
+
+    // multi-GPU parent: split the stripe's MB rows as evenly as possible over the devices
+    const int h16 = (p->height + 15) & ~15, mb_h = h16 / 16;
+    const int rb = p->mb_row_begin, re = p->mb_row_end ? p->mb_row_end : mb_h;
+    if (rb < 0 || re > mb_h || rb >= re) return JMME_ERR_PARAM;
+    jmme_ctx *c = new (std::nothrow) jmme_ctx();
+    if (!c) return JMME_ERR_NOMEM;
+    memset(c, 0, sizeof *c);
+    c->p = *p; c->device = -1;
+    const int rows = re - rb, n = std::min(p->n_gpus, rows);
+    int r0 = rb;
+    for (int g = 0; g < n; g++) {
+        jmme_params q = *p;
+        q.n_gpus = 1;
+        q.mb_row_begin = r0; q.mb_row_end = r0 + rows / n + (g < rows % n ? 1 : 0);
+        r0 = q.mb_row_end;
+        rc = create_single(&c->sub[g], &q, p->device_ids[g]);
+        if (rc != JMME_OK) { jmme_destroy(c); return rc; }
+        c->n_sub++;
+    }
+    jmme_ctx *s0 = c->sub[0];
+    c->w16 = s0->w16; c->h16 = s0->h16; c->mb_w = s0->mb_w; c->mb_h = s0->mb_h; c->pad = s0->pad;
+    c->pstride = s0->pstride; c->pheight = s0->pheight; c->lambda_factor = s0->lambda_factor;
+    c->p.mb_row_begin = rb; c->p.mb_row_end = re;
+    for (int g = 1; g < c->n_sub; g++) {         // NVLink peer access towards the gathering device
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, s0->device, c->sub[g]->device);
+        if (can) {
+            cudaSetDevice(s0->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(c->sub[g]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        }
+    }
+    *out = c;
+    return JMME_OK;
+}
+
+int jmme_destroy(jmme_ctx *c)
+{
+    if (!c) return JMME_OK;
+    for (int g = 0; g < c->n_sub; g++) jmme_destroy(c->sub[g]);
+    if (!c->n_sub && c->device >= 0) free_device(c);
+    delete c;
+    return JMME_OK;
+}
+
+const char *jmme_strerror(int code)
+{
+    switch (code) {
+    case JMME_OK: return "ok";
+    case JMME_ERR_PARAM: return "invalid parameter";
+    case JMME_ERR_CUDA: return "CUDA error";
+    case JMME_ERR_NOMEM: return "out of memory";
+    case JMME_ERR_UNSUPPORTED: return "unsupported configuration";
+    case JMME_ERR_STATE: return "invalid state (reference not set?)";
+    case JMME_ERR_NODEVICE: return "no CUDA device";
+    default: return "unknown error";
+    }
+}
+const char *jmme_last_error(const jmme_ctx *c) { return c ? c->err : ""; }
+const char *jmme_backend(void) { return "cuda-sm_100a"; }
+int jmme_abi_version(void) { return JMME_ABI_VERSION; }
+int jmme_mb_width(const jmme_ctx *c) { return c ? c->mb_w : 0; }
+int jmme_mb_height(const jmme_ctx *c) { return c ? c->mb_h : 0; }
+int jmme_pad(const jmme_ctx *c) { return c ? c->pad : 0; }
+int jmme_lambda_factor_of(const jmme_ctx *c) { return c ? c->lambda_factor : 0; }
+long long jmme_launch_count(const jmme_ctx *c)
+{
+    if (!c) return 0;
+    long long n = c->launches;
+    for (int g = 0; g < c->n_sub; g++) n += c->sub[g]->launches;
+    return n;
+}
+
+int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d_luma, int stride, void *stream)
+{
+    if (!c || !d_luma || r < 0 || r >= c->p.num_refs || stride < c->p.width) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, jmme_launch_interp((const uint8_t *)d_luma, c->p.width, c->p.height, stride, c->pad, c->pstride, c->pheight,
+                             c->n_planes, c->d_planes[r], (cudaStream_t)stream));
+    c->launches++;
+    c->ref_set[r] = true;
+    return JMME_OK;
+}
+
+int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
+{
+    if (!c || !luma || r < 0 || r >= c->p.num_refs || stride < c->p.width) return JMME_ERR_PARAM;
+    if (c->n_sub) {
+        for (int g = 0; g < c->n_sub; g++) {
+            int rc = jmme_set_reference(c->sub[g], r, luma, stride);
+            if (rc != JMME_OK) return fail(c, rc, c->sub[g]->err);
+        }
+        return JMME_OK;
+    }
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpy2DAsync(c->d_raw, c->p.width, luma, stride, c->p.width, c->p.height, cudaMemcpyHostToDevice,
+                            c->stream));
+    int rc = jmme_set_reference_dev(c, r, c->d_raw, c->p.width, c->stream);
+    if (rc != JMME_OK) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return JMME_OK;
+}
+
+int jmme_get_subimage(jmme_ctx *c, int r, int xf, int yf, uint8_t *dst, int dst_stride)
+{
+    if (!c || !dst || r < 0 || r >= c->p.num_refs || xf < 0 || xf > 3 || yf < 0 || yf > 3 || dst_stride < c->pstride)
+        return JMME_ERR_PARAM;
+    if (c->n_sub) return jmme_get_subimage(c->sub[0], r, xf, yf, dst, dst_stride);
+    if (!c->ref_set[r]) return JMME_ERR_STATE;
+    if ((xf || yf) && c->n_planes != 16) return JMME_ERR_STATE;
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t *src = c->d_planes[r] + (size_t)c->pstride * c->pheight * (yf * 4 + xf);
+    CU(c, cudaMemcpy2DAsync(dst, dst_stride, src, c->pstride, c->pstride, c->pheight, cudaMemcpyDeviceToHost,
+                            c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return JMME_OK;
+}
+
+int jmme_search_frame_dev(jmme_ctx *c, const void *d_cur, int stride, const void *d_pred, void *d_out,
+                          void *d_out_per_ref, void *stream)
+{
+    if (!c || !d_cur || !d_out || stride < c->p.width) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    if (c->p.pred_policy != JMME_PRED_ZERO && !d_pred) return fail(c, JMME_ERR_PARAM, "pred required");
+    CU(c, cudaSetDevice(c->device));
+    return enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
+                          (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
+}
+
+int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t *pred, jmme_mbresult *out,
+                      jmme_mbresult *out_per_ref)
+{
+    if (!c || !cur || !out || stride < c->p.width) return JMME_ERR_PARAM;
+    if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return fail(c, JMME_ERR_PARAM, "pred required");
+    jmme_ctx *subs1[1] = {c};
+    jmme_ctx **subs = c->n_sub ? c->sub : subs1;
+    const int ns = c->n_sub ? c->n_sub : 1;
+    const size_t n_mb = (size_t)c->mb_w * c->mb_h;
+    const int npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
+    const size_t pred_elems = c->p.pred_policy == JMME_PRED_ZERO ? 0 : (size_t)c->p.num_refs * n_mb * npb * 2;
+    for (int r = 0; r < c->p.num_refs; r++)
+        if (!subs[0]->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
+    for (size_t i = 0; i < pred_elems; i++)
+        if (pred[i] > JMME_MAX_PRED_QPEL || pred[i] < -JMME_MAX_PRED_QPEL)
+            return fail(c, JMME_ERR_PARAM, "pred out of range");
+
+    // enqueue on every device, then gather
+    for (int g = 0; g < ns; g++) {
+        jmme_ctx *s = subs[g];
+        CU(c, cudaSetDevice(s->device));
+        CU(c, cudaMemcpy2DAsync(s->d_raw, s->p.width, cur, stride, s->p.width, s->p.height, cudaMemcpyHostToDevice,
+                                s->stream));
+        if (pred_elems)
+            CU(c, cudaMemcpyAsync(s->d_pred, pred, pred_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
+        int rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,
+                                s->stream);
+        if (rc != JMME_OK) return fail(c, rc, s->err);
+        CU(c, cudaEventRecord(s->ev_done, s->stream));
+    }
+    jmme_ctx *s0 = subs[0];
+    CU(c, cudaSetDevice(s0->device));
+    for (int g = 1; g < ns; g++) {                // MV-field gather over NVLink: stripe g -> device 0
+        jmme_ctx *s = subs[g];
+        const size_t off = (size_t)s->p.mb_row_begin * s->mb_w, cnt = (size_t)(s->p.mb_row_end - s->p.mb_row_begin) * s->mb_w;
+        CU(c, cudaStreamWaitEvent(s0->stream, s->ev_done, 0));
+        CU(c, cudaMemcpyPeerAsync(s0->d_out + off, s0->device, s->d_out + off, s->device, cnt * sizeof(jmme_mbresult),
+                                  s0->stream));
+        if (out_per_ref)
+            for (int r = 0; r < c->p.num_refs; r++)
+                CU(c, cudaMemcpyPeerAsync(s0->d_out_per_ref + r * n_mb + off, s0->device,
+                                          s->d_out_per_ref + r * n_mb + off, s->device, cnt * sizeof(jmme_mbresult),
+                                          s0->stream));
+    }
+    const size_t off = (size_t)c->p.mb_row_begin * c->mb_w, cnt = (size_t)(c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w;
+    CU(c, cudaMemcpyAsync(out + off, s0->d_out + off, cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, s0->stream));
+    if (out_per_ref)
+        for (int r = 0; r < c->p.num_refs; r++)
+            CU(c, cudaMemcpyAsync(out_per_ref + r * n_mb + off, s0->d_out_per_ref + r * n_mb + off,
+                                  cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, s0->stream));
+    CU(c, cudaStreamSynchronize(s0->stream));
+    return JMME_OK;
+}
+
+}  // extern "C"

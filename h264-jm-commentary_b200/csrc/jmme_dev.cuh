@@ -1,0 +1,83 @@
+// jmme_dev.cuh — device-side types and helpers shared by the sm_100a kernels.
+// Conventions ("frozen spec") are in DESIGN.md §2; JM function names per SURVEY.md §8(a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jmme.h"
+
+#define JMME_NBLK 41
+#define JMME_MAX_PRED_QPEL 2048          // |pred| limit enforced by the host API
+#define JMME_KEY_BITS 15                 // packed cost = (cost + bias) << 15 | key
+#define JMME_KEY_MASK 0x7FFFu
+#define JMME_NT 64                       // entries of the rate table T[bits]
+
+// per-(ref, MB, block) intermediate result of the integer / sub-pel searches
+struct __align__(8) BlkRes {
+    int16_t mvx, mvy;                    // quarter-pel
+    int32_t cost;                        // distortion + MV rate (no reference rate)
+};
+
+// launch-constant parameters of a search
+struct SearchParams {
+    const uint8_t *cur;                  // current luma, w16 x h16, stride cur_stride
+    int cur_stride;
+    const uint8_t *planes[JMME_MAX_REFS];// per reference: n_planes padded planes, plane 0 = integer
+    int pstride, pheight;                // padded plane geometry
+    int pad;
+    int mb_w, mb_h, mb_row_begin, mb_row_end;
+    int R, ncols;                        // search range, 2R+1
+    int num_refs;
+    int lambda_factor;
+    int rdopt;                           // 0: pre-test + bonus
+    int search_mode;                     // JMME_SEARCH_*
+    int pred_policy;
+    int blocktype_mask;
+    int use_hadamard, satd_round, subpel;
+    const int16_t *pred;                 // [ref][mb][nb][2] or null
+    const uint16_t *spiral_key;          // [ncols*ncols]  (yoff*ncols+xoff) -> spiral index + 1
+    const int16_t *spiral_xy;            // [ncols*ncols][2] spiral index -> (dx,dy)
+    BlkRes *res;                         // [ref][mb][41]
+    jmme_mbresult *out;                  // [mb]
+    jmme_mbresult *out_per_ref;          // [ref][mb] or null
+};
+
+__device__ __forceinline__ int d_se_bits(int v)
+{
+    // signed Exp-Golomb length: 1 for 0, else 2*floor(log2|v|)+3
+    int a = abs(v);
+    return a ? 2 * (31 - __clz(a)) + 3 : 1;
+}
+__device__ __forceinline__ int d_ue_bits(int r) { return 2 * (31 - __clz(r + 1)) + 1; }
+__device__ __forceinline__ int d_weighted_cost(int f, int bits) { return (int)(((long long)f * bits) >> 16); }
+__device__ __forceinline__ int d_ref_cost(int f, int rdopt, int ref)
+{
+    if (rdopt) return d_weighted_cost(f, d_ue_bits(ref));
+    return ref ? (int)((2ll * f) >> 16) : 0;
+}
+__device__ __forceinline__ int d_clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// 4 absolute byte differences summed and accumulated: one VABSDIFF4.U8.ACC
+__device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// block geometry, result order (blocktype 1..7, raster inside the MB)
+__device__ __constant__ const uint8_t c_blk_x[JMME_NBLK] = {
+    0, 0, 0, 0, 8, 0, 8, 0, 8, 0, 8, 0, 8, 0, 8, 0, 8,
+    0, 4, 8, 12, 0, 4, 8, 12, 0, 4, 8, 12, 0, 4, 8, 12, 0, 4, 8, 12, 0, 4, 8, 12};
+__device__ __constant__ const uint8_t c_blk_y[JMME_NBLK] = {
+    0, 0, 8, 0, 0, 0, 0, 8, 8, 0, 0, 4, 4, 8, 8, 12, 12,
+    0, 0, 0, 0, 8, 8, 8, 8, 0, 0, 0, 0, 4, 4, 4, 4, 8, 8, 8, 8, 12, 12, 12, 12};
+__device__ __constant__ const uint8_t c_blk_w[JMME_NBLK] = {
+    16, 16, 16, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+__device__ __constant__ const uint8_t c_blk_h[JMME_NBLK] = {
+    16, 8, 8, 16, 16, 8, 8, 8, 8, 4, 4, 4, 4, 4, 4, 4, 4,
+    8, 8, 8, 8, 8, 8, 8, 8, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+__device__ __constant__ const uint8_t c_blk_type[JMME_NBLK] = {
+    1, 2, 2, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 5, 5,
+    6, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7};

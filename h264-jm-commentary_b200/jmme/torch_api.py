@@ -1,0 +1,57 @@
+"""Device-resident use of the C ABI from PyTorch: torch provides device memory, streams and
+torch.distributed; all compute is libjmme_cuda.so (jmme_set_reference_dev / jmme_search_frame_dev)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+
+class DeviceSearch:
+    """One jmme_ctx bound to the current CUDA device, fed with torch uint8 tensors."""
+
+    def __init__(self, lib: abi.Lib, **params):
+        self.dev = torch.cuda.current_device()
+        params.setdefault("device_ids", [self.dev])
+        self.ctx = lib.context(**params)
+        self.lib = lib
+        n = self.ctx.mb_w * self.ctx.mb_h
+        self.n_mb = n
+        self.out = torch.zeros((n, abi.MBRESULT_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        self.out_per_ref = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def set_reference(self, ref_idx: int, luma: torch.Tensor):
+        assert luma.is_cuda and luma.dtype == torch.uint8 and luma.dim() == 2 and luma.stride(1) == 1
+        self.lib.check(self.lib.dll.jmme_set_reference_dev(self.ctx.handle, ref_idx, C.c_void_p(luma.data_ptr()),
+                                                           luma.stride(0), self._stream()), self.ctx.handle)
+
+    def search(self, cur: torch.Tensor, pred: torch.Tensor | None = None, per_ref: bool = False) -> torch.Tensor:
+        assert cur.is_cuda and cur.dtype == torch.uint8 and cur.dim() == 2 and cur.stride(1) == 1
+        if per_ref and self.out_per_ref is None:
+            self.out_per_ref = torch.zeros((self.ctx.num_refs, self.n_mb, abi.MBRESULT_DTYPE.itemsize),
+                                           dtype=torch.uint8, device="cuda")
+        pp = C.c_void_p(pred.data_ptr()) if pred is not None else None
+        po = C.c_void_p(self.out_per_ref.data_ptr()) if per_ref else None
+        self.lib.check(self.lib.dll.jmme_search_frame_dev(self.ctx.handle, C.c_void_p(cur.data_ptr()), cur.stride(0),
+                                                          pp, C.c_void_p(self.out.data_ptr()), po, self._stream()),
+                       self.ctx.handle)
+        return self.out
+
+    def stripe_rows(self):
+        return self.ctx.params.mb_row_begin, (self.ctx.params.mb_row_end or self.ctx.mb_h)
+
+    @staticmethod
+    def to_numpy(out: torch.Tensor) -> np.ndarray:
+        return out.cpu().numpy().view(abi.MBRESULT_DTYPE).reshape(out.shape[:-1])
+
+    def launch_count(self):
+        return self.ctx.launch_count()
+
+    def close(self):
+        self.ctx.close()

@@ -1,0 +1,278 @@
+"""GPU parity: libjmme_cuda.so (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact: MV, ref_idx and cost of all 41 blocks of every macroblock; every byte of the 16 planes."""
+import os
+
+import numpy as np
+import pytest
+
+import refimpl
+from jmme import abi, synth
+
+pytestmark = pytest.mark.gpu
+BLOCKS = abi.block_table()
+
+
+def run(lib, cur, refs, pred=None, per_ref=False, **kw):
+    h, w = cur.shape
+    with lib.context(width=w, height=h, num_refs=len(refs), **kw) as ctx:
+        for i, r in enumerate(refs):
+            ctx.set_reference(i, r)
+        return ctx.search_frame(cur, pred, per_ref)
+
+
+def assert_same(got, exp, what=""):
+    if got.tobytes() == exp.tobytes():
+        return
+    for f in ("mv", "cost", "ref_idx"):
+        bad = np.argwhere(got[f] != exp[f])
+        if len(bad):
+            i = tuple(bad[0])
+            idx = i[:-1] if f == "mv" else i
+            raise AssertionError(
+                f"{what}: field {f}: {len(bad)} mismatches; first at index {i}: "
+                f"gpu mv={got['mv'][idx]} cost={got['cost'][idx]} ref={got['ref_idx'][idx]} | "
+                f"oracle mv={exp['mv'][idx]} cost={exp['cost'][idx]} ref={exp['ref_idx'][idx]}")
+    raise AssertionError(f"{what}: reserved bytes differ")
+
+
+def test_library_is_the_cuda_backend(cuda):
+    assert cuda.backend() == "cuda-sm_100a"
+    assert cuda.dll.jmme_abi_version() == 1
+
+
+def test_tables_leaf(cuda, oracle):
+    for R in (1, 7, 32, 64):
+        a, b = cuda.init_motion_search_module(R, 700, 16), oracle.init_motion_search_module(R, 700, 16)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    for qp in range(52):
+        for rd in (0, 1):
+            assert cuda.lambda_factor(qp, rd) == oracle.lambda_factor(qp, rd)
+
+
+@pytest.mark.parametrize("w,h,pad,kind,seed", [(16, 16, 8, "noise", 1), (64, 48, 24, "texture", 2),
+                                               (176, 144, 48, "noise", 3), (48, 32, 12, "checker", 0),
+                                               (32, 32, 16, "const", 0)])
+def test_get_sub_images_luma_bit_exact(cuda, oracle, w, h, pad, kind, seed):
+    img = synth.gen_luma(w, h, seed, kind)
+    a, b = cuda.get_sub_images_luma(img, pad), oracle.get_sub_images_luma(img, pad)
+    for fy in range(4):
+        for fx in range(4):
+            bad = np.argwhere(a[fy, fx] != b[fy, fx])
+            assert len(bad) == 0, (f"plane ({fx},{fy}): {len(bad)} bytes differ, first at {bad[0]} "
+                                   f"gpu {a[fy, fx][tuple(bad[0])]} oracle {b[fy, fx][tuple(bad[0])]}")
+
+
+def test_context_planes_non_multiple_of_16(cuda, oracle):
+    img = synth.gen_luma(52, 38, 4, "texture")
+    kw = dict(width=52, height=38, search_range=6, subpel=1)
+    with cuda.context(**kw) as g, oracle.context(**kw) as o:
+        g.set_reference(0, img)
+        o.set_reference(0, img)
+        assert (g.mb_w, g.mb_h, g.pad) == (o.mb_w, o.mb_h, o.pad)
+        for fy in range(4):
+            for fx in range(4):
+                assert np.array_equal(g.get_subimage(0, fx, fy), o.get_subimage(0, fx, fy)), (fx, fy)
+
+
+def test_satd_leaf(cuda, oracle):
+    rng = np.random.default_rng(3)
+    d = rng.integers(-255, 256, size=(4096, 16)).astype(np.int16)
+    d[0] = 255
+    d[1] = np.tile([255, -255], 8)
+    for rnd in (0, 1):
+        assert np.array_equal(cuda.satd(d, rnd), oracle.satd(d, rnd))
+
+
+def test_setup_fastfull_and_block_search_leaves(cuda, oracle):
+    R = 7
+    cur, refs = synth.frame_pair(64, 48, seed=5, search_range=R)
+    pad = 2 * R + 16
+    refp = refimpl.padded(refs[0], pad)
+    f = oracle.lambda_factor(30, 1)
+    for (mbx, mby, cx, cy, bonus) in [(0, 0, 0, 0, 0), (3, 2, -3, 5, 96), (1, 1, 7, -7, 0)]:
+        c = cur[16 * mby:16 * mby + 16, 16 * mbx:16 * mbx + 16]
+        a = cuda.setup_fast_full_pel_search(c, refp, pad, mbx, mby, cx, cy, R, bonus)
+        b = oracle.setup_fast_full_pel_search(c, refp, pad, mbx, mby, cx, cy, R, bonus)
+        assert np.array_equal(a, b)
+        for blk in (0, 2, 7, 20, 40):
+            for (px, py, pre) in [(0, 0, 1), (4 * cx + 1, 4 * cy - 2, 0), (-9, 30, 1)]:
+                ga = cuda.fast_full_pel_block_motion_search(b[blk], R, cx, cy, px, py, f, pre)
+                gb = oracle.fast_full_pel_block_motion_search(b[blk], R, cx, cy, px, py, f, pre)
+                assert ga == gb, (mbx, mby, blk, px, py, pre)
+    for (bx, by, bw, bh, px, py) in [(16, 16, 16, 16, 0, 0), (36, 20, 4, 8, -11, 6), (8, 40, 8, 4, 40, -40)]:
+        ga = cuda.full_pel_block_motion_search(cur, refp, pad, bx, by, bw, bh, px, py, R, f, 37)
+        gb = oracle.full_pel_block_motion_search(cur, refp, pad, bx, by, bw, bh, px, py, R, f, 37)
+        assert ga == gb
+
+
+def test_subpel_leaf(cuda, oracle):
+    cur, refs = synth.frame_pair(64, 48, seed=6, search_range=4)
+    pad = 16
+    planes = oracle.get_sub_images_luma(refs[0], pad)
+    f = oracle.lambda_factor(26, 0)
+    for (bx, by, bw, bh) in [(16, 16, 16, 16), (32, 8, 8, 16), (4, 4, 4, 4), (40, 28, 8, 4)]:
+        for (mv, had, rnd, bonus) in [((0, 0), 1, 0, 64), ((8, -4), 1, 1, 0), ((-12, 4), 0, 0, 0)]:
+            ga = cuda.sub_pel_block_motion_search(cur, planes, pad, bx, by, bw, bh, 3, -5, f, mv, 5000, had, rnd, bonus)
+            gb = oracle.sub_pel_block_motion_search(cur, planes, pad, bx, by, bw, bh, 3, -5, f, mv, 5000, had, rnd,
+                                                    bonus)
+            assert ga == gb, (bx, by, bw, bh, mv, had)
+
+
+CASES = [
+    # w, h, R, kwargs
+    (64, 48, 4, dict()),
+    (64, 48, 4, dict(rdopt=1, qp=33)),
+    (80, 64, 9, dict(qp=20)),
+    (96, 64, 16, dict(rdopt=1, qp=40)),
+    (64, 64, 32, dict(qp=28)),
+    (48, 48, 5, dict(subpel=1)),
+    (64, 48, 8, dict(subpel=1, rdopt=1, qp=24, satd_round=1)),
+    (64, 48, 6, dict(subpel=1, use_hadamard=0)),
+    (52, 38, 6, dict(subpel=1)),                               # not a multiple of 16
+    (64, 48, 7, dict(blocktype_mask=abi.MASK_16x16, search_mode=abi.SEARCH_FULL)),
+    (64, 48, 7, dict(blocktype_mask=abi.MASK_16x16, subpel=1)),
+    (64, 48, 7, dict(blocktype_mask=0x92, subpel=1)),            # 16x16, 8x8, 4x4 only
+    (64, 48, 6, dict(search_mode=abi.SEARCH_FULL, rdopt=0)),
+    (48, 32, 1, dict(subpel=1)),
+    (48, 32, 2, dict()),
+    (48, 32, 3, dict(rdopt=1)),
+]
+
+
+@pytest.mark.parametrize("K", [3, 4])
+@pytest.mark.parametrize("w,h,R,kw", CASES)
+def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, K):
+    os.environ["JMME_K"] = str(K)
+    for kind, seed in (("texture", 1), ("noise", 2)):
+        cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R, kind=kind)
+        got = run(cuda, cur, refs, search_range=R, **kw)
+        exp = run(oracle, cur, refs, search_range=R, **kw)
+        assert_same(got, exp, f"{w}x{h} R={R} {kw} {kind}")
+
+
+@pytest.mark.parametrize("K", [2, 3, 4, 5])
+@pytest.mark.parametrize("policy,nb", [(abi.PRED_PER_MB, 1), (abi.PRED_PER_BLOCK, 41)])
+@pytest.mark.parametrize("rdopt", [0, 1])
+def test_predictor_policies(cuda, oracle, policy, nb, rdopt, K):
+    os.environ["JMME_K"] = str(K)
+    w, h, R = 64, 48, 8
+    cur, refs = synth.frame_pair(w, h, seed=4, search_range=R, num_refs=2)
+    pred = synth.random_pred(2, 12, nb, seed=7 + rdopt, max_qpel=4 * R + 30)   # some centres get clamped
+    kw = dict(search_range=R, qp=31, rdopt=rdopt, pred_policy=policy, subpel=1)
+    g, gp = run(cuda, cur, refs, pred, True, **kw)
+    o, op = run(oracle, cur, refs, pred, True, **kw)
+    assert_same(gp, op, "per-ref")
+    assert_same(g, o, "best-ref")
+
+
+def test_constant_and_checker_frames_all_ties(cuda, oracle):
+    for kind in ("const", "checker"):
+        cur = synth.gen_luma(48, 48, 0, kind)
+        for rdopt in (0, 1):
+            for lf in (0, 1):
+                kw = dict(search_range=6, rdopt=rdopt, lambda_factor=lf, qp=28, subpel=1)
+                assert_same(run(cuda, cur, [cur], **kw), run(oracle, cur, [cur], **kw),
+                            f"{kind} rdopt={rdopt} lf={lf}")
+    pred = np.array([8, -4], np.int16) * np.ones((1, 9, 1, 2), np.int16)
+    for rdopt in (0, 1):
+        kw = dict(search_range=6, rdopt=rdopt, lambda_factor=1, pred_policy=abi.PRED_PER_MB)
+        cur = synth.gen_luma(48, 48, 0, "const")
+        assert_same(run(cuda, cur, [cur], pred, **kw), run(oracle, cur, [cur], pred, **kw))
+
+
+def test_max_sad_no_overflow_in_packed_cost(cuda, oracle):
+    """0/255 opposition gives the largest possible 16x16 SAD (65280) with the largest lambda."""
+    cur = np.zeros((32, 32), np.uint8)
+    ref = np.full((32, 32), 255, np.uint8)
+    pred = synth.random_pred(1, 4, 41, seed=1, max_qpel=2048)
+    for rdopt in (0, 1):
+        kw = dict(search_range=4, qp=51, rdopt=rdopt, pred_policy=abi.PRED_PER_BLOCK)
+        assert_same(run(cuda, cur, [ref], pred, **kw), run(oracle, cur, [ref], pred, **kw))
+
+
+def test_multi_ref_and_stripes(cuda, oracle):
+    w, h, R = 96, 80, 8
+    cur, refs = synth.frame_pair(w, h, seed=12, search_range=R, num_refs=4)
+    kw = dict(search_range=R, qp=30, rdopt=1, subpel=1)
+    g, gp = run(cuda, cur, refs, None, True, **kw)
+    o, op = run(oracle, cur, refs, None, True, **kw)
+    assert_same(gp, op, "per-ref")
+    assert_same(g, o, "best")
+    parts = np.zeros_like(g)
+    for (a, b) in [(0, 2), (2, 3), (3, 5)]:
+        s = run(cuda, cur, refs, mb_row_begin=a, mb_row_end=b, **kw)
+        parts[a * 6:b * 6] = s[a * 6:b * 6]
+        assert not s[:a * 6].tobytes().strip(b"\0") and not s[b * 6:].tobytes().strip(b"\0")
+    assert parts.tobytes() == g.tobytes()
+
+
+def test_errors_mirror_the_oracle(cuda, oracle):
+    for lib in (cuda, oracle):
+        for kw in (dict(width=0, height=16), dict(width=16, height=16, search_range=65),
+                   dict(width=16, height=16, num_refs=5), dict(width=16, height=16, blocktype_mask=0),
+                   dict(width=16, height=16, mb_row_begin=1, mb_row_end=1)):
+            with pytest.raises(abi.JmmeError) as e:
+                lib.context(**kw)
+            assert e.value.code == abi.ERR_PARAM
+        with pytest.raises(abi.JmmeError) as e:
+            lib.context(width=16, height=16, cost_domain=1)
+        assert e.value.code == abi.ERR_UNSUPPORTED
+        with lib.context(width=32, height=32, search_range=4) as ctx:
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.search_frame(np.zeros((32, 32), np.uint8))
+            assert e.value.code == abi.ERR_STATE
+        with lib.context(width=32, height=32, search_range=4, pred_policy=abi.PRED_PER_MB) as ctx:
+            ctx.set_reference(0, np.zeros((32, 32), np.uint8))
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.search_frame(np.zeros((32, 32), np.uint8), np.full((1, 4, 1, 2), 3000, np.int16))
+            assert e.value.code == abi.ERR_PARAM
+
+
+def test_config1_cif_16x16_full_search(cuda, oracle):
+    """BASELINE config 1: CIF 352x288, 16x16 only, +-16, 1 ref, integer (FullPelBlockMotionSearch)."""
+    cur, refs = synth.frame_pair(352, 288, seed=1, search_range=16)
+    kw = dict(search_range=16, blocktype_mask=abi.MASK_16x16, search_mode=abi.SEARCH_FULL, qp=28)
+    assert_same(run(cuda, cur, refs, **kw), run(oracle, cur, refs, **kw), "config 1")
+
+
+def test_config2_720p_stripe_against_oracle_and_planted_motion(cuda, oracle):
+    """BASELINE config 2 at full size on the GPU; oracle on a 4-row stripe; planted motion everywhere."""
+    w, h, R = 1280, 720, 32
+    cur, refs = synth.frame_pair(w, h, seed=1, search_range=R)
+    kw = dict(search_range=R, qp=28)
+    g = run(cuda, cur, refs, **kw)
+    o = run(oracle, cur, refs, mb_row_begin=20, mb_row_end=24, **kw)
+    assert_same(g[20 * 80:24 * 80], o[20 * 80:24 * 80], "720p rows 20..23")
+    ref = synth.gen_luma(w, h, 5, "noise")
+    dx, dy = -19, 27
+    cur2 = np.roll(ref, (-dy, -dx), axis=(0, 1))
+    g2 = run(cuda, cur2, [ref], search_range=R, qp=28, rdopt=1).reshape(45, 80)
+    inner = g2[3:-3, 3:-3]
+    assert np.all(inner["mv"] == [4 * dx, 4 * dy])
+    lam = oracle.lambda_factor(28, 1)
+    exp = refimpl.weighted_cost(lam, refimpl.se_bits(4 * dx) + refimpl.se_bits(4 * dy)) + refimpl.weighted_cost(lam, 1)
+    assert np.all(inner["cost"] == exp)
+
+
+def test_config3_1080p_subpel_properties(cuda, oracle):
+    """BASELINE config 3 at full size: a stripe matches the oracle (including the rows replicated from
+    1080 to 1088) and stripes reproduce the whole-frame result."""
+    w, h, R = 1920, 1080, 32
+    cur, refs = synth.frame_pair(w, h, seed=2, search_range=R)
+    kw = dict(search_range=R, qp=28, subpel=1)
+    g = run(cuda, cur, refs, **kw)
+    assert len(g) == 120 * 68
+    o = run(oracle, cur, refs, mb_row_begin=66, mb_row_end=68, **kw)
+    assert_same(g[66 * 120:], o[66 * 120:], "1080p rows 66..67")
+    s = run(cuda, cur, refs, mb_row_begin=30, mb_row_end=41, **kw)
+    assert s[30 * 120:41 * 120].tobytes() == g[30 * 120:41 * 120].tobytes()
+
+
+def test_launch_counter_counts_kernels(cuda):
+    cur, refs = synth.frame_pair(64, 48, seed=1, search_range=4)
+    with cuda.context(width=64, height=48, search_range=4, subpel=1) as ctx:
+        ctx.set_reference(0, refs[0])
+        n0 = ctx.launch_count()
+        ctx.search_frame(cur)
+        assert n0 == 1 and ctx.launch_count() - n0 == 3          # me_int, me_subpel, select_ref
