@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — ME macroblocks/sec on BASELINE config 3 (1080p, all 41 blocks, +-32 full search,
+quarter-pel SATD refinement, 1 reference; synthetic YUV420 luma).
+
+A step = one pass of the hot path over one frame pair:
+    set_reference (border replication + 16 quarter-pel planes, a12)
+  + search_frame  (integer 41-block search a6/a7 + sub-pel SATD refinement a10/a11 + reference choice)
+  + (N > 1) all-gather of the MV field over NCCL/NVLink.
+N ranks split the frame's 68 MB rows into contiguous stripes (strong scaling: total work fixed).
+
+  value   MB/s with the frame pair already resident in HBM, device-timed with CUDA events
+  e2e     MB/s through the C-ABI host-buffer calls (jmme_set_reference + jmme_search_frame) with
+          pinned host buffers: H2D of both pictures and D2H of the MV field inside the timed region
+  roofline / roofline_interp / cpu_baseline: see DESIGN.md §5
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port":
+/root/reference holds no sources) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "h264-jm-commentary_b200"))
+
+WORKLOADS = {
+    # name: (width, height, R, refs, subpel, blocktype_mask)
+    "1080p_r32_41blk_qpel_1ref": (1920, 1080, 32, 1, 1, 0xFE),          # BASELINE config 3 (headline)
+    "720p_r32_41blk_int_1ref": (1280, 720, 32, 1, 0, 0xFE),             # config 2
+    "1080p_r64_41blk_int_4ref": (1920, 1080, 64, 4, 0, 0xFE),           # config 4
+    "cif_r16_16x16_int_1ref": (352, 288, 16, 1, 0, 0x02),               # config 1
+}
+OPS_PER_CAND_41 = 171      # 64 VABSDIFF4.ACC + 25 partition adds + 41 x (pack + min), SURVEY §8(d)
+OPS_PER_CAND_16 = 66
+QP = 28
+
+
+def stripe_of(rank, world, mb_h):
+    base, rem = divmod(mb_h, world)
+    b = rank * base + min(rank, rem)
+    return b, b + base + (1 if rank < rem else 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def int_peak_live():
+    """Integer issue peak measured on this GPU right now by csrc/microbench (same instruction mix as the
+    search kernel: 64 VABSDIFF4 + 66 IMAD + 41 VIMNMX per candidate)."""
+    exe = ROOT / "h264-jm-commentary_b200" / "csrc" / "microbench"
+    try:
+        d = json.loads(subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, check=True).stdout)
+        return d["mix_64sad_66imad_41min"]["tera_lane_ops_per_s"], "measured live (csrc/microbench, kernel-mix issue rate)", d
+    except Exception as e:  # noqa: BLE001
+        p = ROOT / "profiles" / "INT_PEAKS_r01.json"
+        if p.exists():
+            d = json.loads(p.read_text())
+            return d["mix_64sad_66imad_41min"]["tera_lane_ops_per_s"], f"profiles/INT_PEAKS_r01.json ({type(e).__name__})", d
+        return 25.9, "fallback constant", {}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on all host cores, bounded sample per step (rank 0 only)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as oracle_mod
+    from jmme import synth
+    orc = oracle_mod.load()
+    w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    orc.dll.jmme_oracle_set_threads.restype = C.c_int
+    cores = orc.dll.jmme_oracle_set_threads(cores)
+    cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
+    mb_h = (h + 15) // 16
+    mb_w = (w + 15) // 16
+    # calibrate: one MB row, then size the per-step sample to ~args.ref_seconds of work
+    rows = 1
+    times = []
+    with orc.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
+                     mb_row_begin=mb_h // 2, mb_row_end=mb_h // 2 + 1) as c:
+        t0 = time.perf_counter()
+        for i, r in enumerate(ref_l):
+            c.set_reference(i, r)
+        c.search_frame(cur)
+        t_row = time.perf_counter() - t0
+    rows = int(max(1, min(mb_h, args.ref_seconds / max(t_row, 1e-6))))
+    b = max(0, (mb_h - rows) // 2)
+    with orc.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
+                     mb_row_begin=b, mb_row_end=b + rows) as c:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            for i, r in enumerate(ref_l):
+                c.set_reference(i, r)
+            c.search_frame(cur)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    n_mb = rows * mb_w
+    v = n_mb / (ms * 1e-3)
+    sample = f"{rows} of {mb_h} MB rows ({n_mb} MBs) of {args.workload} per step, interpolation of the whole reference included"
+    print(json.dumps({
+        "impl": "reference", "metric": "ME macroblocks/sec", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "qp": QP, "note": "CPU restatement (oracle/) of the JM path; the mounted "
+                   "reference holds no sources, so this is a port, not JM itself"},
+        "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def cpu_baseline(args):
+    """Single-thread oracle on a bounded sample (rank 0, N=1)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as oracle_mod
+    from jmme import synth
+    orc = oracle_mod.load()
+    orc.dll.jmme_oracle_set_threads.restype = C.c_int
+    orc.dll.jmme_oracle_set_threads(1)
+    w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
+    cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
+    mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
+
+    def go(rows):
+        b = max(0, (mb_h - rows) // 2)
+        with orc.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
+                         mb_row_begin=b, mb_row_end=b + rows) as c:
+            t0 = time.perf_counter()
+            for i, r in enumerate(ref_l):
+                c.set_reference(i, r)
+            c.search_frame(cur)
+            return time.perf_counter() - t0
+    t1 = go(1)
+    rows = int(max(1, min(mb_h, args.cpu_seconds / max(t1, 1e-6))))
+    t = go(rows)
+    n = rows * mb_w
+    return {"value": n / t, "unit": "MB/s", "cores": 1, "kind": "port",
+            "sample": f"{rows} of {mb_h} MB rows ({n} MBs) of {args.workload}, {t:.1f} s, gcc -O2 single thread, "
+                      f"host has {os.cpu_count()} cores"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import jmme
+    from jmme import abi, synth
+    from jmme.torch_api import DeviceSearch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = jmme.load()
+    w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
+    mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
+    n_mb = mb_h * mb_w
+    rb, re = stripe_of(rank, world, mb_h)
+    cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
+    d_cur = torch.from_numpy(cur).cuda()
+    d_refs = [torch.from_numpy(r).cuda() for r in ref_l]
+    ds = DeviceSearch(lib, width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
+                      mb_row_begin=rb, mb_row_end=re)
+    ds.ctx.set_profiling(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+    rec = abi.MBRESULT_DTYPE.itemsize
+    max_rows = -(-mb_h // world)
+    gather_in = torch.zeros(max_rows * mb_w * rec, dtype=torch.uint8, device="cuda") if world > 1 else None
+    gather_out = torch.zeros(world * max_rows * mb_w * rec, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def step_device():
+        for i, r in enumerate(d_refs):
+            ds.set_reference(i, r)
+        out = ds.search(d_cur)
+        if world > 1:                     # MV-field gather over NVLink (the only collective of the path)
+            n = (re - rb) * mb_w * rec
+            gather_in[:n].copy_(out.view(-1)[rb * mb_w * rec: rb * mb_w * rec + n])
+            dist.all_gather_into_tensor(gather_out, gather_in)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ktimes = []
+    l0 = ds.launch_count()
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 255)              # L2 flush between timed iterations (outside the event pair)
+        barrier()
+        ev[s][0].record()
+        step_device()
+        ev[s][1].record()
+        torch.cuda.synchronize()
+        ktimes.append(ds.ctx.kernel_times())
+    barrier()
+    launches = ds.launch_count() - l0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_dev = float(np.mean(step_ms))
+
+    # ---- end to end through the C-ABI host calls (pinned host buffers) -------------------------
+    h_cur = torch.from_numpy(cur).pin_memory()
+    h_refs = [torch.from_numpy(r).pin_memory() for r in ref_l]
+    h_out = torch.zeros(n_mb * rec, dtype=torch.uint8).pin_memory()
+    hctx = lib.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
+                       mb_row_begin=rb, mb_row_end=re, device_ids=[local_rank])
+    pu8 = C.POINTER(C.c_uint8)
+
+    def step_host():
+        for i, r in enumerate(h_refs):
+            lib.check(lib.dll.jmme_set_reference(hctx.handle, i, C.cast(r.data_ptr(), pu8), w), hctx.handle)
+        lib.check(lib.dll.jmme_search_frame(hctx.handle, C.cast(h_cur.data_ptr(), pu8), w, None,
+                                            C.c_void_p(h_out.data_ptr()), None), hctx.handle)
+
+    for _ in range(max(args.warmup, 3)):
+        step_host()
+    e2e_t = []
+    barrier()
+    for s in range(args.steps):
+        flush.fill_(s & 255)
+        barrier()
+        t0 = time.perf_counter()
+        step_host()
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    ms_e2e = 1e3 * float(np.mean(e2e_t))
+    launches_e2e = hctx.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # parity guard: the host path and the device path must agree byte for byte on this rank's stripe
+    got = ds.to_numpy(ds.out)[rb * mb_w:re * mb_w]
+    exp = h_out.numpy().view(abi.MBRESULT_DTYPE)[rb * mb_w:re * mb_w]
+    assert got.tobytes() == exp.tobytes(), "device-resident and host-buffer paths disagree"
+
+    # ---- max over ranks -------------------------------------------------------------------------
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+
+    if rank == 0:
+        ncand = (2 * R + 1) ** 2
+        ops_cand = OPS_PER_CAND_16 if mask == 0x02 else OPS_PER_CAND_41
+        k_int = float(np.mean([k["me_int"] for k in ktimes]))
+        k_sub = float(np.mean([k["me_subpel"] for k in ktimes]))
+        k_itp = float(np.mean([k["interp"] for k in ktimes]))
+        k_sel = float(np.mean([k["select"] for k in ktimes]))
+        peak, peak_src, _ = int_peak_live()
+        hbm, hbm_src = measured_peaks()
+        alg_ops = (re - rb) * mb_w * refs * ncand * ops_cand          # this rank's launch
+        achieved = alg_ops / (k_int * 1e-3) * 1e-12
+        pad = hctx.pad
+        rows_itp = ((16 * mb_h + 2 * pad) if re == mb_h else min(16 * mb_h + 2 * pad, pad + 16 * re + 2 * R + 4)) - \
+            (0 if rb == 0 else max(0, pad + 16 * rb - 2 * R - 4))
+        itp_bytes = 17 * rows_itp * (16 * mb_w + 2 * pad)
+        itp_gbs = itp_bytes / (k_itp * 1e-3) * 1e-9 if k_itp > 0 else None
+        line = {
+            "metric": "ME macroblocks/sec", "value": n_mb / (ms_dev * 1e-3), "unit": "MB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "frame": f"{w}x{h}", "mbs": n_mb, "search_range": R, "refs": refs,
+                       "blocks": 41 if mask != 0x02 else 1, "subpel": "half+quarter SATD" if subpel else "none",
+                       "qp": QP, "pred_policy": "zero", "partition": f"{world} MB-row stripes",
+                       "l2": "256 MB buffer written between timed steps (outside the event pair)",
+                       "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks"},
+            "e2e": {"value": n_mb / (ms_e2e * 1e-3), "unit": "MB/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": (1 + refs) * w * h, "d2h_bytes_per_step": (re - rb) * mb_w * rec,
+                    "api": "jmme_set_reference + jmme_search_frame (C ABI, pinned host buffers)"},
+            "gpu_launches": int(launches + launches_e2e),
+            "kernel_ms": {"interp": k_itp, "me_int": k_int, "me_subpel": k_sub, "select_ref": k_sel,
+                          "share_me_int": k_int / max(k_itp + k_int + k_sub + k_sel, 1e-9)},
+            "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "me_int_kernel",
+                         "algorithmic_ops_per_candidate": ops_cand, "peak_source": peak_src},
+            "roofline_interp": {"bound": "hbm", "achieved": itp_gbs, "peak": hbm, "unit": "GB/s",
+                                "frac": (itp_gbs / hbm) if itp_gbs else None, "traffic": None,
+                                "kernel": "interp_kernel", "algorithmic_bytes_per_pixel": 17, "peak_source": hbm_src},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    hctx.close()
+    ds.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1080p_r32_41blk_qpel_1ref", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
+    ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU work per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world == 1 and args.gpus > 1 and args.impl == "ours":
+        # launched without torchrun: re-exec under it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

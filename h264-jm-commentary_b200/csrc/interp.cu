@@ -25,13 +25,13 @@ __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
 
 // src: raw picture w_in x h_in (stride), out: n_planes planes of ps x ph.
 __global__ void __launch_bounds__(256) interp_kernel(const uint8_t *__restrict__ src, int w_in, int h_in, int stride,
-                                                     int pad, int ps, int ph, int n_planes,
+                                                     int pad, int ps, int ph, int n_planes, int y_begin,
                                                      uint8_t *__restrict__ out)
 {
     __shared__ uint8_t Gs[GH][GW];
     __shared__ int16_t B1s[GH][TW + 2];      // unrounded horizontal half-pel, cols 0..TW
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;   // padded-plane coordinates of the tile
+    const int x0 = blockIdx.x * TW, y0 = y_begin + blockIdx.y * TH;   // padded-plane coordinates of the tile
 
     for (int i = tid; i < GH * GW; i += 256) {
         int r = i / GW, c = i - r * GW;
@@ -121,11 +121,12 @@ __global__ void pad_cur_kernel(const uint8_t *__restrict__ src, int w_in, int h_
 
 }  // namespace
 
+// rows [y_begin, y_end) of the padded planes are produced (y_begin a multiple of 4 is not required)
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
-                               int n_planes, uint8_t *out, cudaStream_t st)
+                               int n_planes, uint8_t *out, int y_begin, int y_end, cudaStream_t st)
 {
-    dim3 grid((ps + TW - 1) / TW, (ph + TH - 1) / TH);
-    interp_kernel<<<grid, 256, 0, st>>>(src, w_in, h_in, stride, pad, ps, ph, n_planes, out);
+    dim3 grid((ps + TW - 1) / TW, (y_end - y_begin + TH - 1) / TH);
+    interp_kernel<<<grid, 256, 0, st>>>(src, w_in, h_in, stride, pad, ps, ph, n_planes, y_begin, out);
     return cudaGetLastError();
 }
 

@@ -17,9 +17,9 @@
 
 #include "jmme_dev.cuh"
 
-cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int K, cudaStream_t st);
+cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st);
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
-                               int n_planes, uint8_t *out, cudaStream_t st);
+                               int n_planes, uint8_t *out, int y_begin, int y_end, cudaStream_t st);
 cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stride, int w16, int h16, uint8_t *dst,
                                 cudaStream_t st);
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st);
@@ -44,6 +44,9 @@ struct jmme_ctx {
     int n_sub;                            // >0: this is a multi-GPU parent, work lives in sub[]
     jmme_ctx *sub[JMME_MAX_GPUS];
     cudaEvent_t ev_done;
+    int profiling;                        // bracket kernels with events
+    cudaEvent_t ev_prof[4][2];            // [interp, me_int, me_subpel, select][begin, end]
+    bool prof_valid[4];
 };
 
 namespace {
@@ -87,6 +90,9 @@ void free_device(jmme_ctx *c)
     cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 2; j++)
+            if (c->ev_prof[i][j]) cudaEventDestroy(c->ev_prof[i][j]);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -121,9 +127,8 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
     if (c->lambda_factor > (96 << 16)) { delete c; return JMME_ERR_PARAM; }
     c->n_planes = p->subpel ? 16 : 1;
     c->ncols = 2 * p->search_range + 1; c->ncand = c->ncols * c->ncols;
-    const char *ek = getenv("JMME_K");
-    c->K = ek ? atoi(ek) : 3;
-    if (c->K < 2 || c->K > 5) c->K = 3;
+    const char *ek = getenv("JMME_VARIANT");      // tuning knob: 10*K + launch shape, see me_int.cu
+    c->K = ek ? atoi(ek) : 32;
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -198,20 +203,28 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         if (!c->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
     const uint8_t *cur = d_cur;
     int cs = stride;
-    if (c->w16 != c->p.width || c->h16 != c->p.height || (stride & 3) || ((uintptr_t)d_cur & 3)) {
+    // the search kernel fetches the current MB with 16-byte cp.async: rows must be 16-byte aligned
+    if (c->w16 != c->p.width || c->h16 != c->p.height || (stride & 15) || ((uintptr_t)d_cur & 15)) {
         CU(c, jmme_launch_pad_cur(d_cur, c->p.width, c->p.height, stride, c->w16, c->h16, c->d_cur16, st));
         c->launches++;
         cur = c->d_cur16; cs = c->w16;
     }
     SearchParams P;
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
+    c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
+    if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[1][0], st));
     CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
+    if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[1][1], st)); c->prof_valid[1] = true; }
     c->launches++;
     if (c->p.subpel) {
+        if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[2][0], st));
         CU(c, jmme_launch_subpel(P, st));
+        if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[2][1], st)); c->prof_valid[2] = true; }
         c->launches++;
     }
+    if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[3][0], st));
     CU(c, jmme_launch_select(P, st));
+    if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[3][1], st)); c->prof_valid[3] = true; }
     c->launches++;
     return JMME_OK;
 }
@@ -323,8 +336,18 @@ int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d_luma, int stride, v
     if (!c || !d_luma || r < 0 || r >= c->p.num_refs || stride < c->p.width) return JMME_ERR_PARAM;
     if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
     CU(c, cudaSetDevice(c->device));
+    // only the plane rows this context's stripe can reach: window centre within +-R, window +-R,
+    // 16 rows of the MB, one more sample for the sub-pel candidates (rounded out to 4)
+    const int R = c->p.search_range;
+    // (a stripe that touches the top / bottom of the picture produces the whole border)
+    const int y_begin = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - 2 * R - 4);
+    const int y_end = c->p.mb_row_end == c->mb_h ? c->pheight
+                                                 : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
+    c->prof_valid[0] = false;
+    if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[0][0], (cudaStream_t)stream));
     CU(c, jmme_launch_interp((const uint8_t *)d_luma, c->p.width, c->p.height, stride, c->pad, c->pstride, c->pheight,
-                             c->n_planes, c->d_planes[r], (cudaStream_t)stream));
+                             c->n_planes, c->d_planes[r], y_begin, y_end, (cudaStream_t)stream));
+    if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[0][1], (cudaStream_t)stream)); c->prof_valid[0] = true; }
     c->launches++;
     c->ref_set[r] = true;
     return JMME_OK;
@@ -346,6 +369,33 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
     int rc = jmme_set_reference_dev(c, r, c->d_raw, c->p.width, c->stream);
     if (rc != JMME_OK) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
+    return JMME_OK;
+}
+
+int jmme_set_profiling(jmme_ctx *c, int enable)
+{
+    if (!c) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "profiling needs a single-device context");
+    CU(c, cudaSetDevice(c->device));
+    if (enable)
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 2; j++)
+                if (!c->ev_prof[i][j]) CU(c, cudaEventCreate(&c->ev_prof[i][j]));
+    c->profiling = enable != 0;
+    return JMME_OK;
+}
+
+int jmme_get_kernel_times(jmme_ctx *c, float ms[4])
+{
+    if (!c || !ms) return JMME_ERR_PARAM;
+    if (c->n_sub || !c->profiling) return fail(c, JMME_ERR_STATE, "profiling is not enabled");
+    CU(c, cudaSetDevice(c->device));
+    for (int i = 0; i < 4; i++) {
+        ms[i] = 0.f;
+        if (!c->prof_valid[i]) continue;
+        CU(c, cudaEventSynchronize(c->ev_prof[i][1]));
+        CU(c, cudaEventElapsedTime(&ms[i], c->ev_prof[i][0], c->ev_prof[i][1]));
+    }
     return JMME_OK;
 }
 

@@ -12,7 +12,7 @@
 #include "jmme_dev.cuh"
 
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
-                               int n_planes, uint8_t *out, cudaStream_t st);
+                               int n_planes, uint8_t *out, int y_begin, int y_end, cudaStream_t st);
 
 namespace {
 
@@ -264,7 +264,7 @@ int jmme_getSubImagesLuma(const uint8_t *luma, int width, int height, int stride
     DevBuf src, dst;
     LCU(upload_rect(src, luma, stride, width, height));
     LCU(dst.alloc((size_t)ps * ph * 16));
-    LCU(jmme_launch_interp(src.as<uint8_t>(), width, height, width, pad, ps, ph, 16, dst.as<uint8_t>(), 0));
+    LCU(jmme_launch_interp(src.as<uint8_t>(), width, height, width, pad, ps, ph, 16, dst.as<uint8_t>(), 0, ph, 0));
     LCU(cudaMemcpy(out_planes, dst.p, (size_t)ps * ph * 16, cudaMemcpyDeviceToHost));
     return JMME_OK;
 }

@@ -5,45 +5,61 @@
 // exists under /root/reference (README.md:1-4 only); conventions are DESIGN.md §2.
 //
 // Mapping
-//   CTA        one (reference, macroblock) work item at a time, persistent grid-stride loop
-//   window     (2R+16) x (2R+16) reference bytes around the search centre, staged in shared
-//              memory as FOUR byte-phase copies (copy p = window shifted left by p bytes), so
-//              that every candidate reads aligned 32-bit words and VABSDIFF4 needs no PRMT
-//   thread     a vertical run of K candidates (same dx, dy..dy+K-1): each reference row is
-//              loaded once (4 LDS.32) and reused by the K candidates; the current MB (64 words)
-//              and the K*16 4x4 partial SADs live in registers
-//   SAD        4x4 SADs once (64 VABSDIFF4.U8.ACC per candidate), 25 adds build the 8x4, 4x8,
-//              8x8, 16x8, 8x16, 16x16 sums (SetupLargerBlocks)
+//   CTA        persistent; one (reference, macroblock) work item at a time, grid-stride order
+//   pipeline   while item i is searched, the raw window rows and the current MB of item i+1 arrive
+//              in shared memory through cp.async (LDGSTS, 16-byte chunks); after the search a short
+//              shared-to-shared pass expands them into the search layout
+//   window     (2R+16) x (2R+16) reference bytes around the search centre, held as one 32-bit word
+//              PER BYTE POSITION: word[row][x] = bytes x..x+3 of the row.  A candidate at horizontal
+//              offset x reads words x, x+4, x+8, x+12: always aligned, no PRMT before VABSDIFF4, and
+//              32 lanes with consecutive x hit 32 consecutive banks
+//   thread     a vertical run of K candidates (same dx, dy..dy+K-1): each reference row is loaded
+//              once (4 LDS.32) and reused by the K candidates; the current MB (64 words) and the
+//              K*16 4x4 partial SADs live in registers
+//   warp       32 consecutive dx of one run (bank-conflict free); the columns left over after the
+//              last full group of 32 are gathered, several runs per warp, into residual tasks
+//   SAD        4x4 SADs once (64 VABSDIFF4.U8.ACC per candidate), 25 adds build the 8x4, 4x8, 8x8,
+//              16x8, 8x16, 16x16 sums (SetupLargerBlocks)
 //   argmin     cost and tie-break key are packed as ((sad + rate + bias) << 15) | key with
-//              key = 1 + spiral index (0 for the MV(0,0) pre-test), so that ONE unsigned min per
-//              (block, candidate) reproduces JM's strict-< scan in spiral order; 41 running
-//              minima per thread, then CREDUX.MIN per warp and shared-memory atomicMin per CTA
+//              key = 1 + spiral index, so that ONE unsigned min per (block, candidate) reproduces
+//              JM's strict-< scan in spiral order; candidates are folded in pairs (VIMNMX3);
+//              41 running minima per thread, then CREDUX.MIN per warp and shared atomicMin per CTA
+//   MV (0,0)   JM's "(0,0) first" pre-test (!rdopt) is the key table entry of that candidate set
+//              to 0 for the item; the 16x16 (0,0) bonus is one extra 16x16 evaluation by warp 0
 #include "jmme_dev.cuh"
 
 namespace {
 
 template <bool PER_BLOCK>
 struct SmemLayout {
-    int RS, rows, copy_stride;          // words
-    int off_win, off_cur, off_T, off_best, off_key, off_bx, off_by, total_words;
+    int RS, rows, RAWW;                 // window row stride (words, multiple of 4), rows, raw row words
+    int off_win, off_raw, off_cur, off_T, off_best, off_key, off_bx, off_by, total_words;
     __host__ __device__ SmemLayout(int R)
     {
-        int ncols = 2 * R + 1;
-        RS = ((2 * R) >> 2) + 4;
+        const int ncols = 2 * R + 1;
+        RS = (2 * R + 13 + 3) & ~3;     // word positions 0 .. 2R+12
         rows = 2 * R + 16;
-        copy_stride = rows * RS;
-        copy_stride += (8 - (copy_stride & 31) + 32) & 31;     // == 8 (mod 32): conflict-free phases
+        RAWW = ((15 + RS + 12 + 15) & ~15) >> 2;      // 16-byte chunks covering any 16-byte phase
         off_win = 0;
-        off_cur = off_win + 4 * copy_stride;
-        off_T = off_cur + 64;
+        off_raw = off_win + rows * RS;
+        off_cur = off_raw + rows * RAWW;
+        off_T = off_cur + 2 * 64;
         off_best = off_T + JMME_NT;
         off_key = off_best + 48;
         off_bx = off_key + (ncols * ncols + 1) / 2;
-        int nb = PER_BLOCK ? JMME_NBLK : 1;
+        const int nb = PER_BLOCK ? JMME_NBLK : 1;
         off_by = off_bx + (nb * ncols + 3) / 4;
         total_words = off_by + (nb * ncols + 3) / 4;
     }
 };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // partition sums of one candidate from its 16 4x4 SADs (SetupLargerBlocks), result order
 __device__ __forceinline__ void larger_blocks(const unsigned (&s)[16], unsigned (&o)[JMME_NBLK])
@@ -69,13 +85,19 @@ __device__ __forceinline__ void larger_blocks(const unsigned (&s)[16], unsigned 
     o[0] = o[1] + o[2];                                                                          // 16x16
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16>
+struct Item {
+    int ref, mbx, mby, mb, cx, cy;
+};
+
+// RS_CT: compile-time window row stride (0 = take it from the layout at run time)
+template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16, int RS_CT>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParams P)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     const SmemLayout<PER_BLOCK> L(P.R);
     uint32_t *s_win = smem + L.off_win;
-    uint32_t *s_cur = smem + L.off_cur;
+    uint32_t *s_raw = smem + L.off_raw;
+    uint32_t *s_cur2 = smem + L.off_cur;
     uint32_t *s_T = smem + L.off_T;
     uint32_t *s_best = smem + L.off_best;
     uint16_t *s_key = (uint16_t *)(smem + L.off_key);
@@ -84,11 +106,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = P.R, ncols = P.ncols, ncand = ncols * ncols;
-    const int RS = L.RS, rows = L.rows, cstride = L.copy_stride;
+    const int RS = RS_CT ? RS_CT : L.RS;
+    const int rows = L.rows, RAWW = L.RAWW;
     const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
     const int n_items = n_mb_stripe * P.num_refs;
     constexpr int NB = ONLY16 ? 1 : JMME_NBLK;
+    constexpr int NA = ONLY16 ? 4 : 16;
+    constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
     // tables that do not depend on the work item
     for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
@@ -96,80 +121,138 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
     const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
     for (int i = tid; i < JMME_NT; i += NW * 32)
         s_T[i] = ((unsigned)d_weighted_cost(P.lambda_factor, i) + bias) << JMME_KEY_BITS;
+    const bool pretest = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
+    int patched = -1;                                    // key-table entry currently forced to 0
 
+    // task geometry: full groups of 32 columns per run, then residual columns, several runs per warp
     const int nruns = (ncols + K - 1) / K;
-    const int W = nruns * ncols;
+    const int nseg = ncols >> 5;
+    const int wr = ncols - 32 * nseg;                    // 1..31 (ncols is odd)
+    const int G = 32 / wr;                               // runs per residual task
+    const int n_main = nruns * nseg;
+    const int n_tasks = n_main + (nruns + G - 1) / G;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ref = item / n_mb_stripe;
-        const int mbi = item - ref * n_mb_stripe;
-        const int mby = P.mb_row_begin + mbi / P.mb_w;
-        const int mbx = mbi % P.mb_w;
-        const int mb = mby * P.mb_w + mbx;
-        const int npb = PER_BLOCK ? JMME_NBLK : 1;
-        const int16_t *pr = P.pred ? P.pred + ((size_t)ref * n_mb + mb) * npb * 2 : nullptr;
+    auto decode_item = [&](int item, Item &it) {
+        it.ref = item / n_mb_stripe;
+        const int mbi = item - it.ref * n_mb_stripe;
+        it.mby = P.mb_row_begin + mbi / P.mb_w;
+        it.mbx = mbi % P.mb_w;
+        it.mb = it.mby * P.mb_w + it.mbx;
+        const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
-        const int cx = d_clamp(p16x / 4, -R, R), cy = d_clamp(p16y / 4, -R, R);
-        const int bonus = (ref == 0) ? bonus_base : 0;
-        const bool pretest = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
-        const bool special = pretest || bonus != 0;
-        const int x00 = R - cx, y00 = R - cy;            // window offsets of MV (0,0)
-
-        __syncthreads();                                 // previous item finished with smem
-        // ---- stage the search window as 4 byte-phase copies --------------------------------
-        {
-            const uint8_t *plane = P.planes[ref];
-            const int gx0 = P.pad + 16 * mbx + cx - R;   // byte column of window column 0
-            const int gy0 = P.pad + 16 * mby + cy - R;
-            const int t = gx0 & 3;
-            const uint32_t *g32 = (const uint32_t *)(plane + (size_t)gy0 * P.pstride + (gx0 & ~3));
-            const int pw = P.pstride >> 2;
-            for (int idx = tid; idx < rows * RS; idx += NW * 32) {
-                int row = idx / RS, w = idx - row * RS;
-                const uint32_t *g = g32 + (size_t)row * pw + w;
-                uint32_t a0 = __ldg(g), a1 = __ldg(g + 1), a2 = __ldg(g + 2);
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    int o = (t + p) >> 2, sh = ((t + p) & 3) * 8;
-                    uint32_t lo = o ? a1 : a0, hi = o ? a2 : a1;
-                    s_win[p * cstride + idx] = __funnelshift_r(lo, hi, sh);
-                }
-            }
-            // current macroblock: 16 rows x 4 words
-            if (tid < 64) {
-                int row = tid >> 2, w = tid & 3;
-                s_cur[tid] = *(const uint32_t *)(P.cur + (size_t)(16 * mby + row) * P.cur_stride + 16 * mbx + 4 * w);
-            }
-            if (tid < 48) s_best[tid] = 0xFFFFFFFFu;
-            // MV-bit tables of this item: bits of (4*mv - pred) per window column / row
-            const int nb = PER_BLOCK ? JMME_NBLK : 1;
-            for (int i = tid; i < nb * ncols; i += NW * 32) {
-                int b = i / ncols, o = i - b * ncols;
-                int px = pr ? pr[2 * b] : 0, py = pr ? pr[2 * b + 1] : 0;
-                s_bx[i] = (uint8_t)d_se_bits(4 * (cx + o - R) - px);
-                s_by[i] = (uint8_t)d_se_bits(4 * (cy + o - R) - py);
-            }
+        it.cx = d_clamp(p16x / 4, -R, R);
+        it.cy = d_clamp(p16y / 4, -R, R);
+    };
+    // asynchronous fetch of the raw window rows (16-byte chunks) and the current MB of an item
+    auto prefetch = [&](const Item &it, int buf) {
+        const uint8_t *plane = P.planes[it.ref];
+        const int gx0 = P.pad + 16 * it.mbx + it.cx - R, gy0 = P.pad + 16 * it.mby + it.cy - R;
+        const uint8_t *g = plane + (size_t)gy0 * P.pstride + (gx0 & ~15);
+        const int nch = RAWW >> 2;
+        for (int i = tid; i < rows * nch; i += NW * 32) {
+            const int row = i / nch, c = i - row * nch;
+            cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
         }
-        __syncthreads();
+        if (tid < 16)                                    // current MB: 16 rows of 16 bytes
+            cp_async16(s_cur2 + buf * 64 + 4 * tid, P.cur + (size_t)(16 * it.mby + tid) * P.cur_stride + 16 * it.mbx);
+        cp_async_commit();
+    };
+    // raw rows -> one word per byte position; per-item tables
+    auto expand = [&](const Item &it) {
+        const int gx0 = P.pad + 16 * it.mbx + it.cx - R;
+        const int t16 = gx0 & 15, sh = (t16 & 3) * 8, w0i = t16 >> 2, nq = RS >> 2;
+        for (int i = tid; i < rows * nq; i += NW * 32) {
+            const int row = i / nq, q = i - row * nq;
+            const uint32_t *a = s_raw + row * RAWW + w0i + q;
+            const uint32_t a0 = a[0], a1 = a[1], a2 = a[2];
+            const uint32_t w0 = __funnelshift_r(a0, a1, sh), w4 = __funnelshift_r(a1, a2, sh);
+            uint4 v;
+            v.x = w0;
+            v.y = __funnelshift_r(w0, w4, 8);
+            v.z = __funnelshift_r(w0, w4, 16);
+            v.w = __funnelshift_r(w0, w4, 24);
+            *(uint4 *)(s_win + row * RS + 4 * q) = v;
+        }
+        if (tid < 48) s_best[tid] = 0xFFFFFFFFu;
+        const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
+        for (int i = tid; i < NPB * ncols; i += NW * 32) {
+            const int b = i / ncols, o = i - b * ncols;
+            const int px = pr ? pr[2 * b] : 0, py = pr ? pr[2 * b + 1] : 0;
+            s_bx[i] = (uint8_t)d_se_bits(4 * (it.cx + o - R) - px);
+            s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + o - R) - py);
+        }
+        const int idx00 = (R - it.cy) * ncols + (R - it.cx);
+        if (pretest && tid == 0) {                       // "(0,0) first": key 0 wins every tie
+            if (patched >= 0 && patched != idx00) s_key[patched] = P.spiral_key[patched];
+            s_key[idx00] = 0;
+        }
+        if (pretest) patched = idx00;
+    };
+
+    Item cur_it, nxt_it;
+    int item = blockIdx.x, buf = 0;
+    if (item >= n_items) return;
+    decode_item(item, cur_it);
+    prefetch(cur_it, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    expand(cur_it);
+    __syncthreads();
+
+    for (; item < n_items; item += gridDim.x) {
+        const int nxt = item + gridDim.x;
+        const bool has_next = nxt < n_items;
+        if (has_next) {
+            decode_item(nxt, nxt_it);
+            prefetch(nxt_it, buf ^ 1);                   // lands while this item is searched
+        }
+        const int cx = cur_it.cx, cy = cur_it.cy;
+        const int bonus = (cur_it.ref == 0) ? bonus_base : 0;
+        const int x00 = R - cx, y00 = R - cy;            // window offsets of MV (0,0)
+        const uint32_t *s_cur = s_cur2 + buf * 64;
 
         uint32_t cur[16][4];
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            uint4 v = *(const uint4 *)(s_cur + 4 * r);
+            const uint4 v = *(const uint4 *)(s_cur + 4 * r);
             cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
         }
+
+        if (bonus != 0 && warp == 0) {
+            // 16x16 block at MV (0,0) with the -WEIGHTED_COST(lambda,16) bonus: one more candidate
+            // evaluation for block 0, spread over the 32 lanes (2 words each)
+            unsigned s = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = lane + 32 * h, row = i >> 2, j = i & 3;
+                s = sad4(s_cur[i], s_win[(y00 + row) * RS + x00 + 4 * j], s);
+            }
+            s = __reduce_add_sync(0xFFFFFFFFu, s);
+            if (lane == 0) {
+                const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + s_key[y00 * ncols + x00] -
+                                   ((unsigned)bonus << JMME_KEY_BITS);
+                atomicMin(&s_best[0], v);
+            }
+        }
+
         uint32_t best[NB];
 #pragma unroll
         for (int b = 0; b < NB; b++) best[b] = 0xFFFFFFFFu;
 
-        for (int it0 = warp * 32; it0 < W; it0 += NW * 32) {
-            const int idx = min(it0 + lane, W - 1);      // idle lanes repeat the last item (idempotent)
-            const int run = idx / ncols;
-            const int xoff = idx - run * ncols;
+        for (int task = warp; task < n_tasks; task += NW) {
+            int run, xoff;
+            if (task < n_main) {
+                run = task / nseg;
+                xoff = 32 * (task - run * nseg) + lane;
+            } else {
+                int g = lane / wr, x = lane - g * wr;
+                if (g >= G) { g = 0; x = 0; }            // idle lanes repeat lane 0 (idempotent)
+                run = min((task - n_main) * G + g, nruns - 1);
+                xoff = 32 * nseg + x;
+            }
             const int ybase = min(run * K, ncols - K);   // last run overlaps the previous one
-            const uint32_t *base = s_win + (xoff & 3) * cstride + ybase * RS + (xoff >> 2);
+            const uint32_t *base = s_win + ybase * RS + xoff;
 
-            constexpr int NA = ONLY16 ? 4 : 16;
             unsigned acc[K][NA];
 #pragma unroll
             for (int k = 0; k < K; k++)
@@ -178,7 +261,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
 #pragma unroll
             for (int rr = 0; rr < 16 + K - 1; rr++) {
                 const uint32_t *rp = base + rr * RS;
-                const unsigned r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+                const unsigned r0 = rp[0], r1 = rp[4], r2 = rp[8], r3 = rp[12];
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const int cr = rr - k;               // current-MB row this reference row meets
@@ -192,57 +275,66 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
                 }
             }
 
+            // rate + key of candidate k (uniform predictor) or the key alone (per-block predictors)
             const unsigned bx0 = s_bx[xoff];
-#pragma unroll
-            for (int k = 0; k < K; k++) {
+            auto kr_of = [&](int k) -> unsigned {
                 const int yoff = ybase + k;
                 const unsigned key = s_key[yoff * ncols + xoff];
-                unsigned pk[NB];
+                return PER_BLOCK ? key : s_T[bx0 + s_by[yoff]] + key;
+            };
+            auto pack = [&](int k, unsigned kr, unsigned (&pk)[NB]) {
                 if constexpr (ONLY16) {
-                    unsigned s = (acc[k][0] + acc[k][1]) + (acc[k][2] + acc[k][3]);
-                    pk[0] = (s << JMME_KEY_BITS) + s_T[bx0 + s_by[yoff]] + key;
+                    const unsigned s = (acc[k][0] + acc[k][1]) + (acc[k][2] + acc[k][3]);
+                    pk[0] = (s << JMME_KEY_BITS) + kr;
                 } else {
                     unsigned o[JMME_NBLK];
                     larger_blocks(acc[k], o);
                     if constexpr (!PER_BLOCK) {
-                        const unsigned kr = s_T[bx0 + s_by[yoff]] + key;
 #pragma unroll
                         for (int b = 0; b < NB; b++) pk[b] = (o[b] << JMME_KEY_BITS) + kr;
                     } else {
+                        const int yoff = ybase + k;
 #pragma unroll
-                        for (int b = 0; b < NB; b++) {
-                            const unsigned kr = s_T[s_bx[b * ncols + xoff] + s_by[b * ncols + yoff]] + key;
-                            pk[b] = (o[b] << JMME_KEY_BITS) + kr;
-                        }
+                        for (int b = 0; b < NB; b++)
+                            pk[b] = (o[b] << JMME_KEY_BITS) + s_T[s_bx[b * ncols + xoff] + s_by[b * ncols + yoff]] + kr;
                     }
                 }
+            };
+            // candidates are folded two at a time: min(best, min(a, b)) is one VIMNMX3
 #pragma unroll
-                for (int b = 0; b < NB; b++) best[b] = min(best[b], pk[b]);
-                if (special && xoff == x00 && yoff == y00) {
-                    // the MV (0,0) candidate: tested first when !rdopt (key 0 wins every tie) and the
-                    // 16x16 block gets the -WEIGHTED_COST(lambda,16) bonus on reference 0
+            for (int k = 0; k + 1 < K; k += 2) {
+                unsigned pa[NB], pb[NB];
+                pack(k, kr_of(k), pa);
+                pack(k + 1, kr_of(k + 1), pb);
 #pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        unsigned v = pk[b];
-                        if (pretest) v &= ~JMME_KEY_MASK;
-                        if (b == 0) v -= (unsigned)bonus << JMME_KEY_BITS;
-                        best[b] = min(best[b], v);
-                    }
-                }
+                for (int b = 0; b < NB; b++) best[b] = min(best[b], min(pa[b], pb[b]));
+            }
+            if (K & 1) {
+                unsigned pa[NB];
+                pack(K - 1, kr_of(K - 1), pa);
+#pragma unroll
+                for (int b = 0; b < NB; b++) best[b] = min(best[b], pa[b]);
             }
         }
 
-        // ---- reduce: lanes -> warp (CREDUX.MIN) -> CTA (shared atomicMin) ---------------------
+        // ---- reduce: lanes -> warp (CREDUX.MIN), lane b keeps block b, two shared atomicMin ------
+        {
+            unsigned m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
-            unsigned m = __reduce_min_sync(0xFFFFFFFFu, best[b]);
-            if (lane == 0) atomicMin(&s_best[b], m);
+            for (int b = 0; b < NB; b++) {
+                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, best[b]);
+                if (b < 32) m0 = (lane == b) ? m : m0;
+                else m1 = (lane == b - 32) ? m : m1;
+            }
+            if (lane < NB) atomicMin(&s_best[lane], m0);
+            if (NB > 32 && lane < NB - 32) atomicMin(&s_best[32 + lane], m1);
         }
-        __syncthreads();
+        cp_async_wait_all();                             // next item's raw rows have landed
+        __syncthreads();                                 // every warp is done with s_win / s_best
         if (tid < NB) {
             const unsigned v = s_best[tid];
             const unsigned key = v & JMME_KEY_MASK;
-            int mvx = 0, mvy = 0;
+            int mvx = 0, mvy = 0;                        // key 0 = the MV (0,0) pre-test
             if (key) {
                 mvx = cx + P.spiral_xy[2 * (key - 1)];
                 mvy = cy + P.spiral_xy[2 * (key - 1) + 1];
@@ -251,17 +343,23 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
             r.mvx = (int16_t)(4 * mvx);
             r.mvy = (int16_t)(4 * mvy);
             r.cost = (int)(v >> JMME_KEY_BITS) - (int)bias;
-            P.res[((size_t)ref * n_mb + mb) * JMME_NBLK + tid] = r;
+            P.res[((size_t)cur_it.ref * n_mb + cur_it.mb) * JMME_NBLK + tid] = r;
         }
+        if (!has_next) break;
+        __syncthreads();                                 // s_best read before expand() resets it
+        expand(nxt_it);
+        __syncthreads();
+        cur_it = nxt_it;
+        buf ^= 1;
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16>
+template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16, int RS_CT>
 cudaError_t launch_one(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     SmemLayout<PER_BLOCK> L(P.R);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_kernel<K, NW, MINB, PER_BLOCK, ONLY16>;
+    auto kern = me_int_kernel<K, NW, MINB, PER_BLOCK, ONLY16, RS_CT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     int occ = 0;
@@ -274,24 +372,33 @@ cudaError_t launch_one(const SearchParams &P, int num_sms, cudaStream_t st)
     return cudaGetLastError();
 }
 
-}  // namespace
-
-// K: candidates per thread run; chosen by the host (tuning knob), must be <= 2R+1
-cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int K, cudaStream_t st)
+template <int K, int NW, int MINB>
+cudaError_t launch_shape(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     const bool per_block = P.pred_policy == JMME_PRED_PER_BLOCK;
     const bool only16 = P.blocktype_mask == JMME_MASK_16x16;
+    if (only16 && !per_block) return launch_one<K, NW, MINB, false, true, 0>(P, num_sms, st);
+    if (per_block) return launch_one<K, NW, MINB, true, false, 0>(P, num_sms, st);
+    if (P.R == 32) return launch_one<K, NW, MINB, false, false, 80>(P, num_sms, st);   // RS of R=32
+    if (P.R == 64) return launch_one<K, NW, MINB, false, false, 144>(P, num_sms, st);  // RS of R=64
+    return launch_one<K, NW, MINB, false, false, 0>(P, num_sms, st);
+}
+
+}  // namespace
+
+// variant = 10*K + c:  K candidates per thread run (must be <= 2R+1);
+//   c = 0: 6 warps, >= 2 CTAs/SM (<= 168 registers)    c = 1: 8 warps, 1 CTA/SM (<= 255 registers)
+//   c = 2: 4 warps, >= 3 CTAs/SM (<= 168 registers)   c = 3: 10 warps, 1 CTA/SM (<= 204 registers)
+cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st)
+{
+    int K = variant / 10, c = variant % 10;
     if (K > P.ncols) K = 3;
-// K <= 3: 6 warps, 2 CTAs/SM (<=168 registers); K >= 4: 8 warps, 1 CTA/SM (<=255 registers)
-#define GO(KK, PB, O16) return launch_one<KK, (KK <= 3 ? 6 : 8), (KK <= 3 ? 2 : 1), PB, O16>(P, num_sms, st)
-#define PICK(KK)                                  \
-    if (K == KK) {                                \
-        if (only16 && !per_block) GO(KK, false, true); \
-        if (per_block) GO(KK, true, false);       \
-        GO(KK, false, false);                     \
-    }
-    PICK(2) PICK(3) PICK(4) PICK(5)
-#undef PICK
-#undef GO
+#define PICKC(KK, CC, NWW, MB) \
+    if (K == KK && c == CC) return launch_shape<KK, NWW, MB>(P, num_sms, st);
+    PICKC(2, 0, 6, 2) PICKC(3, 0, 6, 2) PICKC(4, 0, 6, 2)
+    PICKC(3, 1, 8, 1) PICKC(4, 1, 8, 1) PICKC(5, 1, 8, 1)
+    PICKC(2, 2, 4, 3) PICKC(3, 2, 4, 3) PICKC(4, 2, 4, 3)
+    PICKC(3, 3, 10, 1) PICKC(4, 3, 10, 1) PICKC(5, 3, 10, 1)
+#undef PICKC
     return cudaErrorInvalidValue;
 }

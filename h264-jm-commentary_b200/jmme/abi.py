@@ -52,7 +52,8 @@ EXPORTS = [
     "jmme_default_params", "jmme_create", "jmme_destroy", "jmme_strerror", "jmme_last_error", "jmme_backend",
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
     "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_subimage",
-    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_launch_count", "jmme_InitMotionSearchModule",
+    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_launch_count", "jmme_set_profiling",
+    "jmme_get_kernel_times", "jmme_InitMotionSearchModule",
     "jmme_getSubImagesLuma", "jmme_SATD", "jmme_SetupFastFullPelSearch", "jmme_FastFullPelBlockMotionSearch",
     "jmme_FullPelBlockMotionSearch", "jmme_SubPelBlockMotionSearch",
 ]
@@ -95,6 +96,8 @@ class Lib:
             "jmme_set_reference_dev": (i32, [vp, i32, vp, i32, vp]),
             "jmme_search_frame_dev": (i32, [vp, vp, i32, vp, vp, vp, vp]),
             "jmme_launch_count": (C.c_longlong, [vp]),
+            "jmme_set_profiling": (i32, [vp, i32]),
+            "jmme_get_kernel_times": (i32, [vp, C.POINTER(C.c_float)]),
             "jmme_InitMotionSearchModule": (i32, [i32, i32, pi32, i32, pi32, pi16, pi16]),
             "jmme_getSubImagesLuma": (i32, [pu8, i32, i32, i32, i32, pu8]),
             "jmme_SATD": (i32, [pi16, i32, i32, pi32]),
@@ -273,3 +276,12 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.dll.jmme_launch_count(self.handle))
+
+    def set_profiling(self, enable=True):
+        self.lib.check(self.lib.dll.jmme_set_profiling(self.handle, int(enable)), self.handle)
+
+    def kernel_times(self):
+        """ms of the last (interp, me_int, me_subpel, select) kernels; needs set_profiling(True)."""
+        ms = (C.c_float * 4)()
+        self.lib.check(self.lib.dll.jmme_get_kernel_times(self.handle, ms), self.handle)
+        return dict(interp=ms[0], me_int=ms[1], me_subpel=ms[2], select=ms[3])

@@ -139,6 +139,14 @@ int jmme_search_frame_dev(jmme_ctx *ctx, const void *d_cur_luma, int stride, con
                           void *d_out, void *d_out_per_ref, void *stream);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 long long jmme_launch_count(const jmme_ctx *ctx);
+/* Per-kernel device times.  jmme_set_profiling(ctx,1) makes every later set_reference / search
+ * bracket its kernels with CUDA events on the launching stream; jmme_get_kernel_times waits for
+ * the last bracket and returns milliseconds of the most recent
+ *   ms[0] quarter-pel plane kernel (a12)   ms[1] integer search kernel (a6,a7)
+ *   ms[2] sub-pel kernel (a10,a11)         ms[3] reference-selection kernel
+ * (0 for a kernel that did not run).  Single-device contexts only. */
+int jmme_set_profiling(jmme_ctx *ctx, int enable);
+int jmme_get_kernel_times(jmme_ctx *ctx, float ms[4]);
 
 /* ---- JM-named leaf entry points on plain arrays ----------------------------------------- */
 /* (a1) tables.  mvbits has 2*max_mvd+1 entries, index (v + max_mvd); refbits n_refbits;

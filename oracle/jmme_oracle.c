@@ -24,9 +24,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define MAX_MVD 4096                 /* |cand - pred| in quarter-pel units stays below this */
 #define MAX_PRED 2048                /* |pred| limit, quarter-pel                            */
+
+static int g_threads = 1;            /* worker threads, see jmme_oracle_set_threads */
 
 /* ---- block geometry (JM blc_size) -------------------------------------------- */
 static const int blc_w[8] = {0, 16, 16, 8, 8, 8, 4, 4};
@@ -145,6 +150,7 @@ static int build_planes(const uint8_t *luma, int w_in, int h_in, int stride, int
     /* samples beyond the apron are replicas of the border column/row, so clamping the tap
      * coordinate to the apron is exact */
 #define GC(xx, yy) AT(G, clampi(xx, -ap, ps + ap - 1), clampi(yy, -ap, ph + ap - 1))
+#pragma omp parallel for private(x) num_threads(g_threads)
     for (y = -ap; y < ph + ap; y++)
         for (x = -ap; x < ps + ap; x++) {
             AT(B1, x, y) = GC(x - 2, y) - 5 * GC(x - 1, y) + 20 * GC(x, y) + 20 * GC(x + 1, y)
@@ -153,6 +159,7 @@ static int build_planes(const uint8_t *luma, int w_in, int h_in, int stride, int
                            - 5 * GC(x, y + 2) + GC(x, y + 3);
         }
 #define B1C(xx, yy) AT(B1, xx, clampi(yy, -ap, ph + ap - 1))
+#pragma omp parallel for private(x) num_threads(g_threads)
     for (y = 0; y < ph + 1; y++)
         for (x = 0; x < ps + 1; x++)
             AT(J1, x, y) = B1C(x, y - 2) - 5 * B1C(x, y - 1) + 20 * B1C(x, y) + 20 * B1C(x, y + 1)
@@ -163,6 +170,7 @@ static int build_planes(const uint8_t *luma, int w_in, int h_in, int stride, int
 #define hs(xx, yy) clip255((AT(H1, xx, yy) + 16) >> 5)
 #define js(xx, yy) clip255((AT(J1, xx, yy) + 512) >> 10)
     Pb = PL(2, 0); Ph = PL(0, 2); Pj = PL(2, 2);
+#pragma omp parallel for private(x) num_threads(g_threads)
     for (y = 0; y < ph; y++)
         for (x = 0; x < ps; x++) {
             size_t o = (size_t)y * ps + x;
@@ -300,12 +308,28 @@ const char *jmme_strerror(int code)
 }
 const char *jmme_last_error(const jmme_ctx *c) { return c ? c->err : ""; }
 const char *jmme_backend(void) { return "cpu-oracle"; }
+/* oracle-only extension (not part of jmme.h): worker threads used by jmme_set_reference and
+ * jmme_search_frame.  1 = the single-threaded JM-like baseline (default); bench.py's
+ * `--impl reference` arm raises it to the host's core count.  Returns the value in effect. */
+int jmme_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n < 1) n = omp_get_num_procs();
+    g_threads = n;
+#else
+    (void)n;
+    g_threads = 1;
+#endif
+    return g_threads;
+}
 int jmme_abi_version(void) { return JMME_ABI_VERSION; }
 int jmme_mb_width(const jmme_ctx *c) { return c ? c->mb_w : 0; }
 int jmme_mb_height(const jmme_ctx *c) { return c ? c->mb_h : 0; }
 int jmme_pad(const jmme_ctx *c) { return c ? c->pad : 0; }
 int jmme_lambda_factor_of(const jmme_ctx *c) { return c ? c->lambda_factor : 0; }
 long long jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }
+int jmme_set_profiling(jmme_ctx *c, int e) { (void)e; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no kernels"); }
+int jmme_get_kernel_times(jmme_ctx *c, float ms[4]) { (void)ms; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no kernels"); }
 
 int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
 {
@@ -543,99 +567,119 @@ int jmme_SubPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *plan
 }
 
 /* ---- (a4,a5) PartitionMotionSearch / BlockMotionSearch over a frame ----------------------- */
+/* every (reference, blocktype, block) of one macroblock; bsad = scratch [41][ncand] (FASTFULL) */
+static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred, jmme_mbresult *out,
+                      jmme_mbresult *out_per_ref, int mbx, int mby, int32_t *bsad)
+{
+    const int R = c->p.search_range, nmb = c->mb_w * c->mb_h, mb = mby * c->mb_w + mbx;
+    const int npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
+    const int bonus_base = c->p.rdopt ? 0 : weighted_cost(c->lambda_factor, 16);
+    jmme_mbresult *o = &out[mb];
+    int r, t, b;
+    for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
+        o->mv[b][0] = o->mv[b][1] = 0; o->cost[b] = INT_MAX; o->ref_idx[b] = -1;
+    }
+    memset(o->reserved, 0, sizeof o->reserved);
+    for (r = 0; r < c->p.num_refs; r++) {
+        const uint8_t *ref00 = plane_at(c->planes[r], c->pstride, c->pad, 0, 0);   /* integer plane */
+        const int16_t *pr = pred ? pred + ((size_t)r * nmb + mb) * npb * 2 : NULL;
+        const int bonus = r == 0 ? bonus_base : 0;
+        jmme_mbresult *opr = out_per_ref ? &out_per_ref[(size_t)r * nmb + mb] : NULL;
+        const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
+        const int cx = clampi(p16x / 4, -R, R), cy = clampi(p16y / 4, -R, R);
+        if (opr) {
+            for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
+                opr->mv[b][0] = opr->mv[b][1] = 0; opr->cost[b] = INT_MAX; opr->ref_idx[b] = -1;
+            }
+            memset(opr->reserved, 0, sizeof opr->reserved);
+        }
+        if (c->p.search_mode == JMME_SEARCH_FASTFULL)
+            setup_fastfull(cur + (size_t)16 * mby * c->w16 + 16 * mbx, c->w16, ref00, c->pstride, mbx, mby, cx,
+                           cy, c->ncand, c->spx, c->spy, bonus, bsad);
+        for (t = 1; t <= 7; t++) {
+            const int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh;
+            int j, i;
+            if (!(c->p.blocktype_mask & (1 << t))) continue;
+            for (j = 0; j < nby; j++)
+                for (i = 0; i < nbx; i++) {
+                    const int blk = blk_base[t] + j * nbx + i;
+                    const int px = pr ? pr[(npb == 1 ? 0 : blk) * 2] : 0;
+                    const int py = pr ? pr[(npb == 1 ? 0 : blk) * 2 + 1] : 0;
+                    const int bx = 16 * mbx + i * bw, by = 16 * mby + j * bh;
+                    int mvx, mvy, cost, total;
+                    if (c->p.search_mode == JMME_SEARCH_FASTFULL) {
+                        int bp;
+                        fastfull_block(bsad + (size_t)blk * c->ncand, c->ncand, c->spx, c->spy, c->mvbits,
+                                       c->lambda_factor, cx, cy, px, py, !c->p.rdopt, &bp, &cost);
+                        mvx = cx + c->spx[bp]; mvy = cy + c->spy[bp];
+                    } else {
+                        const int bcx = clampi(px / 4, -R, R), bcy = clampi(py / 4, -R, R);
+                        full_block(cur, c->w16, ref00, c->pstride, bx, by, bw, bh, bcx, bcy, px, py, c->ncand,
+                                   c->spx, c->spy, c->mvbits, c->lambda_factor, t == 1 ? bonus : 0, &mvx, &mvy,
+                                   &cost);
+                    }
+                    mvx *= 4; mvy *= 4;
+                    if (c->p.subpel)
+                        subpel_block(cur, c->w16, c->planes[r], c->pstride, c->pheight, c->pad, bx, by, bw, bh, px,
+                                     py, c->mvbits, c->lambda_factor, c->p.use_hadamard, c->p.satd_round,
+                                     t == 1 ? bonus : 0, c->spx, c->spy, &mvx, &mvy, &cost);
+                    if (opr) {
+                        opr->mv[blk][0] = (int16_t)mvx; opr->mv[blk][1] = (int16_t)mvy;
+                        opr->cost[blk] = cost; opr->ref_idx[blk] = (int8_t)r;
+                    }
+                    total = cost + ref_cost(c, r);
+                    if (total < o->cost[blk]) {                 /* lowest ref wins ties */
+                        o->mv[blk][0] = (int16_t)mvx; o->mv[blk][1] = (int16_t)mvy;
+                        o->cost[blk] = total; o->ref_idx[blk] = (int8_t)r;
+                    }
+                }
+        }
+    }
+}
+
 int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int16_t *pred,
                       jmme_mbresult *out, jmme_mbresult *out_per_ref)
 {
-    int R, mbx, mby, r, t, x, y, rc = JMME_OK;
-    int nmb, npb, bonus_base;
+    int r, x, y, nmb, npb, n_stripe, fail = 0;
     uint8_t *cur;                    /* current picture padded to x16 by replication */
-    int32_t *bsad = NULL;
     if (!c || !cur_in || !out || stride < c->p.width) return JMME_ERR_PARAM;
     if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return set_err(c, JMME_ERR_PARAM, "pred required");
     for (r = 0; r < c->p.num_refs; r++)
         if (!c->ref_set[r]) return set_err(c, JMME_ERR_STATE, "reference not set");
-    R = c->p.search_range; nmb = c->mb_w * c->mb_h;
+    nmb = c->mb_w * c->mb_h;
     npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
-    if (pred) {
+    if (pred && c->p.pred_policy != JMME_PRED_ZERO) {
         size_t i, n = (size_t)c->p.num_refs * nmb * npb * 2;
-        if (c->p.pred_policy != JMME_PRED_ZERO)
-            for (i = 0; i < n; i++)
-                if (pred[i] > MAX_PRED || pred[i] < -MAX_PRED) return set_err(c, JMME_ERR_PARAM, "pred out of range");
+        for (i = 0; i < n; i++)
+            if (pred[i] > MAX_PRED || pred[i] < -MAX_PRED) return set_err(c, JMME_ERR_PARAM, "pred out of range");
     }
+    if (c->p.pred_policy == JMME_PRED_ZERO) pred = NULL;
     cur = (uint8_t *)malloc((size_t)c->w16 * c->h16);
-    if (c->p.search_mode == JMME_SEARCH_FASTFULL)
-        bsad = (int32_t *)malloc(sizeof(int32_t) * JMME_BLOCKS_PER_MB * (size_t)c->ncand);
-    if (!cur || (c->p.search_mode == JMME_SEARCH_FASTFULL && !bsad)) { free(cur); free(bsad); return JMME_ERR_NOMEM; }
+    if (!cur) return JMME_ERR_NOMEM;
     for (y = 0; y < c->h16; y++)
         for (x = 0; x < c->w16; x++)
-            cur[(size_t)y * c->w16 + x] = cur_in[(size_t)clampi(y, 0, c->p.height - 1) * stride + clampi(x, 0, c->p.width - 1)];
-    bonus_base = c->p.rdopt ? 0 : weighted_cost(c->lambda_factor, 16);
-
-    for (mby = c->p.mb_row_begin; mby < c->p.mb_row_end; mby++)
-        for (mbx = 0; mbx < c->mb_w; mbx++) {
-            int mb = mby * c->mb_w + mbx, b;
-            jmme_mbresult *o = &out[mb];
-            for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
-                o->mv[b][0] = o->mv[b][1] = 0; o->cost[b] = INT_MAX; o->ref_idx[b] = -1;
-            }
-            memset(o->reserved, 0, sizeof o->reserved);
-            for (r = 0; r < c->p.num_refs; r++) {
-                const uint8_t *pl0 = c->planes[r];               /* integer plane */
-                const uint8_t *ref00 = plane_at(pl0, c->pstride, c->pad, 0, 0);
-                const int16_t *pr = pred ? pred + ((size_t)r * nmb + mb) * npb * 2 : NULL;
-                int bonus = r == 0 ? bonus_base : 0;
-                jmme_mbresult *opr = out_per_ref ? &out_per_ref[(size_t)r * nmb + mb] : NULL;
-                int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
-                int cx = clampi(p16x / 4, -R, R), cy = clampi(p16y / 4, -R, R);
-                if (opr) {
-                    for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
-                        opr->mv[b][0] = opr->mv[b][1] = 0; opr->cost[b] = INT_MAX; opr->ref_idx[b] = -1;
-                    }
-                    memset(opr->reserved, 0, sizeof opr->reserved);
-                }
-                if (c->p.search_mode == JMME_SEARCH_FASTFULL)
-                    setup_fastfull(cur + (size_t)16 * mby * c->w16 + 16 * mbx, c->w16, ref00, c->pstride, mbx,
-                                   mby, cx, cy, c->ncand, c->spx, c->spy, bonus, bsad);
-                for (t = 1; t <= 7; t++) {
-                    int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh, j, i;
-                    if (!(c->p.blocktype_mask & (1 << t))) continue;
-                    for (j = 0; j < nby; j++)
-                        for (i = 0; i < nbx; i++) {
-                            int blk = blk_base[t] + j * nbx + i;
-                            int px = pr ? pr[(npb == 1 ? 0 : blk) * 2] : 0;
-                            int py = pr ? pr[(npb == 1 ? 0 : blk) * 2 + 1] : 0;
-                            int bx = 16 * mbx + i * bw, by = 16 * mby + j * bh;
-                            int mvx, mvy, cost, total;
-                            if (c->p.search_mode == JMME_SEARCH_FASTFULL) {
-                                int bp;
-                                fastfull_block(bsad + (size_t)blk * c->ncand, c->ncand, c->spx, c->spy, c->mvbits,
-                                               c->lambda_factor, cx, cy, px, py, !c->p.rdopt, &bp, &cost);
-                                mvx = cx + c->spx[bp]; mvy = cy + c->spy[bp];
-                            } else {
-                                int bcx = clampi(px / 4, -R, R), bcy = clampi(py / 4, -R, R);
-                                full_block(cur, c->w16, ref00, c->pstride, bx, by, bw, bh, bcx, bcy, px, py,
-                                           c->ncand, c->spx, c->spy, c->mvbits, c->lambda_factor,
-                                           t == 1 ? bonus : 0, &mvx, &mvy, &cost);
-                            }
-                            mvx *= 4; mvy *= 4;
-                            if (c->p.subpel)
-                                subpel_block(cur, c->w16, c->planes[r], c->pstride, c->pheight, c->pad, bx, by,
-                                             bw, bh, px, py, c->mvbits, c->lambda_factor, c->p.use_hadamard,
-                                             c->p.satd_round, t == 1 ? bonus : 0, c->spx, c->spy, &mvx, &mvy,
-                                             &cost);
-                            if (opr) {
-                                opr->mv[blk][0] = (int16_t)mvx; opr->mv[blk][1] = (int16_t)mvy;
-                                opr->cost[blk] = cost; opr->ref_idx[blk] = (int8_t)r;
-                            }
-                            total = cost + ref_cost(c, r);
-                            if (total < o->cost[blk]) {         /* lowest ref wins ties */
-                                o->mv[blk][0] = (int16_t)mvx; o->mv[blk][1] = (int16_t)mvy;
-                                o->cost[blk] = total; o->ref_idx[blk] = (int8_t)r;
-                            }
-                        }
-                }
+            cur[(size_t)y * c->w16 + x] =
+                cur_in[(size_t)clampi(y, 0, c->p.height - 1) * stride + clampi(x, 0, c->p.width - 1)];
+    n_stripe = (c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w;
+#pragma omp parallel num_threads(g_threads)
+    {
+        int i;
+        int32_t *bsad = NULL;
+        if (c->p.search_mode == JMME_SEARCH_FASTFULL) {
+            bsad = (int32_t *)malloc(sizeof(int32_t) * JMME_BLOCKS_PER_MB * (size_t)c->ncand);
+            if (!bsad) {
+#pragma omp atomic write
+                fail = 1;
             }
         }
-    free(cur); free(bsad);
-    return rc;
+#pragma omp barrier
+        if (!fail) {
+#pragma omp for schedule(dynamic, 4)
+            for (i = 0; i < n_stripe; i++)
+                search_mb(c, cur, pred, out, out_per_ref, i % c->mb_w, c->p.mb_row_begin + i / c->mb_w, bsad);
+        }
+        free(bsad);
+    }
+    free(cur);
+    return fail ? JMME_ERR_NOMEM : JMME_OK;
 }

@@ -140,10 +140,10 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("K", [3, 4])
+@pytest.mark.parametrize("variant", [30, 41])
 @pytest.mark.parametrize("w,h,R,kw", CASES)
-def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, K):
-    os.environ["JMME_K"] = str(K)
+def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
+    os.environ["JMME_VARIANT"] = str(variant)
     for kind, seed in (("texture", 1), ("noise", 2)):
         cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R, kind=kind)
         got = run(cuda, cur, refs, search_range=R, **kw)
@@ -151,11 +151,11 @@ def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, K):
         assert_same(got, exp, f"{w}x{h} R={R} {kw} {kind}")
 
 
-@pytest.mark.parametrize("K", [2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [20, 30, 40, 31, 41, 51, 22, 32, 42, 33, 43, 53])
 @pytest.mark.parametrize("policy,nb", [(abi.PRED_PER_MB, 1), (abi.PRED_PER_BLOCK, 41)])
 @pytest.mark.parametrize("rdopt", [0, 1])
-def test_predictor_policies(cuda, oracle, policy, nb, rdopt, K):
-    os.environ["JMME_K"] = str(K)
+def test_predictor_policies(cuda, oracle, policy, nb, rdopt, variant):
+    os.environ["JMME_VARIANT"] = str(variant)
     w, h, R = 64, 48, 8
     cur, refs = synth.frame_pair(w, h, seed=4, search_range=R, num_refs=2)
     pred = synth.random_pred(2, 12, nb, seed=7 + rdopt, max_qpel=4 * R + 30)   # some centres get clamped

@@ -21,7 +21,7 @@ ap.add_argument("--refs", type=int, default=1)
 ap.add_argument("--subpel", type=int, default=1)
 ap.add_argument("--mask", type=lambda s: int(s, 0), default=0xFE)
 ap.add_argument("--pred", type=int, default=0)
-ap.add_argument("--Ks", default="2,3,4,5")
+ap.add_argument("--Ks", default="20,30,40,31,41,51,22,32,42,33,43,53")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
 
@@ -30,7 +30,7 @@ cur, refs = synth.frame_pair(a.w, a.h, seed=1, search_range=a.R, num_refs=a.refs
 dcur = torch.from_numpy(cur).cuda()
 drefs = [torch.from_numpy(r).cuda() for r in refs]
 for K in [int(k) for k in a.Ks.split(",")]:
-    os.environ["JMME_K"] = str(K)
+    os.environ["JMME_VARIANT"] = str(K)
     for subpel in sorted({0, a.subpel}):
         s = DeviceSearch(lib, width=a.w, height=a.h, search_range=a.R, num_refs=a.refs, subpel=subpel,
                          blocktype_mask=a.mask, pred_policy=a.pred, qp=28)
