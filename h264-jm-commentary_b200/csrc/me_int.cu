@@ -211,10 +211,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
         const int x00 = R - cx, y00 = R - cy;            // window offsets of MV (0,0)
         const uint32_t *s_cur = s_cur2 + buf * 64;
 
+        // The current MB is the same for every lane; an opaque zero lane offset keeps ptxas from
+        // parking it in uniform registers (it then pays a UR->R move per VABSDIFF4 operand).
+        unsigned lz;
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(lz) : "r"(lane));
         uint32_t cur[16][4];
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            const uint4 v = *(const uint4 *)(s_cur + 4 * r);
+            const uint4 v = *(const uint4 *)(s_cur + lz + 4 * r);
             cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
         }
 
@@ -389,9 +393,15 @@ cudaError_t launch_shape(const SearchParams &P, int num_sms, cudaStream_t st)
 // variant = 10*K + c:  K candidates per thread run (must be <= 2R+1);
 //   c = 0: 6 warps, >= 2 CTAs/SM (<= 168 registers)    c = 1: 8 warps, 1 CTA/SM (<= 255 registers)
 //   c = 2: 4 warps, >= 3 CTAs/SM (<= 168 registers)   c = 3: 10 warps, 1 CTA/SM (<= 204 registers)
+cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st);
+
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st)
 {
     int K = variant / 10, c = variant % 10;
+    if (c >= 7) {                                   // two-threads-per-candidate kernel (me_int_tb.cu)
+        if (P.blocktype_mask != JMME_MASK_16x16 && K <= P.ncols) return jmme_launch_me_int_tb(P, num_sms, K, c, st);
+        K = 3; c = 2;                               // 16x16 only, or a window narrower than one run
+    }
     if (K > P.ncols) K = 3;
 #define PICKC(KK, CC, NWW, MB) \
     if (K == KK && c == CC) return launch_shape<KK, NWW, MB>(P, num_sms, st);

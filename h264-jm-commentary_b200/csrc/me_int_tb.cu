@@ -1,0 +1,379 @@
+// me_int_tb.cu — integer full-pel search, all 41 blocks, "two threads per candidate" mapping (sm_100a).
+//
+// Same function as me_int.cu (JM SetupFastFullPelSearch + SetupLargerBlocks +
+// FastFullPelBlockMotionSearch) and the same pipeline, window layout and
+// packed (cost,key) argmin; what changes is the thread mapping, chosen from the ncu profile of
+// me_int.cu (profiles/r01_*): one thread per candidate needs 64 (current MB) + 16K (4x4 SADs) +
+// 41 (minima) live registers, which at 12 warps/SM (168 registers) made ptxas park the current MB
+// in uniform registers and pay one UR->R move per ~1.4 VABSDIFF4.
+//
+//   thread pair  lanes l and l+16 share a run of K candidates: lane l (T) owns MB rows 0-7, lane
+//                l+16 (B) rows 8-15.  Each holds 32 words of the current MB, 8K partial SADs and 22
+//                minima (19 blocks inside its half + 16x16, 8x16 left, 8x16 right, for which the
+//                halves exchange their two 8x8 sums with SHFL.BFLY)
+//   banks        the window row stride is == 2 (mod 4) words, so the B lanes (8 rows further down)
+//                sit 16 banks away from the T lanes: 16 + 16 consecutive banks, conflict-free
+//   K            up to 8 candidates per run: 4*(7+K)/K row words per thread and candidate
+#include "jmme_dev.cuh"
+
+namespace {
+
+struct TbLayout {
+    int RS, rows, RAWW;                 // window row stride (words, == 2 mod 4), rows, raw row words
+    int off_win, off_raw, off_cur, off_T, off_best, off_key, off_bx, off_by, total_words;
+    __host__ __device__ TbLayout(int R, bool per_block)
+    {
+        const int ncols = 2 * R + 1;
+        RS = 2 * R + 13;                // word positions 0 .. 2R+12
+        while ((RS & 3) != 2) RS++;
+        rows = 2 * R + 16;
+        RAWW = ((15 + RS + 12 + 15) & ~15) >> 2;
+        off_win = 0;
+        off_raw = (off_win + rows * RS + 3) & ~3;
+        off_cur = off_raw + rows * RAWW;
+        off_T = off_cur + 2 * 64;
+        off_best = off_T + JMME_NT;
+        off_key = off_best + 48;
+        off_bx = off_key + (ncols * ncols + 1) / 2;
+        const int nb = per_block ? JMME_NBLK : 1;
+        off_by = off_bx + (nb * ncols + 3) / 4;
+        total_words = off_by + (nb * ncols + 3) / 4;
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// local block order of one half: [0] 16x8, [1,2] 8x8, [3..6] 8x4, [7..10] 4x8, [11..18] 4x4,
+// [19] 16x16, [20] 8x16 left, [21] 8x16 right;  global block = kGT[l] + half * kDL[l]
+constexpr int NL = 22;
+__device__ constexpr int kGT[NL] = {1, 5, 6, 9, 10, 11, 12, 17, 18, 19, 20, 25, 26, 27, 28, 29, 30, 31, 32, 0, 3, 4};
+__device__ constexpr int kDL[NL] = {1, 2, 2, 4, 4, 4, 4, 4, 4, 4, 4, 8, 8, 8, 8, 8, 8, 8, 8, 0, 0, 0};
+
+struct Item {
+    int ref, mbx, mby, mb, cx, cy;
+};
+
+// RS_CT: compile-time window row stride (0 = from the layout at run time): row addresses become immediates
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT>
+__global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const TbLayout L(P.R, PER_BLOCK);
+    uint32_t *s_win = smem + L.off_win;
+    uint32_t *s_raw = smem + L.off_raw;
+    uint32_t *s_cur2 = smem + L.off_cur;
+    uint32_t *s_T = smem + L.off_T;
+    uint32_t *s_best = smem + L.off_best;
+    uint16_t *s_key = (uint16_t *)(smem + L.off_key);
+    uint8_t *s_bx = (uint8_t *)(smem + L.off_bx);
+    uint8_t *s_by = (uint8_t *)(smem + L.off_by);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, l16 = lane & 15;
+    const int R = P.R, ncols = P.ncols, ncand = ncols * ncols;
+    const int RS = RS_CT ? RS_CT : L.RS;
+    const int rows = L.rows, RAWW = L.RAWW;
+    const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
+    const int n_mb = P.mb_w * P.mb_h;
+    const int n_items = n_mb_stripe * P.num_refs;
+    constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
+
+    for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
+    const int bonus_base = P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16);
+    const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
+    for (int i = tid; i < JMME_NT; i += NW * 32)
+        s_T[i] = ((unsigned)d_weighted_cost(P.lambda_factor, i) + bias) << JMME_KEY_BITS;
+    const bool pretest = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
+    int patched = -1;
+
+    // tasks: 16 consecutive columns of one run per warp; residual columns gathered several runs per warp
+    const int nruns = (ncols + K - 1) / K;
+    const int nseg = ncols >> 4;
+    const int wr = ncols - 16 * nseg;                    // 1..15 (ncols is odd)
+    const int G = 16 / wr;
+    const int n_main = nruns * nseg;
+    const int n_tasks = n_main + (nruns + G - 1) / G;
+
+    auto decode_item = [&](int item, Item &it) {
+        it.ref = item / n_mb_stripe;
+        const int mbi = item - it.ref * n_mb_stripe;
+        it.mby = P.mb_row_begin + mbi / P.mb_w;
+        it.mbx = mbi % P.mb_w;
+        it.mb = it.mby * P.mb_w + it.mbx;
+        const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
+        const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
+        it.cx = d_clamp(p16x / 4, -R, R);
+        it.cy = d_clamp(p16y / 4, -R, R);
+    };
+    auto prefetch = [&](const Item &it, int buf) {
+        const uint8_t *plane = P.planes[it.ref];
+        const int gx0 = P.pad + 16 * it.mbx + it.cx - R, gy0 = P.pad + 16 * it.mby + it.cy - R;
+        const uint8_t *g = plane + (size_t)gy0 * P.pstride + (gx0 & ~15);
+        const int nch = RAWW >> 2;
+        for (int i = tid; i < rows * nch; i += NW * 32) {
+            const int row = i / nch, c = i - row * nch;
+            cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
+        }
+        if (tid < 16)
+            cp_async16(s_cur2 + buf * 64 + 4 * tid, P.cur + (size_t)(16 * it.mby + tid) * P.cur_stride + 16 * it.mbx);
+        cp_async_commit();
+    };
+    auto expand = [&](const Item &it) {
+        const int gx0 = P.pad + 16 * it.mbx + it.cx - R;
+        const int t16 = gx0 & 15, np = RS >> 1;          // word pairs per row (RS is even)
+        for (int i = tid; i < rows * np; i += NW * 32) {
+            const int row = i / np, x = 2 * (i - row * np);
+            const uint32_t *raw = s_raw + row * RAWW;
+            const int o0 = t16 + x, o1 = o0 + 1;
+            uint2 v;
+            v.x = __funnelshift_r(raw[o0 >> 2], raw[(o0 >> 2) + 1], (o0 & 3) * 8);
+            v.y = __funnelshift_r(raw[o1 >> 2], raw[(o1 >> 2) + 1], (o1 & 3) * 8);
+            *(uint2 *)(s_win + row * RS + x) = v;
+        }
+        if (tid < 48) s_best[tid] = 0xFFFFFFFFu;
+        const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
+        for (int i = tid; i < NPB * ncols; i += NW * 32) {
+            const int b = i / ncols, o = i - b * ncols;
+            const int px = pr ? pr[2 * b] : 0, py = pr ? pr[2 * b + 1] : 0;
+            s_bx[i] = (uint8_t)d_se_bits(4 * (it.cx + o - R) - px);
+            s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + o - R) - py);
+        }
+        const int idx00 = (R - it.cy) * ncols + (R - it.cx);
+        if (pretest && tid == 0) {                       // "(0,0) first": key 0 wins every tie
+            if (patched >= 0 && patched != idx00) s_key[patched] = P.spiral_key[patched];
+            s_key[idx00] = 0;
+        }
+        if (pretest) patched = idx00;
+    };
+
+    Item cur_it, nxt_it;
+    int item = blockIdx.x, buf = 0;
+    if (item >= n_items) return;
+    decode_item(item, cur_it);
+    prefetch(cur_it, 0);
+    cp_async_wait_all();
+    __syncthreads();
+    expand(cur_it);
+    __syncthreads();
+
+    for (; item < n_items; item += gridDim.x) {
+        const int nxt = item + gridDim.x;
+        const bool has_next = nxt < n_items;
+        if (has_next) {
+            decode_item(nxt, nxt_it);
+            prefetch(nxt_it, buf ^ 1);
+        }
+        const int cx = cur_it.cx, cy = cur_it.cy;
+        const int bonus = (cur_it.ref == 0) ? bonus_base : 0;
+        const int x00 = R - cx, y00 = R - cy;
+        const uint32_t *s_cur = s_cur2 + buf * 64;
+
+        // The current MB is the same for every lane; an opaque zero lane offset keeps ptxas from
+        // parking it in uniform registers (it then pays a UR->R move per VABSDIFF4 operand).
+        unsigned lz;
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(lz) : "r"(lane));
+        uint32_t cur[8][4];                              // this half's 8 rows of the current MB
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const uint4 v = *(const uint4 *)(s_cur + lz + 4 * (8 * half + r));
+            cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
+        }
+
+        if (bonus != 0 && warp == 0) {                   // 16x16 at MV (0,0) with its bonus
+            unsigned s = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int i = lane + 32 * h, row = i >> 2, j = i & 3;
+                s = sad4(s_cur[i], s_win[(y00 + row) * RS + x00 + 4 * j], s);
+            }
+            s = __reduce_add_sync(0xFFFFFFFFu, s);
+            if (lane == 0) {
+                const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + s_key[y00 * ncols + x00] -
+                                   ((unsigned)bonus << JMME_KEY_BITS);
+                atomicMin(&s_best[0], v);
+            }
+        }
+
+        uint32_t best[NL];
+#pragma unroll
+        for (int b = 0; b < NL; b++) best[b] = 0xFFFFFFFFu;
+
+        for (int task = warp; task < n_tasks; task += NW) {
+            int run, xoff;
+            if (task < n_main) {
+                run = task / nseg;
+                xoff = 16 * (task - run * nseg) + l16;
+            } else {
+                int g = l16 / wr, x = l16 - g * wr;
+                if (g >= G) { g = 0; x = 0; }            // idle lanes repeat lane 0 (idempotent)
+                run = min((task - n_main) * G + g, nruns - 1);
+                xoff = 16 * nseg + x;
+            }
+            const int ybase = min(run * K, ncols - K);
+            const uint32_t *base = s_win + (ybase + 8 * half) * RS + xoff;
+
+            unsigned acc[K][8];
+#pragma unroll
+            for (int k = 0; k < K; k++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[k][i] = 0;
+
+            const unsigned bx0 = s_bx[xoff];
+            auto pack = [&](int k, unsigned (&pk)[NL]) {
+                const int yoff = ybase + k;
+                const unsigned key = s_key[yoff * ncols + xoff];
+                unsigned o[NL];
+                const unsigned(&s)[8] = acc[k];
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[11 + i] = s[i];                         // 4x4
+#pragma unroll
+                for (int i = 0; i < 4; i++) o[7 + i] = s[i] + s[4 + i];               // 4x8
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) o[3 + 2 * j + i] = s[4 * j + 2 * i] + s[4 * j + 2 * i + 1];   // 8x4
+                o[1] = o[3] + o[5];                                                   // 8x8 left, right
+                o[2] = o[4] + o[6];
+                o[0] = o[1] + o[2];                                                   // 16x8
+                const unsigned pl = __shfl_xor_sync(0xFFFFFFFFu, o[1], 16);          // the other half's 8x8 sums
+                const unsigned pr8 = __shfl_xor_sync(0xFFFFFFFFu, o[2], 16);
+                o[20] = o[1] + pl;                                                    // 8x16 left
+                o[21] = o[2] + pr8;                                                   // 8x16 right
+                o[19] = o[20] + o[21];                                                // 16x16
+                if constexpr (!PER_BLOCK) {
+                    const unsigned kr = s_T[bx0 + s_by[yoff]] + key;
+#pragma unroll
+                    for (int b = 0; b < NL; b++) pk[b] = (o[b] << JMME_KEY_BITS) + kr;
+                } else {
+#pragma unroll
+                    for (int b = 0; b < NL; b++) {
+                        const int gb = kGT[b] + half * kDL[b];
+                        pk[b] = (o[b] << JMME_KEY_BITS) + s_T[s_bx[gb * ncols + xoff] + s_by[gb * ncols + yoff]] + key;
+                    }
+                }
+            };
+
+            // Row loop.  Candidate k is complete after row 7+k; its partition sums, packs (FMA pipe) and
+            // minima are emitted right there, between the VABSDIFF4 (ALU pipe) of the later candidates,
+            // two candidates at a time so that min(best, min(a, b)) is one VIMNMX3.
+#pragma unroll
+            for (int rr = 0; rr < 8 + K - 1; rr++) {
+                const uint32_t *rp = base + rr * RS;
+                const unsigned r0 = rp[0], r1 = rp[4], r2 = rp[8], r3 = rp[12];
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const int cr = rr - k;
+                    if (cr >= 0 && cr < 8) {
+                        const int a = (cr >> 2) * 4;
+                        acc[k][a + 0] = sad4(cur[cr][0], r0, acc[k][a + 0]);
+                        acc[k][a + 1] = sad4(cur[cr][1], r1, acc[k][a + 1]);
+                        acc[k][a + 2] = sad4(cur[cr][2], r2, acc[k][a + 2]);
+                        acc[k][a + 3] = sad4(cur[cr][3], r3, acc[k][a + 3]);
+                    }
+                }
+                const int kc = rr - 7;                   // candidate completed by this row
+                if (kc >= 1 && (kc & 1)) {
+                    unsigned pa[NL], pb[NL];
+                    pack(kc - 1, pa);
+                    pack(kc, pb);
+#pragma unroll
+                    for (int b = 0; b < NL; b++) best[b] = min(best[b], min(pa[b], pb[b]));
+                } else if (kc == K - 1 && !(kc & 1)) {
+                    unsigned pa[NL];
+                    pack(kc, pa);
+#pragma unroll
+                    for (int b = 0; b < NL; b++) best[b] = min(best[b], pa[b]);
+                }
+            }
+        }
+
+        // ---- reduce: per half over its 16 lanes (the other half contributes the identity), lane b
+        //      keeps global block b, two shared atomicMin per warp ---------------------------------
+        {
+            unsigned m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+            auto keep = [&](int gb, unsigned m) {
+                if (gb < 32) m0 = (lane == gb) ? m : m0;
+                else m1 = (lane == gb - 32) ? m : m1;
+            };
+#pragma unroll
+            for (int b = 0; b < NL; b++) {
+                if (kDL[b] == 0) {
+                    keep(kGT[b], __reduce_min_sync(0xFFFFFFFFu, best[b]));
+                } else {
+                    keep(kGT[b], __reduce_min_sync(0xFFFFFFFFu, half == 0 ? best[b] : 0xFFFFFFFFu));
+                    keep(kGT[b] + kDL[b], __reduce_min_sync(0xFFFFFFFFu, half == 1 ? best[b] : 0xFFFFFFFFu));
+                }
+            }
+            atomicMin(&s_best[lane], m0);
+            if (lane < JMME_NBLK - 32) atomicMin(&s_best[32 + lane], m1);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid < JMME_NBLK) {
+            const unsigned v = s_best[tid];
+            const unsigned key = v & JMME_KEY_MASK;
+            int mvx = 0, mvy = 0;
+            if (key) {
+                mvx = cx + P.spiral_xy[2 * (key - 1)];
+                mvy = cy + P.spiral_xy[2 * (key - 1) + 1];
+            }
+            BlkRes r;
+            r.mvx = (int16_t)(4 * mvx);
+            r.mvy = (int16_t)(4 * mvy);
+            r.cost = (int)(v >> JMME_KEY_BITS) - (int)bias;
+            P.res[((size_t)cur_it.ref * n_mb + cur_it.mb) * JMME_NBLK + tid] = r;
+        }
+        if (!has_next) break;
+        __syncthreads();
+        expand(nxt_it);
+        __syncthreads();
+        cur_it = nxt_it;
+        buf ^= 1;
+    }
+}
+
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT>
+cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
+{
+    TbLayout L(P.R, PER_BLOCK);
+    size_t bytes = (size_t)L.total_words * 4;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
+    int grid = min(n_items, num_sms * occ);
+    kern<<<grid, NW * 32, bytes, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// shape 7: 4 warps, >= 4 CTAs/SM (<= 128 registers)   shape 8: 4 warps, >= 3 CTAs/SM (<= 168 registers)
+// shape 9: 8 warps, >= 2 CTAs/SM (<= 128 registers)
+cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st)
+{
+    const bool pb = P.pred_policy == JMME_PRED_PER_BLOCK;
+    if (K > P.ncols) K = 2;
+#define TB(KK, SH, NWW, MB)                                                               \
+    if (K == KK && shape == SH) {                                                         \
+        if (pb) return launch_tb<KK, NWW, MB, true, 0>(P, num_sms, st);                   \
+        if (P.R == 32) return launch_tb<KK, NWW, MB, false, 78>(P, num_sms, st);          \
+        if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142>(P, num_sms, st);         \
+        return launch_tb<KK, NWW, MB, false, 0>(P, num_sms, st);                          \
+    }
+    TB(2, 7, 4, 4) TB(4, 7, 4, 4) TB(5, 7, 4, 4) TB(6, 7, 4, 4)
+    TB(4, 8, 4, 3) TB(6, 8, 4, 3) TB(8, 8, 4, 3)
+    TB(4, 9, 8, 2) TB(6, 9, 8, 2)
+#undef TB
+    return cudaErrorInvalidValue;
+}

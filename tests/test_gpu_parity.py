@@ -140,7 +140,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [30, 41])
+@pytest.mark.parametrize("variant", [32, 67, 88])
 @pytest.mark.parametrize("w,h,R,kw", CASES)
 def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
     os.environ["JMME_VARIANT"] = str(variant)
@@ -151,7 +151,7 @@ def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
         assert_same(got, exp, f"{w}x{h} R={R} {kw} {kind}")
 
 
-@pytest.mark.parametrize("variant", [20, 30, 40, 31, 41, 51, 22, 32, 42, 33, 43, 53])
+@pytest.mark.parametrize("variant", [30, 31, 51, 22, 32, 42, 27, 47, 57, 67, 48, 68, 88, 49, 69])
 @pytest.mark.parametrize("policy,nb", [(abi.PRED_PER_MB, 1), (abi.PRED_PER_BLOCK, 41)])
 @pytest.mark.parametrize("rdopt", [0, 1])
 def test_predictor_policies(cuda, oracle, policy, nb, rdopt, variant):
