@@ -4,12 +4,7 @@
 // Stands in for JM's SubPelBlockMotionSearch with SATD ‖ HadamardSAD4x4
 // (a11) and the REF_COST comparison of PartitionMotionSearch's caller (a4).  Conventions: DESIGN.md §2.
 //
-// Mapping: one CTA per (reference, macroblock).  A work unit is one 4x4 cell of one blocktype at
-// one of the 9 (half-pel) / 8 (quarter-pel) candidate positions: the unit fetches its 4x4 reference
-// samples from the quarter-pel plane selected by the candidate's fractional phase, forms the
-// difference with the current MB (held in shared memory), applies the 4x4 Hadamard transform in
-// registers and adds |coefficients|/2 to the (block, position) cost in shared memory.  Thread b < 41
-// then adds the MV rate, takes the strict-< minimum in position order and publishes the winner.
+// Mapping: one CTA per (reference, macroblock), thread = (blocktype, 4x4 cell); see me_subpel_kernel.
 #include "jmme_dev.cuh"
 
 namespace {
@@ -48,14 +43,20 @@ __device__ __forceinline__ int satd16(const int (&d)[16], int satd_round)
     return satd_round ? (s + 1) >> 1 : s >> 1;
 }
 
-__global__ void __launch_bounds__(256) me_subpel_kernel(const SearchParams P)
-{
-    __shared__ uint8_t s_cur[16][16];
-    __shared__ int s_cost[JMME_NBLK][9];
-    __shared__ int s_mvx[JMME_NBLK], s_mvy[JMME_NBLK], s_min[JMME_NBLK];
-    __shared__ int s_px[JMME_NBLK], s_py[JMME_NBLK];
+// need[t]: XOR offsets (within the 16 cells of an MB, cell = 4*cy4 + cx4) that gather the cells of one
+// block of blocktype t: 16x16 all, 16x8 {1,2,4}, 8x16 {1,4,8}, 8x8 {1,4}, 8x4 {1}, 4x8 {4}, 4x4 none
+__device__ __forceinline__ int need_of_type(int t) { return (0x0415D7F0u >> (4 * t)) & 15; }
 
-    const int tid = threadIdx.x;
+// One CTA (4 warps) per (reference, macroblock).  Thread = (blocktype, 4x4 cell): half-warp h of warp w
+// owns blocktype 2w+h+1 (the last half-warp is idle), lane&15 is the cell.  For each candidate
+// position the thread computes its cell's SATD (or SAD) from four unaligned 32-bit reference reads,
+// the cells of a block are summed with a masked XOR-shuffle butterfly, and every lane of the block
+// runs the same strict-< scan over the positions — no shared memory, no barriers, no atomics.
+__global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = 2 * warp + (lane >> 4) + 1;            // blocktype 1..7 (8 = idle)
+    const int cell = lane & 15, cx4 = cell & 3, cy4 = cell >> 2;
     const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
     const int item = blockIdx.x;
@@ -63,81 +64,83 @@ __global__ void __launch_bounds__(256) me_subpel_kernel(const SearchParams P)
     const int mbi = item - ref * n_mb_stripe;
     const int mby = P.mb_row_begin + mbi / P.mb_w, mbx = mbi % P.mb_w;
     const int mb = mby * P.mb_w + mbx;
+    const bool active = t <= 7 && ((P.blocktype_mask >> t) & 1);
+    const int b = t <= 7 ? block_of_cell(t, cx4, cy4) : 0;
+    const int need = t <= 7 ? need_of_type(t) : 0;
     BlkRes *res = P.res + ((size_t)ref * n_mb + mb) * JMME_NBLK;
-    const int bonus = (!P.rdopt && ref == 0) ? d_weighted_cost(P.lambda_factor, 16) : 0;
+    const int bonus = (!P.rdopt && ref == 0 && b == 0) ? d_weighted_cost(P.lambda_factor, 16) : 0;
     const size_t psz = (size_t)P.pstride * P.pheight;
     const uint8_t *planes = P.planes[ref];
 
-    if (tid < 64) {
-        int row = tid >> 2, w = tid & 3;
-        *(uint32_t *)&s_cur[row][4 * w] =
-            *(const uint32_t *)(P.cur + (size_t)(16 * mby + row) * P.cur_stride + 16 * mbx + 4 * w);
+    // this cell of the current MB, as 16 ints
+    int c[16];
+    {
+        const uint8_t *cp = P.cur + (size_t)(16 * mby + 4 * cy4) * P.cur_stride + 16 * mbx + 4 * cx4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            const uint32_t w = *(const uint32_t *)(cp + (size_t)y * P.cur_stride);
+            c[4 * y] = w & 255; c[4 * y + 1] = (w >> 8) & 255; c[4 * y + 2] = (w >> 16) & 255; c[4 * y + 3] = w >> 24;
+        }
     }
-    if (tid < JMME_NBLK) {
-        BlkRes r = res[tid];
-        s_mvx[tid] = r.mvx; s_mvy[tid] = r.mvy;
-        s_min[tid] = P.use_hadamard ? INT_MAX : r.cost;
-        int npb = P.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
-        const int16_t *pr = P.pred ? P.pred + ((size_t)ref * n_mb + mb) * npb * 2 : nullptr;
-        int pb = npb == 1 ? 0 : tid;
-        s_px[tid] = pr ? pr[2 * pb] : 0;
-        s_py[tid] = pr ? pr[2 * pb + 1] : 0;
+    int mvx, mvy, mn, px = 0, py = 0;
+    {
+        const BlkRes r = res[b];
+        mvx = r.mvx; mvy = r.mvy;
+        mn = P.use_hadamard ? INT_MAX : r.cost;
+        if (P.pred) {
+            const int npb = P.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
+            const int16_t *pr = P.pred + ((size_t)ref * n_mb + mb) * npb * 2 + (npb == 1 ? 0 : 2 * b);
+            px = pr[0]; py = pr[1];
+        }
     }
+    // reference position of this cell at MV (0,0), in padded-plane coordinates
+    const int rx0 = P.pad + 16 * mbx + 4 * cx4, ry0 = P.pad + 16 * mby + 4 * cy4;
 
     for (int step = 2; step >= 1; step--) {
         const int pos0 = (step == 2 && P.use_hadamard) ? 0 : 1;
-        for (int i = tid; i < JMME_NBLK * 9; i += 256) (&s_cost[0][0])[i] = 0;
-        __syncthreads();
-        // units: (pos, blocktype, cell)
-        const int n_units = 9 * 7 * 16;
-        for (int u = tid; u < n_units; u += 256) {
-            const int pos = u / 112, rem = u - pos * 112;
-            const int t = 1 + rem / 16, cell = rem & 15;
-            if (pos < pos0 || !(P.blocktype_mask & (1 << t))) continue;
-            const int cx4 = cell & 3, cy4 = cell >> 2;
-            const int b = block_of_cell(t, cx4, cy4);
-            const int qx = s_mvx[b] + step * c_sp9[pos][0], qy = s_mvy[b] + step * c_sp9[pos][1];
-            const uint8_t *rp = planes + psz * ((qy & 3) * 4 + (qx & 3)) +
-                                (size_t)(P.pad + 16 * mby + 4 * cy4 + (qy >> 2)) * P.pstride +
-                                (P.pad + 16 * mbx + 4 * cx4 + (qx >> 2));
-            int d[16];
+        const int ox = mvx, oy = mvy;
+        int best = 0;
+        for (int pos = pos0; pos < 9; pos++) {
+            const int qx = ox + step * c_sp9[pos][0], qy = oy + step * c_sp9[pos][1];
+            int v = 0;
+            if (active) {
+                const size_t off = psz * ((qy & 3) * 4 + (qx & 3)) + (size_t)(ry0 + (qy >> 2)) * P.pstride + (rx0 + (qx >> 2));
+                const uint32_t *rp = (const uint32_t *)(planes + (off & ~(size_t)3));
+                const int sh = (int)(off & 3) * 8, pw = P.pstride >> 2;
+                int d[16];
 #pragma unroll
-            for (int y = 0; y < 4; y++)
+                for (int y = 0; y < 4; y++) {
+                    const uint32_t w = __funnelshift_r(__ldg(rp + y * pw), __ldg(rp + y * pw + 1), sh);
+                    d[4 * y] = c[4 * y] - (int)(w & 255);
+                    d[4 * y + 1] = c[4 * y + 1] - (int)((w >> 8) & 255);
+                    d[4 * y + 2] = c[4 * y + 2] - (int)((w >> 16) & 255);
+                    d[4 * y + 3] = c[4 * y + 3] - (int)(w >> 24);
+                }
+                if (P.use_hadamard) {
+                    v = satd16(d, P.satd_round);
+                } else {
 #pragma unroll
-                for (int x = 0; x < 4; x++)
-                    d[4 * y + x] = (int)s_cur[4 * cy4 + y][4 * cx4 + x] - (int)__ldg(rp + (size_t)y * P.pstride + x);
-            int v;
-            if (P.use_hadamard) {
-                v = satd16(d, P.satd_round);
-            } else {
-                v = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) v += abs(d[k]);
+                    for (int k = 0; k < 16; k++) v += abs(d[k]);
+                }
             }
-            atomicAdd(&s_cost[b][pos], v);
-        }
-        __syncthreads();
-        if (tid < JMME_NBLK) {
-            const int b = tid;
-            int mn = s_min[b], best = 0;
-            const int ox = s_mvx[b], oy = s_mvy[b];
-            for (int pos = pos0; pos < 9; pos++) {
-                const int qx = ox + step * c_sp9[pos][0], qy = oy + step * c_sp9[pos][1];
-                int c = d_weighted_cost(P.lambda_factor, d_se_bits(qx - s_px[b]) + d_se_bits(qy - s_py[b])) +
-                        s_cost[b][pos];
-                if (b == 0 && qx == 0 && qy == 0) c -= bonus;
-                if (c < mn) { mn = c; best = pos; }
+            // sum the cells of this block: masked XOR butterfly inside the half-warp
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const int u = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                if (need & o) v += u;
             }
-            s_min[b] = mn;
-            s_mvx[b] = ox + step * c_sp9[best][0];
-            s_mvy[b] = oy + step * c_sp9[best][1];
+            int cst = d_weighted_cost(P.lambda_factor, d_se_bits(qx - px) + d_se_bits(qy - py)) + v;
+            if (qx == 0 && qy == 0) cst -= bonus;
+            if (cst < mn) { mn = cst; best = pos; }
         }
-        __syncthreads();
+        mvx = ox + step * c_sp9[best][0];
+        mvy = oy + step * c_sp9[best][1];
     }
-    if (tid < JMME_NBLK) {
+    // the lane that owns the block's top-left cell publishes the result
+    if (active && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2)) {
         BlkRes r;
-        r.mvx = (int16_t)s_mvx[tid]; r.mvy = (int16_t)s_mvy[tid]; r.cost = s_min[tid];
-        res[tid] = r;
+        r.mvx = (int16_t)mvx; r.mvy = (int16_t)mvy; r.cost = mn;
+        res[b] = r;
     }
 }
 
@@ -179,7 +182,7 @@ __global__ void select_ref_kernel(const SearchParams P)
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
 {
     int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
-    me_subpel_kernel<<<n_items, 256, 0, st>>>(P);
+    me_subpel_kernel<<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
 }
 
