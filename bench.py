@@ -45,12 +45,6 @@ OPS_PER_CAND_16 = 66
 QP = 28
 
 
-def stripe_of(rank, world, mb_h):
-    base, rem = divmod(mb_h, world)
-    b = rank * base + min(rank, rem)
-    return b, b + base + (1 if rank < rem else 0)
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -204,6 +198,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import jmme
     from jmme import abi, synth
+    from jmme.dist import StripeGather, stripe_of
     from jmme.torch_api import DeviceSearch
 
     if not torch.cuda.is_available():
@@ -219,24 +214,20 @@ def run_ours(args, rank, world, local_rank):
     cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
     d_cur = torch.from_numpy(cur).cuda()
     d_refs = [torch.from_numpy(r).cuda() for r in ref_l]
+    if re <= rb:
+        raise SystemExit(f"rank {rank}: empty stripe — {mb_h} MB rows cannot feed {world} ranks of {-(-mb_h // world)} rows")
     ds = DeviceSearch(lib, width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
                       mb_row_begin=rb, mb_row_end=re)
     ds.ctx.set_profiling(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     rec = abi.MBRESULT_DTYPE.itemsize
-    max_rows = -(-mb_h // world)
-    gather_in = torch.zeros(max_rows * mb_w * rec, dtype=torch.uint8, device="cuda") if world > 1 else None
-    gather_out = torch.zeros(world * max_rows * mb_w * rec, dtype=torch.uint8, device="cuda") if world > 1 else None
+    gather = StripeGather(mb_w, mb_h, "cuda")          # the search writes its stripe straight into the field
 
     def step_device():
         for i, r in enumerate(d_refs):
             ds.set_reference(i, r)
-        out = ds.search(d_cur)
-        if world > 1:                     # MV-field gather over NVLink (the only collective of the path)
-            n = (re - rb) * mb_w * rec
-            gather_in[:n].copy_(out.view(-1)[rb * mb_w * rec: rb * mb_w * rec + n])
-            dist.all_gather_into_tensor(gather_out, gather_in)
-        return out
+        ds.search(d_cur, out=gather.field)
+        return gather.gather()            # N > 1: one in-place all-gather over NVLink, the only collective
 
     def barrier():
         torch.cuda.synchronize()
@@ -297,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # parity guard: the host path and the device path must agree byte for byte on this rank's stripe
-    got = ds.to_numpy(ds.out)[rb * mb_w:re * mb_w]
+    got = ds.to_numpy(gather.frame())[rb * mb_w:re * mb_w]
     exp = h_out.numpy().view(abi.MBRESULT_DTYPE)[rb * mb_w:re * mb_w]
     assert got.tobytes() == exp.tobytes(), "device-resident and host-buffer paths disagree"
 

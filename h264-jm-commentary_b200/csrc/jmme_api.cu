@@ -128,7 +128,7 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
     c->n_planes = p->subpel ? 16 : 1;
     c->ncols = 2 * p->search_range + 1; c->ncand = c->ncols * c->ncols;
     const char *ek = getenv("JMME_VARIANT");      // tuning knob: 10*K + launch shape, see me_int.cu
-    c->K = ek ? atoi(ek) : 68;
+    c->K = ek ? atoi(ek) : 0;                      // 0 = choose by search range
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

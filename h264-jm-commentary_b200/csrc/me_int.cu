@@ -364,14 +364,23 @@ cudaError_t launch_one(const SearchParams &P, int num_sms, cudaStream_t st)
     SmemLayout<PER_BLOCK> L(P.R);
     size_t bytes = (size_t)L.total_words * 4;
     auto kern = me_int_kernel<K, NW, MINB, PER_BLOCK, ONLY16, RS_CT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
+    static thread_local int c_dev = -1, c_occ = 0;
+    static thread_local size_t c_bytes = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (dev != c_dev || bytes != c_bytes) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        c_dev = dev; c_bytes = bytes; c_occ = occ;
+    }
     int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
-    int grid = min(n_items, num_sms * occ);
+    int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
 }
@@ -397,6 +406,7 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st)
 {
+    if (variant <= 0) variant = P.R <= 32 ? 68 : 51;   // default: measured best per search range
     int K = variant / 10, c = variant % 10;
     if (c >= 7) {                                   // two-threads-per-candidate kernel (me_int_tb.cu)
         if (P.blocktype_mask != JMME_MASK_16x16 && K <= P.ncols) return jmme_launch_me_int_tb(P, num_sms, K, c, st);

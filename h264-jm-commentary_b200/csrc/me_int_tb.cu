@@ -21,7 +21,7 @@ namespace {
 struct TbLayout {
     int RS, rows, RAWW;                 // window row stride (words, == 2 mod 4), rows, raw row words
     int off_win, off_raw, off_cur, off_T, off_best, off_key, off_bx, off_by, total_words;
-    __host__ __device__ TbLayout(int R, bool per_block)
+    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem)
     {
         const int ncols = 2 * R + 1;
         RS = 2 * R + 13;                // word positions 0 .. 2R+12
@@ -34,7 +34,7 @@ struct TbLayout {
         off_T = off_cur + 2 * 64;
         off_best = off_T + JMME_NT;
         off_key = off_best + 48;
-        off_bx = off_key + (ncols * ncols + 1) / 2;
+        off_bx = off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0);
         const int nb = per_block ? JMME_NBLK : 1;
         off_by = off_bx + (nb * ncols + 3) / 4;
         total_words = off_by + (nb * ncols + 3) / 4;
@@ -60,11 +60,13 @@ struct Item {
 };
 
 // RS_CT: compile-time window row stride (0 = from the layout at run time): row addresses become immediates
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT>
+// KEYG: read the spiral keys from global memory (L1) instead of a shared-memory copy — frees 33 KB at R = 64
+// so that two CTAs fit on an SM
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const TbLayout L(P.R, PER_BLOCK);
+    const TbLayout L(P.R, PER_BLOCK, !KEYG);
     uint32_t *s_win = smem + L.off_win;
     uint32_t *s_raw = smem + L.off_raw;
     uint32_t *s_cur2 = smem + L.off_cur;
@@ -84,7 +86,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int n_items = n_mb_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
-    for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
+    if (!KEYG)
+        for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
     const int bonus_base = P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16);
     const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
     for (int i = tid; i < JMME_NT; i += NW * 32)
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + o - R) - py);
         }
         const int idx00 = (R - it.cy) * ncols + (R - it.cx);
-        if (pretest && tid == 0) {                       // "(0,0) first": key 0 wins every tie
+        if (!KEYG && pretest && tid == 0) {              // "(0,0) first": key 0 wins every tie
             if (patched >= 0 && patched != idx00) s_key[patched] = P.spiral_key[patched];
             s_key[idx00] = 0;
         }
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             }
             s = __reduce_add_sync(0xFFFFFFFFu, s);
             if (lane == 0) {
-                const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + s_key[y00 * ncols + x00] -
+                const unsigned k00 = pretest ? 0u : (unsigned)P.spiral_key[y00 * ncols + x00];
+                const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + k00 -
                                    ((unsigned)bonus << JMME_KEY_BITS);
                 atomicMin(&s_best[0], v);
             }
@@ -227,7 +231,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             const unsigned bx0 = s_bx[xoff];
             auto pack = [&](int k, unsigned (&pk)[NL]) {
                 const int yoff = ybase + k;
-                const unsigned key = s_key[yoff * ncols + xoff];
+                unsigned key;
+                if constexpr (KEYG) {
+                    const int ki = yoff * ncols + xoff;
+                    key = (ki == patched) ? 0u : (unsigned)__ldg(P.spiral_key + ki);    // patched = MV (0,0) pre-test
+                } else {
+                    key = s_key[yoff * ncols + xoff];
+                }
                 unsigned o[NL];
                 const unsigned(&s)[8] = acc[k];
 #pragma unroll
@@ -338,20 +348,29 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT>
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
-    TbLayout L(P.R, PER_BLOCK);
+    TbLayout L(P.R, PER_BLOCK, !KEYG);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG>;
+    // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
+    static thread_local int c_dev = -1, c_occ = 0;
+    static thread_local size_t c_bytes = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
+    if (dev != c_dev || bytes != c_bytes) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        c_dev = dev; c_bytes = bytes; c_occ = occ;
+    }
     int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
-    int grid = min(n_items, num_sms * occ);
+    int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
 }
@@ -359,21 +378,21 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 }  // namespace
 
 // shape 7: 4 warps, >= 4 CTAs/SM (<= 128 registers)   shape 8: 4 warps, >= 3 CTAs/SM (<= 168 registers)
-// shape 9: 8 warps, >= 2 CTAs/SM (<= 128 registers)
+// shape 9: 6 warps, >= 2 CTAs/SM (<= 168 registers), spiral keys read from global memory: the shape for
+//          R > 32, where the window (80 KB at R = 64) leaves room for only two CTAs per SM
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st)
 {
     const bool pb = P.pred_policy == JMME_PRED_PER_BLOCK;
-    if (K > P.ncols) K = 2;
-#define TB(KK, SH, NWW, MB)                                                               \
-    if (K == KK && shape == SH) {                                                         \
-        if (pb) return launch_tb<KK, NWW, MB, true, 0>(P, num_sms, st);                   \
-        if (P.R == 32) return launch_tb<KK, NWW, MB, false, 78>(P, num_sms, st);          \
-        if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142>(P, num_sms, st);         \
-        return launch_tb<KK, NWW, MB, false, 0>(P, num_sms, st);                          \
+#define TB(KK, SH, NWW, MB, KG)                                                            \
+    if (K == KK && shape == SH) {                                                          \
+        if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
+        if (P.R == 32) return launch_tb<KK, NWW, MB, false, 78, KG>(P, num_sms, st);       \
+        if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142, KG>(P, num_sms, st);      \
+        return launch_tb<KK, NWW, MB, false, 0, KG>(P, num_sms, st);                       \
     }
-    TB(2, 7, 4, 4) TB(4, 7, 4, 4) TB(5, 7, 4, 4) TB(6, 7, 4, 4)
-    TB(4, 8, 4, 3) TB(6, 8, 4, 3) TB(8, 8, 4, 3)
-    TB(4, 9, 8, 2) TB(6, 9, 8, 2)
+    TB(4, 7, 4, 4, false) TB(5, 7, 4, 4, false)
+    TB(4, 8, 4, 3, false) TB(6, 8, 4, 3, false) TB(8, 8, 4, 3, false)
+    TB(4, 9, 6, 2, true) TB(6, 9, 6, 2, true) TB(8, 9, 6, 2, true)
 #undef TB
     return cudaErrorInvalidValue;
 }

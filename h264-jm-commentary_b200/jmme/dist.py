@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing of the search: MB-row stripes (one per rank) and the single collective of the
+path, an all-gather of the MV field (torch.distributed: NCCL over NVLink on GPUs, gloo in CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import abi
+
+REC = abi.MBRESULT_DTYPE.itemsize
+
+
+def stripe_of(rank: int, world: int, mb_h: int):
+    """Contiguous MB rows [begin, end) of `rank`.  Every stripe has ceil(mb_h/world) rows except the
+    last non-empty one: the largest stripe is as small as an even split would make
+    it, and rank r's rows start at r*ceil(mb_h/world), so that the stripes, padded to that size, tile
+    the all-gather buffer in frame order and the gather needs no re-packing.  A rank past the end of
+    the frame gets an empty stripe (begin == end)."""
+    rows = -(-mb_h // world)
+    b = min(rank * rows, mb_h)
+    return b, min(b + rows, mb_h)
+
+
+class StripeGather:
+    """All-gather of the per-rank stripes of jmme_mbresult records into the whole-frame MV field.
+
+    `field` is a uint8 tensor [world * rows_per_rank * mb_w, 372] whose first mb_w*mb_h records are the
+    frame; rank r's stripe is chunk r.  A rank lets its search write straight into `field` (whole-frame
+    indexing puts its stripe into its own chunk), then `gather()` runs ONE in-place all-gather — the
+    only collective of the path."""
+
+    def __init__(self, mb_w: int, mb_h: int, device, group=None):
+        self.mb_w, self.mb_h, self.group = mb_w, mb_h, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rows = -(-mb_h // self.world)
+        self.chunk = self.rows * mb_w
+        self.field = torch.zeros((self.world * self.chunk, REC), dtype=torch.uint8, device=device)
+
+    def frame(self) -> torch.Tensor:
+        return self.field[: self.mb_w * self.mb_h]
+
+    def gather(self) -> torch.Tensor:
+        if self.world > 1:
+            mine = self.field[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+            dist.all_gather_into_tensor(self.field, mine, group=self.group)
+        return self.frame()

@@ -31,8 +31,14 @@ class DeviceSearch:
         self.lib.check(self.lib.dll.jmme_set_reference_dev(self.ctx.handle, ref_idx, C.c_void_p(luma.data_ptr()),
                                                            luma.stride(0), self._stream()), self.ctx.handle)
 
-    def search(self, cur: torch.Tensor, pred: torch.Tensor | None = None, per_ref: bool = False) -> torch.Tensor:
+    def search(self, cur: torch.Tensor, pred: torch.Tensor | None = None, per_ref: bool = False,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+        """out: optional uint8 cuda tensor with room for mb_w*mb_h records (whole-frame indexing)."""
         assert cur.is_cuda and cur.dtype == torch.uint8 and cur.dim() == 2 and cur.stride(1) == 1
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
+            assert out.numel() >= self.n_mb * abi.MBRESULT_DTYPE.itemsize
+            self.out = out
         if per_ref and self.out_per_ref is None:
             self.out_per_ref = torch.zeros((self.ctx.num_refs, self.n_mb, abi.MBRESULT_DTYPE.itemsize),
                                            dtype=torch.uint8, device="cuda")

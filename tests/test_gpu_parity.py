@@ -140,7 +140,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [32, 67, 88])
+@pytest.mark.parametrize("variant", [0, 32, 57, 69])
 @pytest.mark.parametrize("w,h,R,kw", CASES)
 def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
     os.environ["JMME_VARIANT"] = str(variant)
@@ -151,7 +151,7 @@ def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
         assert_same(got, exp, f"{w}x{h} R={R} {kw} {kind}")
 
 
-@pytest.mark.parametrize("variant", [30, 31, 51, 22, 32, 42, 27, 47, 57, 67, 48, 68, 88, 49, 69])
+@pytest.mark.parametrize("variant", [0, 30, 31, 51, 22, 32, 42, 47, 57, 48, 68, 88, 49, 69, 89])
 @pytest.mark.parametrize("policy,nb", [(abi.PRED_PER_MB, 1), (abi.PRED_PER_BLOCK, 41)])
 @pytest.mark.parametrize("rdopt", [0, 1])
 def test_predictor_policies(cuda, oracle, policy, nb, rdopt, variant):
@@ -276,3 +276,20 @@ def test_launch_counter_counts_kernels(cuda):
         n0 = ctx.launch_count()
         ctx.search_frame(cur)
         assert n0 == 1 and ctx.launch_count() - n0 == 3          # me_int, me_subpel, select_ref
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_in_library_multi_gpu_mode_on_virtual_devices(cuda, oracle, n):
+    """jmme_params.n_gpus splits the frame into MB-row stripes, one sub-context each, and gathers the MV
+    field to the first device.  With fewer GPUs than stripes the same device is listed several times
+    (N virtual GPUs on one device must reproduce the one-stripe field byte for byte)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    w, h, R = 96, 144, 8                                     # 9 MB rows
+    cur, refs = synth.frame_pair(w, h, seed=21, search_range=R, num_refs=2)
+    kw = dict(search_range=R, qp=29, subpel=1)
+    ids = [i % ndev for i in range(n)]
+    g, gp = run(cuda, cur, refs, None, True, n_gpus=n, device_ids=ids, **kw)
+    o, op = run(oracle, cur, refs, None, True, **kw)
+    assert_same(gp, op, f"per-ref n_gpus={n}")
+    assert_same(g, o, f"best n_gpus={n}")

@@ -1,0 +1,66 @@
+"""N > 1 host logic on CPU: world_size 2 and 3 over gloo.  Each rank searches its MB-row stripe (with
+the oracle standing in for the GPU) and the all-gathered MV field must equal the single-rank field
+byte for byte — the partition is invisible in the result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from jmme import abi, synth
+from jmme.dist import StripeGather, stripe_of
+
+
+def test_stripes_cover_rows_exactly():
+    for mb_h in (1, 5, 18, 45, 68, 135):
+        for world in (1, 2, 3, 4, 8):
+            if world > mb_h:
+                continue
+            parts = [stripe_of(r, world, mb_h) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == mb_h
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in parts]
+            assert max(sizes) == -(-mb_h // world)           # no stripe larger than an even split's largest
+            assert all(b == min(r * max(sizes), mb_h) for r, (b, e) in enumerate(parts))
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import oracle as oracle_mod
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = oracle_mod.load()
+    w, h, R = 80, 112, 6                                     # 7 MB rows: uneven stripes
+    cur, refs = synth.frame_pair(w, h, seed=3, search_range=R, num_refs=2)
+    rb, re = stripe_of(rank, world, 7)
+    g = StripeGather(5, 7, "cpu")
+    if re > rb:                                              # a rank past the end of the frame has no rows
+        with orc.context(width=w, height=h, search_range=R, num_refs=2, subpel=1, mb_row_begin=rb, mb_row_end=re) as c:
+            for i, r in enumerate(refs):
+                c.set_reference(i, r)
+            mine = c.search_frame(cur)                       # whole-frame indexing, stripe rows valid
+        rec = torch.from_numpy(mine.view(np.uint8).reshape(-1, abi.MBRESULT_DTYPE.itemsize))
+        g.field[rb * 5:re * 5].copy_(rec[rb * 5:re * 5])
+    full = g.gather()
+    np.save(os.path.join(tmp, f"full_{world}_{rank}.npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_gathered_field_equals_single_rank_field(oracle, tmp_path, world):
+    w, h, R = 80, 112, 6
+    cur, refs = synth.frame_pair(w, h, seed=3, search_range=R, num_refs=2)
+    with oracle.context(width=w, height=h, search_range=R, num_refs=2, subpel=1) as c:
+        for i, r in enumerate(refs):
+            c.set_reference(i, r)
+        ref_field = c.search_frame(cur)
+    port = 29600 + world + (os.getpid() % 200)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"full_{world}_{r}.npy")
+        assert got.tobytes() == ref_field.tobytes(), f"rank {r} of {world}"
