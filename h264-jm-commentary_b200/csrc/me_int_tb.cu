@@ -20,8 +20,8 @@ namespace {
 
 struct TbLayout {
     int RS, rows, RAWW;                 // window row stride (words, == 2 mod 4), rows, raw row words
-    int off_win, off_raw, off_cur, off_T, off_best, off_key, off_bx, off_by, total_words;
-    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem)
+    int off_win, off_raw, off_cur, off_T, off_best, off_task, off_key, off_bx, off_by, total_words;
+    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem, int K)
     {
         const int ncols = 2 * R + 1;
         RS = 2 * R + 13;                // word positions 0 .. 2R+12
@@ -33,7 +33,8 @@ struct TbLayout {
         off_cur = off_raw + rows * RAWW;
         off_T = off_cur + 2 * 64;
         off_best = off_T + JMME_NT;
-        off_key = off_best + 48;
+        off_task = off_best + 48;                       // u16 (ybase << 8 | xbase) per main task
+        off_key = off_task + ((((ncols + K - 1) / K) * (ncols >> 4) + 1) >> 1);
         off_bx = off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0);
         const int nb = per_block ? JMME_NBLK : 1;
         off_by = off_bx + (nb * ncols + 3) / 4;
@@ -66,12 +67,13 @@ template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const TbLayout L(P.R, PER_BLOCK, !KEYG);
+    const TbLayout L(P.R, PER_BLOCK, !KEYG, K);
     uint32_t *s_win = smem + L.off_win;
     uint32_t *s_raw = smem + L.off_raw;
     uint32_t *s_cur2 = smem + L.off_cur;
     uint32_t *s_T = smem + L.off_T;
     uint32_t *s_best = smem + L.off_best;
+    uint16_t *s_task = (uint16_t *)(smem + L.off_task);
     uint16_t *s_key = (uint16_t *)(smem + L.off_key);
     uint8_t *s_bx = (uint8_t *)(smem + L.off_bx);
     uint8_t *s_by = (uint8_t *)(smem + L.off_by);
@@ -95,13 +97,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const bool pretest = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
     int patched = -1;
 
-    // tasks: 16 consecutive columns of one run per warp; residual columns gathered several runs per warp
+    // tasks: 16 consecutive columns of one run per warp; residual columns gathered several runs per warp.
+    // Main tasks come from a small table (no division in the task loop); the residual mapping of a lane
+    // is a kernel constant.
     const int nruns = (ncols + K - 1) / K;
     const int nseg = ncols >> 4;
     const int wr = ncols - 16 * nseg;                    // 1..15 (ncols is odd)
     const int G = 16 / wr;
     const int n_main = nruns * nseg;
     const int n_tasks = n_main + (nruns + G - 1) / G;
+    for (int i = tid; i < n_main; i += NW * 32) {
+        const int run = i / nseg, seg = i - run * nseg;
+        s_task[i] = (uint16_t)((min(run * K, ncols - K) << 8) | (16 * seg));
+    }
+    int res_g = l16 / wr;                                // residual task: run offset and column of this lane
+    int res_x = 16 * nseg + (l16 - res_g * wr);
+    if (res_g >= G) { res_g = 0; res_x = 16 * nseg; }    // idle lanes repeat lane 0 (idempotent)
 
     auto decode_item = [&](int item, Item &it) {
         it.ref = item / n_mb_stripe;
@@ -118,10 +129,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         const uint8_t *plane = P.planes[it.ref];
         const int gx0 = P.pad + 16 * it.mbx + it.cx - R, gy0 = P.pad + 16 * it.mby + it.cy - R;
         const uint8_t *g = plane + (size_t)gy0 * P.pstride + (gx0 & ~15);
-        const int nch = RAWW >> 2;
-        for (int i = tid; i < rows * nch; i += NW * 32) {
-            const int row = i / nch, c = i - row * nch;
-            cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
+        const int nch = RAWW >> 2;                       // 16-byte chunks per raw row
+        if (nch <= 8) {                                  // thread = (row, chunk slot): no division
+            const int c = tid & 7;
+            if (c < nch)
+                for (int row = tid >> 3; row < rows; row += NW * 4)
+                    cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
+        } else {
+            const int c = tid & 15;
+            if (c < nch)
+                for (int row = tid >> 4; row < rows; row += NW * 2)
+                    cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
         }
         if (tid < 16)
             cp_async16(s_cur2 + buf * 64 + 4 * tid, P.cur + (size_t)(16 * it.mby + tid) * P.cur_stride + 16 * it.mbx);
@@ -130,14 +148,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     auto expand = [&](const Item &it) {
         const int gx0 = P.pad + 16 * it.mbx + it.cx - R;
         const int t16 = gx0 & 15, np = RS >> 1;          // word pairs per row (RS is even)
-        for (int i = tid; i < rows * np; i += NW * 32) {
-            const int row = i / np, x = 2 * (i - row * np);
-            const uint32_t *raw = s_raw + row * RAWW;
-            const int o0 = t16 + x, o1 = o0 + 1;
-            uint2 v;
-            v.x = __funnelshift_r(raw[o0 >> 2], raw[(o0 >> 2) + 1], (o0 & 3) * 8);
-            v.y = __funnelshift_r(raw[o1 >> 2], raw[(o1 >> 2) + 1], (o1 & 3) * 8);
-            *(uint2 *)(s_win + row * RS + x) = v;
+        for (int xp = lane; xp < np; xp += 32) {         // this lane's word pair(s): fixed across rows
+            const int o0 = t16 + 2 * xp, i0 = o0 >> 2, b0 = o0 & 3;
+            // words at byte offsets o0 and o0+1 out of three aligned raw words (byte permute)
+            const unsigned sel0 = 0x3210u + 0x1111u * b0;
+            const unsigned sel1 = b0 == 3 ? 0x3210u : 0x3210u + 0x1111u * (b0 + 1);
+#pragma unroll 4
+            for (int row = warp; row < rows; row += NW) {
+                const uint32_t *raw = s_raw + row * RAWW + i0;
+                const uint32_t a0 = raw[0], a1 = raw[1], a2 = raw[2];
+                uint2 v;
+                v.x = __byte_perm(a0, a1, sel0);
+                v.y = b0 == 3 ? __byte_perm(a1, a2, sel1) : __byte_perm(a0, a1, sel1);
+                *(uint2 *)(s_win + row * RS + 2 * xp) = v;
+            }
         }
         if (tid < 48) s_best[tid] = 0xFFFFFFFFu;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
@@ -208,18 +232,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
         for (int b = 0; b < NL; b++) best[b] = 0xFFFFFFFFu;
 
+        unsigned e_next = warp < n_main ? s_task[warp] : 0u;     // task descriptor, fetched one task ahead
         for (int task = warp; task < n_tasks; task += NW) {
-            int run, xoff;
+            int ybase, xoff;
             if (task < n_main) {
-                run = task / nseg;
-                xoff = 16 * (task - run * nseg) + l16;
+                ybase = e_next >> 8;
+                xoff = (e_next & 255) + l16;
             } else {
-                int g = l16 / wr, x = l16 - g * wr;
-                if (g >= G) { g = 0; x = 0; }            // idle lanes repeat lane 0 (idempotent)
-                run = min((task - n_main) * G + g, nruns - 1);
-                xoff = 16 * nseg + x;
+                ybase = min(min((task - n_main) * G + res_g, nruns - 1) * K, ncols - K);
+                xoff = res_x;
             }
-            const int ybase = min(run * K, ncols - K);
+            if (task + NW < n_main) e_next = s_task[task + NW];
             const uint32_t *base = s_win + (ybase + 8 * half) * RS + xoff;
 
             unsigned acc[K][8];
@@ -351,7 +374,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
-    TbLayout L(P.R, PER_BLOCK, !KEYG);
+    TbLayout L(P.R, PER_BLOCK, !KEYG, K);
     size_t bytes = (size_t)L.total_words * 4;
     auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG>;
     // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
@@ -378,6 +401,8 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 }  // namespace
 
 // shape 7: 4 warps, >= 4 CTAs/SM (<= 128 registers)   shape 8: 4 warps, >= 3 CTAs/SM (<= 168 registers)
+// shape 6: 3 warps, >= 4 CTAs/SM (<= 168 registers): 45 tasks per MB at R = 32, K = 6 split 15/15/15
+// shape 5: 5 warps, >= 2 CTAs/SM
 // shape 9: 6 warps, >= 2 CTAs/SM (<= 168 registers), spiral keys read from global memory: the shape for
 //          R > 32, where the window (80 KB at R = 64) leaves room for only two CTAs per SM
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st)
@@ -393,6 +418,7 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
     TB(4, 7, 4, 4, false) TB(5, 7, 4, 4, false)
     TB(4, 8, 4, 3, false) TB(6, 8, 4, 3, false) TB(8, 8, 4, 3, false)
     TB(4, 9, 6, 2, true) TB(6, 9, 6, 2, true) TB(8, 9, 6, 2, true)
+    TB(6, 6, 3, 4, false) TB(8, 6, 3, 4, false) TB(6, 5, 5, 2, false)
 #undef TB
     return cudaErrorInvalidValue;
 }
