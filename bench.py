@@ -193,7 +193,19 @@ def cpu_baseline(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _watchdog(seconds):
+    """Hard exit if the run has not finished in time: a hung collective must not stall the caller."""
+    def fire():
+        sys.stderr.write(f"bench.py watchdog: no exit after {seconds} s, leaving\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def run_ours(args, rank, world, local_rank):
+    _watchdog(args.watchdog)
     import torch
     import torch.distributed as dist
     import jmme
@@ -238,23 +250,52 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    # per-kernel device times (CUDA events around each kernel, eager launches) for the roofline
+    ktimes = []
+    for s in range(min(args.steps, 10)):
+        flush.fill_(s & 255)
+        step_device()
+        torch.cuda.synchronize()
+        ktimes.append(ds.ctx.kernel_times())
+    ds.ctx.set_profiling(False)
+    # the whole step (kernels + the all-gather) is captured once in a CUDA graph and replayed
+    launch_mode, graph = "eager", None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_device()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_device()
+            launch_mode = "cuda-graph replay of the captured step"
+        except Exception as e:  # noqa: BLE001
+            graph, launch_mode = None, f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+    run_step = graph.replay if graph is not None else step_device
+    for _ in range(3):
+        run_step()
+    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ktimes = []
     l0 = ds.launch_count()
     barrier()
     for s in range(args.steps):
         flush.fill_(s & 255)              # L2 flush between timed iterations (outside the event pair)
         barrier()
         ev[s][0].record()
-        step_device()
+        run_step()
         ev[s][1].record()
         torch.cuda.synchronize()
-        ktimes.append(ds.ctx.kernel_times())
     barrier()
     launches = ds.launch_count() - l0
+    if graph is not None:                 # replays launch the captured kernels without passing the counter
+        launches = args.steps * (len(d_refs) + (1 if (w % 16 or h % 16) else 0) + 2 + (1 if subpel else 0))
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_dev = float(np.mean(step_ms))
 
@@ -263,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
     h_refs = [torch.from_numpy(r).pin_memory() for r in ref_l]
     h_out = torch.zeros(n_mb * rec, dtype=torch.uint8).pin_memory()
     hctx = lib.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
-                       mb_row_begin=rb, mb_row_end=re, device_ids=[local_rank])
+                       mb_row_begin=rb, mb_row_end=re, device_ids=[local_rank], async_reference=1)
     pu8 = C.POINTER(C.c_uint8)
 
     def step_host():
@@ -322,7 +363,8 @@ def run_ours(args, rank, world, local_rank):
                        "blocks": 41 if mask != 0x02 else 1, "subpel": "half+quarter SATD" if subpel else "none",
                        "qp": QP, "pred_policy": "zero", "partition": f"{world} MB-row stripes",
                        "l2": "256 MB buffer written between timed steps (outside the event pair)",
-                       "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks"},
+                       "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
+                       "launch": launch_mode},
             "e2e": {"value": n_mb / (ms_e2e * 1e-3), "unit": "MB/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (1 + refs) * w * h, "d2h_bytes_per_step": (re - rb) * mb_w * rec,
                     "api": "jmme_set_reference + jmme_search_frame (C ABI, pinned host buffers)"},
@@ -340,10 +382,17 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
-    hctx.close()
-    ds.close()
+    # Orderly exit.  A captured graph holds NCCL work; destroying the process group with it alive was seen
+    # to hang, so the graph goes first, every rank meets at a barrier, and the process leaves without
+    # running the communicator's destructor (a watchdog bounds everything above in case a rank is stuck).
+    sys.stdout.flush()
+    graph = None
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():
@@ -356,6 +405,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU work per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--watchdog", type=float, default=300.0, help="hard exit after this many seconds")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -30,7 +30,8 @@ struct jmme_ctx {
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
     int device, num_sms, K;
     cudaStream_t stream;
-    uint8_t *d_raw;                       // staging for one raw luma picture (width x height)
+    uint8_t *d_raw;                       // staging for the raw current picture (width x height)
+    uint8_t *d_raw_ref[JMME_MAX_REFS];    // staging for the raw reference pictures
     uint8_t *d_planes[JMME_MAX_REFS];
     bool ref_set[JMME_MAX_REFS];
     uint8_t *d_cur16;
@@ -86,7 +87,7 @@ void free_device(jmme_ctx *c)
 {
     if (c->device >= 0) cudaSetDevice(c->device);
     cudaFree(c->d_raw);
-    for (int r = 0; r < JMME_MAX_REFS; r++) cudaFree(c->d_planes[r]);
+    for (int r = 0; r < JMME_MAX_REFS; r++) { cudaFree(c->d_planes[r]); cudaFree(c->d_raw_ref[r]); }
     cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
@@ -150,7 +151,10 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         CUC(cudaMalloc(&c->d_raw, (size_t)p->width * p->height));
-        for (int r = 0; r < p->num_refs; r++) CUC(cudaMalloc(&c->d_planes[r], psz * c->n_planes));
+        for (int r = 0; r < p->num_refs; r++) {
+            CUC(cudaMalloc(&c->d_planes[r], psz * c->n_planes));
+            CUC(cudaMalloc(&c->d_raw_ref[r], (size_t)p->width * p->height));
+        }
         CUC(cudaMalloc(&c->d_cur16, (size_t)c->w16 * c->h16));
         CUC(cudaMalloc(&c->d_pred, sizeof(int16_t) * 2 * JMME_NBLK * n_mb * p->num_refs));
         CUC(cudaMalloc(&c->d_res, sizeof(BlkRes) * JMME_NBLK * n_mb * p->num_refs));
@@ -364,11 +368,11 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
         return JMME_OK;
     }
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemcpy2DAsync(c->d_raw, c->p.width, luma, stride, c->p.width, c->p.height, cudaMemcpyHostToDevice,
+    CU(c, cudaMemcpy2DAsync(c->d_raw_ref[r], c->p.width, luma, stride, c->p.width, c->p.height, cudaMemcpyHostToDevice,
                             c->stream));
-    int rc = jmme_set_reference_dev(c, r, c->d_raw, c->p.width, c->stream);
+    int rc = jmme_set_reference_dev(c, r, c->d_raw_ref[r], c->p.width, c->stream);
     if (rc != JMME_OK) return rc;
-    CU(c, cudaStreamSynchronize(c->stream));
+    if (!c->p.async_reference) CU(c, cudaStreamSynchronize(c->stream));
     return JMME_OK;
 }
 

@@ -41,7 +41,8 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "width", "height", "search_range", "num_refs", "blocktype_mask", "lambda_factor", "qp", "rdopt",
         "use_hadamard", "subpel", "search_mode", "pred_policy", "satd_round", "cost_domain",
-        "mb_row_begin", "mb_row_end", "n_gpus")] + [("device_ids", C.c_int32 * MAX_GPUS)]
+        "mb_row_begin", "mb_row_end", "n_gpus")] + [("device_ids", C.c_int32 * MAX_GPUS),
+                                                     ("async_reference", C.c_int32)]
 
 
 MBRESULT_DTYPE = np.dtype([("mv", np.int16, (BLOCKS_PER_MB, 2)), ("cost", np.int32, (BLOCKS_PER_MB,)),

@@ -82,6 +82,9 @@ typedef struct jmme_params {
     int32_t mb_row_end;          /* 0 = to the last row                                          */
     int32_t n_gpus;              /* 0/1 = one device; >1 = split the stripe over device_ids      */
     int32_t device_ids[JMME_MAX_GPUS];
+    int32_t async_reference;     /* 1: jmme_set_reference returns once its copy and kernel are   */
+                                 /* queued; the luma buffer must stay unchanged until the next  */
+                                 /* jmme_search_frame / jmme_get_subimage returns (pinned memory) */
 } jmme_params;
 
 /* One macroblock's result.  Block order: blocktype 1..7, raster order inside the MB
