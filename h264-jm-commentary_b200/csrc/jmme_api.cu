@@ -18,6 +18,7 @@
 #include "jmme_dev.cuh"
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st);
+cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st);
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
                                int n_planes, uint8_t *out, int y_begin, int y_end, cudaStream_t st);
 cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stride, int w16, int h16, uint8_t *dst,
@@ -217,7 +218,10 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
     if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[1][0], st));
-    CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
+    if (c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK)
+        CU(c, jmme_launch_me_full(P, st));           // a window per block: nothing to share (me_full.cu)
+    else
+        CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
     if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[1][1], st)); c->prof_valid[1] = true; }
     c->launches++;
     if (c->p.subpel) {
@@ -258,8 +262,6 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
     *out = nullptr;
     int rc = validate(p);
     if (rc != JMME_OK) return rc;
-    if (p->search_mode == JMME_SEARCH_FULL && p->pred_policy == JMME_PRED_PER_BLOCK)
-        return JMME_ERR_UNSUPPORTED;    // per-block windows: not built on the GPU
     if (p->n_gpus <= 1) return create_single(out, p, p->device_ids[0]);
 
     // multi-GPU parent: split the stripe's MB rows as evenly as possible over the devices

@@ -293,3 +293,20 @@ def test_in_library_multi_gpu_mode_on_virtual_devices(cuda, oracle, n):
     o, op = run(oracle, cur, refs, None, True, **kw)
     assert_same(gp, op, f"per-ref n_gpus={n}")
     assert_same(g, o, f"best n_gpus={n}")
+
+
+@pytest.mark.parametrize("rdopt,subpel", [(0, 0), (1, 1)])
+def test_full_search_with_per_block_windows(cuda, oracle, rdopt, subpel):
+    """search_mode FULL + 41 predictors per MB: every block searches a window centred on its own predictor
+    (JM FullPelBlockMotionSearch, a8) — the dedicated me_full kernel."""
+    w, h, R = 64, 48, 7
+    cur, refs = synth.frame_pair(w, h, seed=15, search_range=R, num_refs=2)
+    pred = synth.random_pred(2, 12, 41, seed=3, max_qpel=4 * R + 9)
+    kw = dict(search_range=R, qp=27, rdopt=rdopt, subpel=subpel, search_mode=abi.SEARCH_FULL,
+              pred_policy=abi.PRED_PER_BLOCK)
+    g, gp = run(cuda, cur, refs, pred, True, **kw)
+    o, op = run(oracle, cur, refs, pred, True, **kw)
+    assert_same(gp, op, "per-ref")
+    assert_same(g, o, "best")
+    kw["blocktype_mask"] = 0x8A                                  # 16x16, 8x16, 4x4
+    assert_same(run(cuda, cur, refs, pred, **kw), run(oracle, cur, refs, pred, **kw), "masked")
