@@ -210,7 +210,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     import jmme
     from jmme import abi, synth
-    from jmme.dist import StripeGather, stripe_of
+    from jmme.dist import PeerPushGather, StripeGather, stripe_of
     from jmme.torch_api import DeviceSearch
 
     if not torch.cuda.is_available():
@@ -233,13 +233,27 @@ def run_ours(args, rank, world, local_rank):
     ds.ctx.set_profiling(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     rec = abi.MBRESULT_DTYPE.itemsize
-    gather = StripeGather(mb_w, mb_h, "cuda")          # the search writes its stripe straight into the field
+    # the search writes its stripe straight into the field; N > 1: gathered either by peer stores over
+    # NVLink into symmetric memory (default) or by one in-place NCCL all-gather (--gather nccl)
+    gather, gather_mode = None, "none (1 rank)"
+    if world > 1 and args.gather == "p2p":
+        try:
+            gather = PeerPushGather(mb_w, mb_h, "cuda")
+            gather_mode = "peer stores into symmetric memory (jmme_push_stripe_dev) + symm-mem barrier"
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL\n")
+            gather = None
+    if gather is None:
+        gather = StripeGather(mb_w, mb_h, "cuda")
+        if world > 1:
+            gather_mode = "in-place NCCL all_gather_into_tensor"
+    p2p = isinstance(gather, PeerPushGather)
 
     def step_device():
         for i, r in enumerate(d_refs):
             ds.set_reference(i, r)
         ds.search(d_cur, out=gather.field)
-        return gather.gather()            # N > 1: one in-place all-gather over NVLink, the only collective
+        return gather.gather(ds) if p2p else gather.gather()
 
     def barrier():
         torch.cuda.synchronize()
@@ -274,7 +288,10 @@ def run_ours(args, rank, world, local_rank):
             launch_mode = "cuda-graph replay of the captured step"
         except Exception as e:  # noqa: BLE001
             graph, launch_mode = None, f"eager (graph capture failed: {type(e).__name__})"
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
     run_step = graph.replay if graph is not None else step_device
     for _ in range(3):
         run_step()
@@ -295,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = ds.launch_count() - l0
     if graph is not None:                 # replays launch the captured kernels without passing the counter
-        launches = args.steps * (len(d_refs) + (1 if (w % 16 or h % 16) else 0) + 2 + (1 if subpel else 0))
+        launches = args.steps * (len(d_refs) + (1 if (w % 16 or h % 16) else 0) + 2 + (1 if subpel else 0) + (1 if p2p else 0))
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_dev = float(np.mean(step_ms))
 
@@ -333,6 +350,16 @@ def run_ours(args, rank, world, local_rank):
     exp = h_out.numpy().view(abi.MBRESULT_DTYPE)[rb * mb_w:re * mb_w]
     assert got.tobytes() == exp.tobytes(), "device-resident and host-buffer paths disagree"
 
+    # the gathered field must be the same on every rank and equal to an independent NCCL gather
+    if world > 1:
+        step_device()
+        torch.cuda.synchronize()
+        chk = StripeGather(mb_w, mb_h, "cuda")
+        chk.field[rb * mb_w:re * mb_w].copy_(gather.field[rb * mb_w:re * mb_w])
+        ref_field = chk.gather()
+        torch.cuda.synchronize()
+        assert torch.equal(ref_field, gather.frame()), f"rank {rank}: gathered MV field differs from the NCCL gather"
+
     # ---- max over ranks -------------------------------------------------------------------------
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -364,7 +391,7 @@ def run_ours(args, rank, world, local_rank):
                        "qp": QP, "pred_policy": "zero", "partition": f"{world} MB-row stripes",
                        "l2": "256 MB buffer written between timed steps (outside the event pair)",
                        "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
-                       "launch": launch_mode},
+                       "launch": launch_mode, "gather": gather_mode},
             "e2e": {"value": n_mb / (ms_e2e * 1e-3), "unit": "MB/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (1 + refs) * w * h, "d2h_bytes_per_step": (re - rb) * mb_w * rec,
                     "api": "jmme_set_reference + jmme_search_frame (C ABI, pinned host buffers)"},
@@ -406,6 +433,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU work per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the MV field is gathered")
     ap.add_argument("--watchdog", type=float, default=300.0, help="hard exit after this many seconds")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

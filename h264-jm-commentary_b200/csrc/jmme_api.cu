@@ -25,6 +25,7 @@ cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stri
                                 cudaStream_t st);
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st);
 cudaError_t jmme_launch_select(const SearchParams &P, cudaStream_t st);
+cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st);
 
 struct jmme_ctx {
     jmme_params p;
@@ -429,6 +430,23 @@ int jmme_search_frame_dev(jmme_ctx *c, const void *d_cur, int stride, const void
     CU(c, cudaSetDevice(c->device));
     return enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
                           (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
+}
+
+int jmme_push_stripe_dev(jmme_ctx *c, const void *d_local, void *const *d_peers, int n_peers, void *stream)
+{
+    if (!c || !d_local || !d_peers || n_peers < 1 || n_peers > JMME_MAX_GPUS) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    CU(c, cudaSetDevice(c->device));
+    const size_t off = (size_t)c->p.mb_row_begin * c->mb_w * sizeof(jmme_mbresult);          // bytes, multiple of 4
+    const size_t n_words = (size_t)(c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w * sizeof(jmme_mbresult) / 4;
+    uint32_t *dst[JMME_MAX_GPUS];
+    int n = 0;
+    for (int i = 0; i < n_peers; i++)
+        if (d_peers[i] && d_peers[i] != d_local) dst[n++] = (uint32_t *)((uint8_t *)d_peers[i] + off);
+    if (!n) return JMME_OK;
+    CU(c, jmme_launch_push((const uint32_t *)((const uint8_t *)d_local + off), dst, n, n_words, (cudaStream_t)stream));
+    c->launches++;
+    return JMME_OK;
 }
 
 int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t *pred, jmme_mbresult *out,

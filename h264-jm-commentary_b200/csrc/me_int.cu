@@ -401,7 +401,7 @@ cudaError_t launch_shape(const SearchParams &P, int num_sms, cudaStream_t st)
 
 // variant = 10*K + c:  K candidates per thread run (must be <= 2R+1);
 //   c = 0: 6 warps, >= 2 CTAs/SM (<= 168 registers)    c = 1: 8 warps, 1 CTA/SM (<= 255 registers)
-//   c = 2: 4 warps, >= 3 CTAs/SM (<= 168 registers)   c = 3: 10 warps, 1 CTA/SM (<= 204 registers)
+//   c = 2: 4 warps, >= 3 CTAs/SM (<= 168 registers)
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st);
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st)
@@ -415,10 +415,9 @@ cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, 
     if (K > P.ncols) K = 3;
 #define PICKC(KK, CC, NWW, MB) \
     if (K == KK && c == CC) return launch_shape<KK, NWW, MB>(P, num_sms, st);
-    PICKC(2, 0, 6, 2) PICKC(3, 0, 6, 2) PICKC(4, 0, 6, 2)
-    PICKC(3, 1, 8, 1) PICKC(4, 1, 8, 1) PICKC(5, 1, 8, 1)
-    PICKC(2, 2, 4, 3) PICKC(3, 2, 4, 3) PICKC(4, 2, 4, 3)
-    PICKC(3, 3, 10, 1) PICKC(4, 3, 10, 1) PICKC(5, 3, 10, 1)
+    PICKC(3, 0, 6, 2)
+    PICKC(3, 1, 8, 1) PICKC(5, 1, 8, 1)
+    PICKC(2, 2, 4, 3) PICKC(3, 2, 4, 3)
 #undef PICKC
     return cudaErrorInvalidValue;
 }

@@ -402,7 +402,6 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 
 // shape 7: 4 warps, >= 4 CTAs/SM (<= 128 registers)   shape 8: 4 warps, >= 3 CTAs/SM (<= 168 registers)
 // shape 6: 3 warps, >= 4 CTAs/SM (<= 168 registers): 45 tasks per MB at R = 32, K = 6 split 15/15/15
-// shape 5: 5 warps, >= 2 CTAs/SM
 // shape 9: 6 warps, >= 2 CTAs/SM (<= 168 registers), spiral keys read from global memory: the shape for
 //          R > 32, where the window (80 KB at R = 64) leaves room for only two CTAs per SM
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st)
@@ -415,10 +414,10 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
         if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142, KG>(P, num_sms, st);      \
         return launch_tb<KK, NWW, MB, false, 0, KG>(P, num_sms, st);                       \
     }
-    TB(4, 7, 4, 4, false) TB(5, 7, 4, 4, false)
+    TB(4, 7, 4, 4, false)
     TB(4, 8, 4, 3, false) TB(6, 8, 4, 3, false) TB(8, 8, 4, 3, false)
-    TB(4, 9, 6, 2, true) TB(6, 9, 6, 2, true) TB(8, 9, 6, 2, true)
-    TB(6, 6, 3, 4, false) TB(8, 6, 3, 4, false) TB(6, 5, 5, 2, false)
+    TB(6, 9, 6, 2, true)
+    TB(6, 6, 3, 4, false)
 #undef TB
     return cudaErrorInvalidValue;
 }

@@ -5,6 +5,8 @@
 // (a11) and the REF_COST comparison of PartitionMotionSearch's caller (a4).  Conventions: DESIGN.md §2.
 //
 // Mapping: one CTA per (reference, macroblock), thread = (blocktype, 4x4 cell); see me_subpel_kernel.
+#include <algorithm>
+
 #include "jmme_dev.cuh"
 
 namespace {
@@ -177,7 +179,29 @@ __global__ void select_ref_kernel(const SearchParams P)
     o->mv[b][0] = (int16_t)bx; o->mv[b][1] = (int16_t)by; o->cost[b] = bc; o->ref_idx[b] = (int8_t)br;
 }
 
+// stripe of the MV field -> the same offsets of up to 8 peer buffers (NVLink peer stores, 4-byte words)
+struct PushArgs {
+    uint32_t *dst[JMME_MAX_GPUS];
+};
+__global__ void __launch_bounds__(256) push_stripe_kernel(const uint32_t *__restrict__ src, PushArgs a, int n_dst,
+                                                          size_t n_words)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_words; i += (size_t)gridDim.x * 256) {
+        const uint32_t v = src[i];
+        for (int d = 0; d < n_dst; d++) a.dst[d][i] = v;
+    }
+}
+
 }  // namespace
+
+cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st)
+{
+    PushArgs a;
+    for (int d = 0; d < JMME_MAX_GPUS; d++) a.dst[d] = d < n_dst ? dst[d] : nullptr;
+    const int grid = (int)std::min<size_t>((n_words + 255) / 256, 592);
+    push_stripe_kernel<<<grid, 256, 0, st>>>(src, a, n_dst, n_words);
+    return cudaGetLastError();
+}
 
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
 {

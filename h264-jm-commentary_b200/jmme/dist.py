@@ -45,3 +45,31 @@ class StripeGather:
             mine = self.field[self.rank * self.chunk:(self.rank + 1) * self.chunk]
             dist.all_gather_into_tensor(self.field, mine, group=self.group)
         return self.frame()
+
+
+class PeerPushGather:
+    """The same gather without a collective library: the MV field lives in symmetric memory
+    (torch.distributed._symmetric_memory: every rank's buffer is mapped into every process), each rank
+    pushes its stripe into all peers' fields with one kernel of NVLink peer stores
+    (jmme_push_stripe_dev) and a symmetric-memory barrier orders the reads."""
+
+    def __init__(self, mb_w: int, mb_h: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.mb_w, self.mb_h = mb_w, mb_h
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows = -(-mb_h // self.world)
+        n = self.world * self.rows * mb_w
+        self.field = symm_mem.empty((n, REC), dtype=torch.uint8, device=device)
+        self.field.zero_()
+        self.hdl = symm_mem.rendezvous(self.field, group if group is not None else dist.group.WORLD)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def frame(self) -> torch.Tensor:
+        return self.field[: self.mb_w * self.mb_h]
+
+    def gather(self, search) -> torch.Tensor:
+        """search: the DeviceSearch whose last result was written into self.field."""
+        self.hdl.barrier(channel=0)            # peers are done reading the previous field
+        search.push_stripe(self.field, self.peer_ptrs)
+        self.hdl.barrier(channel=1)            # every stripe has landed everywhere
+        return self.frame()

@@ -49,6 +49,12 @@ class DeviceSearch:
                        self.ctx.handle)
         return self.out
 
+    def push_stripe(self, field: torch.Tensor, peer_ptrs):
+        """Copy this rank's stripe of `field` into the same offsets of the peer buffers (NVLink stores)."""
+        arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        self.lib.check(self.lib.dll.jmme_push_stripe_dev(self.ctx.handle, C.c_void_p(field.data_ptr()), arr, len(peer_ptrs),
+                                                         self._stream()), self.ctx.handle)
+
     def stripe_rows(self):
         return self.ctx.params.mb_row_begin, (self.ctx.params.mb_row_end or self.ctx.mb_h)
 

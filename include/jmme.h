@@ -140,6 +140,13 @@ int jmme_get_subimage(jmme_ctx *ctx, int ref_idx, int xfrac, int yfrac,
 int jmme_set_reference_dev(jmme_ctx *ctx, int ref_idx, const void *d_luma, int stride, void *stream);
 int jmme_search_frame_dev(jmme_ctx *ctx, const void *d_cur_luma, int stride, const void *d_pred,
                           void *d_out, void *d_out_per_ref, void *stream);
+/* Multi-GPU gather without a collective library: copy this context's stripe of the MV field from
+ * d_field_local (whole-frame indexed, as written by jmme_search_frame_dev) into the same offsets of
+ * n_peers peer buffers — device pointers mapped into this process (CUDA IPC / symmetric memory); the
+ * stores travel over NVLink.  An entry equal to d_field_local is skipped.  Asynchronous on `stream`; the
+ * caller provides the cross-rank barrier before the field is read. */
+int jmme_push_stripe_dev(jmme_ctx *ctx, const void *d_field_local, void *const *d_field_peers, int n_peers,
+                         void *stream);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 long long jmme_launch_count(const jmme_ctx *ctx);
 /* Per-kernel device times.  jmme_set_profiling(ctx,1) makes every later set_reference / search

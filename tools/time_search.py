@@ -21,7 +21,7 @@ ap.add_argument("--refs", type=int, default=1)
 ap.add_argument("--subpel", type=int, default=1)
 ap.add_argument("--mask", type=lambda s: int(s, 0), default=0xFE)
 ap.add_argument("--pred", type=int, default=0)
-ap.add_argument("--Ks", default="68,66,86,65,88,48")
+ap.add_argument("--Ks", default="0,68,48,88,32,51")
 ap.add_argument("--iters", type=int, default=10)
 a = ap.parse_args()
 
