@@ -382,6 +382,12 @@ def run_ours(args, rank, world, local_rank):
             (0 if rb == 0 else max(0, pad + 16 * rb - 2 * R - 4))
         itp_bytes = 17 * rows_itp * (16 * mb_w + 2 * pad)
         itp_gbs = itp_bytes / (k_itp * 1e-3) * 1e-9 if k_itp > 0 else None
+        # rows the host path really uploads for this rank's stripe (jmme_api.cu: set_reference / search_frame)
+        yb = 0 if rb == 0 else max(0, pad + 16 * rb - 2 * R - 4)
+        ye = (16 * mb_h + 2 * pad) if re == mb_h else min(16 * mb_h + 2 * pad, pad + 16 * re + 2 * R + 4)
+        ref_rows = min(max(ye - pad + 3, 1), h) - min(max(yb - pad - 3, 0), h - 1)
+        cur_rows = max(min(16 * re, h) - min(16 * rb, h - 1), 1)
+        h2d_bytes = (refs * ref_rows + cur_rows) * w
         line = {
             "metric": "ME macroblocks/sec", "value": n_mb / (ms_dev * 1e-3), "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
@@ -393,7 +399,7 @@ def run_ours(args, rank, world, local_rank):
                        "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
                        "launch": launch_mode, "gather": gather_mode},
             "e2e": {"value": n_mb / (ms_e2e * 1e-3), "unit": "MB/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": (1 + refs) * w * h, "d2h_bytes_per_step": (re - rb) * mb_w * rec,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": (re - rb) * mb_w * rec,
                     "api": "jmme_set_reference + jmme_search_frame (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches + launches_e2e),
             "kernel_ms": {"interp": k_itp, "me_int": k_int, "me_subpel": k_sub, "select_ref": k_sel,

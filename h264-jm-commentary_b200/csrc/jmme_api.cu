@@ -371,8 +371,16 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
         return JMME_OK;
     }
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemcpy2DAsync(c->d_raw_ref[r], c->p.width, luma, stride, c->p.width, c->p.height, cudaMemcpyHostToDevice,
-                            c->stream));
+    {
+        // upload only the picture rows the stripe's planes are built from (plane rows +-3 filter taps)
+        const int R = c->p.search_range;
+        const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - 2 * R - 4);
+        const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
+        const int s0 = std::min(std::max(yb - c->pad - 3, 0), c->p.height - 1);
+        const int s1 = std::min(std::max(ye - c->pad + 3, 1), c->p.height);          // exclusive; clamps hit row h-1
+        CU(c, cudaMemcpy2DAsync(c->d_raw_ref[r] + (size_t)s0 * c->p.width, c->p.width, luma + (size_t)s0 * stride, stride,
+                                c->p.width, s1 - s0, cudaMemcpyHostToDevice, c->stream));
+    }
     int rc = jmme_set_reference_dev(c, r, c->d_raw_ref[r], c->p.width, c->stream);
     if (rc != JMME_OK) return rc;
     if (!c->p.async_reference) CU(c, cudaStreamSynchronize(c->stream));
@@ -470,8 +478,13 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
     for (int g = 0; g < ns; g++) {
         jmme_ctx *s = subs[g];
         CU(c, cudaSetDevice(s->device));
-        CU(c, cudaMemcpy2DAsync(s->d_raw, s->p.width, cur, stride, s->p.width, s->p.height, cudaMemcpyHostToDevice,
-                                s->stream));
+        {
+            // only the current-picture rows of this stripe (row h-1 stands in for the replicated rows below it)
+            const int s0 = std::min(16 * s->p.mb_row_begin, s->p.height - 1);
+            const int s1 = std::min(16 * s->p.mb_row_end, s->p.height);
+            CU(c, cudaMemcpy2DAsync(s->d_raw + (size_t)s0 * s->p.width, s->p.width, cur + (size_t)s0 * stride, stride,
+                                    s->p.width, std::max(s1 - s0, 1), cudaMemcpyHostToDevice, s->stream));
+        }
         if (pred_elems)
             CU(c, cudaMemcpyAsync(s->d_pred, pred, pred_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
         int rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,

@@ -408,7 +408,7 @@ cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, 
 {
     if (variant <= 0) variant = P.R <= 32 ? 68 : 51;   // default: measured best per search range
     int K = variant / 10, c = variant % 10;
-    if (c >= 5) {                                   // two-threads-per-candidate kernel (me_int_tb.cu)
+    if (c >= 4) {                                   // two-threads-per-candidate kernel (me_int_tb.cu)
         if (P.blocktype_mask != JMME_MASK_16x16 && K <= P.ncols) return jmme_launch_me_int_tb(P, num_sms, K, c, st);
         K = 3; c = 2;                               // 16x16 only, or a window narrower than one run
     }

@@ -401,6 +401,7 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 }  // namespace
 
 // shape 7: 4 warps, >= 4 CTAs/SM (<= 128 registers)   shape 8: 4 warps, >= 3 CTAs/SM (<= 168 registers)
+// shape 5: 6 warps, >= 2 CTAs/SM; shape 4: 12 warps, 1 CTA/SM — fewer, faster items for short stripes
 // shape 6: 3 warps, >= 4 CTAs/SM (<= 168 registers): 45 tasks per MB at R = 32, K = 6 split 15/15/15
 // shape 9: 6 warps, >= 2 CTAs/SM (<= 168 registers), spiral keys read from global memory: the shape for
 //          R > 32, where the window (80 KB at R = 64) leaves room for only two CTAs per SM
@@ -418,6 +419,7 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
     TB(4, 8, 4, 3, false) TB(6, 8, 4, 3, false) TB(8, 8, 4, 3, false)
     TB(6, 9, 6, 2, true)
     TB(6, 6, 3, 4, false)
+    TB(6, 5, 6, 2, false) TB(6, 4, 12, 1, false)
 #undef TB
     return cudaErrorInvalidValue;
 }

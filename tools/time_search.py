@@ -23,6 +23,7 @@ ap.add_argument("--mask", type=lambda s: int(s, 0), default=0xFE)
 ap.add_argument("--pred", type=int, default=0)
 ap.add_argument("--Ks", default="0,68,48,88,32,51")
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--rows", type=int, default=0, help="search only the first N MB rows (stripe)")
 a = ap.parse_args()
 
 lib = jmme.load()
@@ -33,7 +34,7 @@ for K in [int(k) for k in a.Ks.split(",")]:
     os.environ["JMME_VARIANT"] = str(K)
     for subpel in sorted({0, a.subpel}):
         s = DeviceSearch(lib, width=a.w, height=a.h, search_range=a.R, num_refs=a.refs, subpel=subpel,
-                         blocktype_mask=a.mask, pred_policy=a.pred, qp=28)
+                         blocktype_mask=a.mask, pred_policy=a.pred, qp=28, mb_row_end=a.rows)
         pred = None
         if a.pred:
             nb = 1 if a.pred == 1 else 41
@@ -58,5 +59,5 @@ for K in [int(k) for k in a.Ks.split(",")]:
         ms_ref = e0.elapsed_time(e1) / a.iters
         print(json.dumps(dict(K=K, subpel=subpel, w=a.w, h=a.h, R=a.R, refs=a.refs, mask=a.mask, pred=a.pred,
                               ms_search=round(ms, 4), ms_set_reference=round(ms_ref, 4),
-                              mb_per_s=round(s.n_mb / (ms * 1e-3)))), flush=True)
+                              rows=a.rows, mb_per_s=round((s.n_mb if not a.rows else a.rows * s.ctx.mb_w) / (ms * 1e-3)))), flush=True)
         s.close()
