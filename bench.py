@@ -405,7 +405,8 @@ def run_ours(args, rank, world, local_rank):
             "kernel_ms": {"interp": k_itp, "me_int": k_int, "me_subpel": k_sub, "select_ref": k_sel,
                           "share_me_int": k_int / max(k_itp + k_int + k_sub + k_sel, 1e-9)},
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "me_int_kernel",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "me_int_tb_kernel" if (R <= 32 and mask != 0x02) else "me_int_kernel",
                          "algorithmic_ops_per_candidate": ops_cand, "peak_source": peak_src},
             "roofline_interp": {"bound": "hbm", "achieved": itp_gbs, "peak": hbm, "unit": "GB/s",
                                 "frac": (itp_gbs / hbm) if itp_gbs else None, "traffic": None,
