@@ -25,6 +25,10 @@ cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stri
                                 cudaStream_t st);
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st);
 cudaError_t jmme_launch_select(const SearchParams &P, cudaStream_t st);
+cudaError_t jmme_launch_predict(const int16_t *mv4, const int8_t *ref4, int mb_w, int mb_h, int num_refs, int16_t *pred,
+                                cudaStream_t st);
+cudaError_t jmme_launch_commit(const jmme_mbresult *res, int mb_w, int mb_h, int mask, int16_t *mv4, int8_t *ref4,
+                               uint8_t *mode, cudaStream_t st);
 cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st);
 
 struct jmme_ctx {
@@ -438,6 +442,60 @@ int jmme_search_frame_dev(jmme_ctx *c, const void *d_cur, int stride, const void
     CU(c, cudaSetDevice(c->device));
     return enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
                           (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
+}
+
+int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_t *ref4, uint8_t *mode)
+{
+    if (!c || !res || !mv4 || !ref4 || !mode) return JMME_ERR_PARAM;
+    jmme_ctx *s = c->n_sub ? c->sub[0] : c;
+    const size_t n_mb = (size_t)s->mb_w * s->mb_h, cells = 16 * n_mb;
+    CU(c, cudaSetDevice(s->device));
+    int16_t *d_mv = nullptr; int8_t *d_ref = nullptr; uint8_t *d_mode = nullptr;
+    int rc = JMME_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_mv, cells * 4)) != cudaSuccess || (e = cudaMalloc(&d_ref, cells)) != cudaSuccess ||
+        (e = cudaMalloc(&d_mode, 5 * n_mb)) != cudaSuccess)
+        rc = fail(c, JMME_ERR_CUDA, "cudaMalloc(field)", e);
+    if (rc == JMME_OK && (e = cudaMemcpyAsync(s->d_out, res, n_mb * sizeof(jmme_mbresult), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess)
+        rc = fail(c, JMME_ERR_CUDA, "cudaMemcpyAsync(res)", e);
+    if (rc == JMME_OK && (e = jmme_launch_commit(s->d_out, s->mb_w, s->mb_h, s->p.blocktype_mask, d_mv, d_ref, d_mode, s->stream)) != cudaSuccess)
+        rc = fail(c, JMME_ERR_CUDA, "commit_kernel", e);
+    if (rc == JMME_OK) {
+        s->launches++;
+        cudaMemcpyAsync(mv4, d_mv, cells * 4, cudaMemcpyDeviceToHost, s->stream);
+        cudaMemcpyAsync(ref4, d_ref, cells, cudaMemcpyDeviceToHost, s->stream);
+        cudaMemcpyAsync(mode, d_mode, 5 * n_mb, cudaMemcpyDeviceToHost, s->stream);
+        if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) rc = fail(c, JMME_ERR_CUDA, "commit_field", e);
+    }
+    cudaFree(d_mv); cudaFree(d_ref); cudaFree(d_mode);
+    return rc;
+}
+
+int jmme_predict_frame(jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int16_t *pred)
+{
+    if (!c || !mv4 || !ref4 || !pred) return JMME_ERR_PARAM;
+    jmme_ctx *s = c->n_sub ? c->sub[0] : c;
+    const size_t n_mb = (size_t)s->mb_w * s->mb_h, cells = 16 * n_mb;
+    const size_t n_pred = (size_t)s->p.num_refs * n_mb * JMME_NBLK * 2;
+    CU(c, cudaSetDevice(s->device));
+    int16_t *d_mv = nullptr; int8_t *d_ref = nullptr;
+    int rc = JMME_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_mv, cells * 4)) != cudaSuccess || (e = cudaMalloc(&d_ref, cells)) != cudaSuccess)
+        rc = fail(c, JMME_ERR_CUDA, "cudaMalloc(field)", e);
+    if (rc == JMME_OK) {
+        cudaMemcpyAsync(d_mv, mv4, cells * 4, cudaMemcpyHostToDevice, s->stream);
+        cudaMemcpyAsync(d_ref, ref4, cells, cudaMemcpyHostToDevice, s->stream);
+        if ((e = jmme_launch_predict(d_mv, d_ref, s->mb_w, s->mb_h, s->p.num_refs, s->d_pred, s->stream)) != cudaSuccess)
+            rc = fail(c, JMME_ERR_CUDA, "predict_kernel", e);
+    }
+    if (rc == JMME_OK) {
+        s->launches++;
+        cudaMemcpyAsync(pred, s->d_pred, n_pred * sizeof(int16_t), cudaMemcpyDeviceToHost, s->stream);
+        if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) rc = fail(c, JMME_ERR_CUDA, "predict_frame", e);
+    }
+    cudaFree(d_mv); cudaFree(d_ref);
+    return rc;
 }
 
 int jmme_push_stripe_dev(jmme_ctx *c, const void *d_local, void *const *d_peers, int n_peers, void *stream)

@@ -55,7 +55,8 @@ EXPORTS = [
     "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_subimage",
     "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_push_stripe_dev", "jmme_launch_count",
     "jmme_set_profiling",
-    "jmme_get_kernel_times", "jmme_InitMotionSearchModule",
+    "jmme_get_kernel_times", "jmme_InitMotionSearchModule", "jmme_SetMotionVectorPredictor",
+    "jmme_commit_field", "jmme_predict_frame",
     "jmme_getSubImagesLuma", "jmme_SATD", "jmme_SetupFastFullPelSearch", "jmme_FastFullPelBlockMotionSearch",
     "jmme_FullPelBlockMotionSearch", "jmme_SubPelBlockMotionSearch",
 ]
@@ -102,6 +103,9 @@ class Lib:
             "jmme_set_profiling": (i32, [vp, i32]),
             "jmme_get_kernel_times": (i32, [vp, C.POINTER(C.c_float)]),
             "jmme_InitMotionSearchModule": (i32, [i32, i32, pi32, i32, pi32, pi16, pi16]),
+            "jmme_SetMotionVectorPredictor": (i32, [i32, i32, i32, pi16, i32, i32, pi16, i32, i32, pi16, i32, i32, pi16]),
+            "jmme_commit_field": (i32, [vp, vp, pi16, C.POINTER(C.c_int8), pu8]),
+            "jmme_predict_frame": (i32, [vp, pi16, C.POINTER(C.c_int8), pi16]),
             "jmme_getSubImagesLuma": (i32, [pu8, i32, i32, i32, i32, pu8]),
             "jmme_SATD": (i32, [pi16, i32, i32, pi32]),
             "jmme_SetupFastFullPelSearch": (i32, [pu8, i32, pu8, i32, i32, i32, i32, i32, i32, i32, pi32]),
@@ -159,6 +163,15 @@ class Lib:
             refbits.ctypes.data_as(C.POINTER(C.c_int32)), sx.ctypes.data_as(C.POINTER(C.c_int16)),
             sy.ctypes.data_as(C.POINTER(C.c_int16))))
         return mvbits, refbits, sx, sy
+
+    def set_motion_vector_predictor(self, blocktype, part, ref_idx, A, B, Cn):
+        """A, B, Cn: (mvx, mvy, ref, avail) of the left, up and up-right(-or-up-left) neighbours."""
+        arr = [np.array(n[:2], np.int16) for n in (A, B, Cn)]
+        out = np.zeros(2, np.int16)
+        p16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int16))                       # noqa: E731
+        self.check(self.dll.jmme_SetMotionVectorPredictor(blocktype, part, ref_idx, p16(arr[0]), A[2], A[3], p16(arr[1]),
+                                                          B[2], B[3], p16(arr[2]), Cn[2], Cn[3], p16(out)))
+        return int(out[0]), int(out[1])
 
     def get_sub_images_luma(self, luma, pad):
         luma, p = _u8(luma)
@@ -269,6 +282,27 @@ class Context:
         self.lib.check(self.lib.dll.jmme_search_frame(self.handle, p, cur.strides[0], pp, out.ctypes.data,
                                                       opr.ctypes.data if per_ref else None), self.handle)
         return (out, opr) if per_ref else out
+
+    def commit_field(self, res):
+        """ME-only mode decision -> (mv4 [4mb_h,4mb_w,2] int16, ref4 [4mb_h,4mb_w] int8, mode [n_mb,5] uint8)."""
+        res = np.ascontiguousarray(res)
+        mv4 = np.zeros((4 * self.mb_h, 4 * self.mb_w, 2), np.int16)
+        ref4 = np.zeros((4 * self.mb_h, 4 * self.mb_w), np.int8)
+        mode = np.zeros((self.mb_w * self.mb_h, 5), np.uint8)
+        self.lib.check(self.lib.dll.jmme_commit_field(self.handle, res.ctypes.data, mv4.ctypes.data_as(C.POINTER(C.c_int16)),
+                                                      ref4.ctypes.data_as(C.POINTER(C.c_int8)),
+                                                      mode.ctypes.data_as(C.POINTER(C.c_uint8))), self.handle)
+        return mv4, ref4, mode
+
+    def predict_frame(self, mv4, ref4):
+        """PER_BLOCK predictors int16 [num_refs, n_mb, 41, 2] from a committed field."""
+        mv4 = np.ascontiguousarray(mv4, np.int16)
+        ref4 = np.ascontiguousarray(ref4, np.int8)
+        pred = np.zeros((self.num_refs, self.mb_w * self.mb_h, BLOCKS_PER_MB, 2), np.int16)
+        self.lib.check(self.lib.dll.jmme_predict_frame(self.handle, mv4.ctypes.data_as(C.POINTER(C.c_int16)),
+                                                       ref4.ctypes.data_as(C.POINTER(C.c_int8)),
+                                                       pred.ctypes.data_as(C.POINTER(C.c_int16))), self.handle)
+        return pred
 
     def get_subimage(self, ref_idx, xfrac, yfrac):
         ph, pw = self.mb_h * 16 + 2 * self.pad, self.mb_w * 16 + 2 * self.pad

@@ -23,6 +23,10 @@
  *   jmme_FullPelBlockMotionSearch      FullPelBlockMotionSearch, one block                  (a8)
  *   jmme_SubPelBlockMotionSearch       SubPelBlockMotionSearch, one block                   (a10)
  *   jmme_SATD                          SATD / HadamardSAD4x4, batched                       (a11)
+ *   jmme_SetMotionVectorPredictor      SetMotionVectorPredictor / GetMotionVectorPredictorNormal (a3)
+ *   jmme_predict_frame                 the same for all 41 blocks of every MB from a committed
+ *                                      4x4-granular motion field (enc_picture->mv / ref_idx)
+ *   jmme_commit_field                  ME-only stand-in for the mode decision that fills that field
  *
  * The arithmetic conventions ("the frozen spec") are in DESIGN.md §2.  C89-includable.
  */
@@ -164,6 +168,27 @@ int jmme_get_kernel_times(jmme_ctx *ctx, float ms[4]);
 int jmme_InitMotionSearchModule(int search_range, int max_mvd, int32_t *mvbits,
                                 int n_refbits, int32_t *refbits,
                                 int16_t *spiral_x, int16_t *spiral_y);
+
+/* (a3) H.264 8.4.1.3 median / directional MV prediction of one partition from its neighbours.
+ * blocktype 1..7; part: 16x8 0 = upper, 1 = lower; 8x16 0 = left, 1 = right; ignored otherwise.
+ * Neighbour C must already be D when C is not available.  refN < 0 = intra / other list. */
+int jmme_SetMotionVectorPredictor(int blocktype, int part, int ref_idx,
+                                  const int16_t mvA[2], int refA, int availA,
+                                  const int16_t mvB[2], int refB, int availB,
+                                  const int16_t mvC[2], int refC, int availC, int16_t pred[2]);
+
+/* ME-only mode decision: per MB the cheapest of 16x16, 16x8, 8x16 and P8x8 (each 8x8
+ * the cheapest of 8x8, 8x4, 4x8, 4x4) by summed block cost, lower mode on ties; writes the chosen
+ * vectors into a 4x4-granular field: mv4 [4*mb_h][4*mb_w][2], ref4 [4*mb_h][4*mb_w],
+ * mode [mb_h*mb_w][5] = {MB mode 1,2,3 or 8, sub-type of the four 8x8s (0 when unused)}.
+ * res: whole-frame jmme_search_frame output (host). */
+int jmme_commit_field(jmme_ctx *ctx, const jmme_mbresult *res, int16_t *mv4, int8_t *ref4, uint8_t *mode);
+
+/* MV predictors of all 41 blocks of every MB and reference from a committed field: neighbours
+ * A (left), B (up), C (up-right, else D up-left) with the standard's availability (picture
+ * border, MB raster order, partition order inside the MB), then jmme_SetMotionVectorPredictor.
+ * pred: int16 [num_refs][mb_h*mb_w][41][2], the layout JMME_PRED_PER_BLOCK takes. */
+int jmme_predict_frame(jmme_ctx *ctx, const int16_t *mv4, const int8_t *ref4, int16_t *pred);
 
 /* (a12) 16 planes from one luma image; out[(yfrac*4+xfrac)] planes are contiguous, each
  * (width+2*pad) x (height+2*pad) bytes; width/height must be multiples of 16. */

@@ -568,6 +568,151 @@ int jmme_SubPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *plan
     return JMME_OK;
 }
 
+/* ---- (a3) SetMotionVectorPredictor ‖ GetMotionVectorPredictorNormal [STD 8.4.1.3] ------------ */
+static int median3(int a, int b, int c)
+{
+    int mn = a < b ? (a < c ? a : c) : (b < c ? b : c);
+    int mx = a > b ? (a > c ? a : c) : (b > c ? b : c);
+    return a + b + c - mn - mx;
+}
+int jmme_SetMotionVectorPredictor(int blocktype, int part, int ref_idx, const int16_t mvA[2], int refA, int availA,
+                                  const int16_t mvB[2], int refB, int availB, const int16_t mvC[2], int refC,
+                                  int availC, int16_t pred[2])
+{
+    int a[2], b[2], c[2], k, n;
+    if (blocktype < 1 || blocktype > 7 || !mvA || !mvB || !mvC || !pred) return JMME_ERR_PARAM;
+    for (k = 0; k < 2; k++) { a[k] = availA ? mvA[k] : 0; b[k] = availB ? mvB[k] : 0; c[k] = availC ? mvC[k] : 0; }
+    if (!availA) refA = -1;
+    if (!availB) refB = -1;
+    if (!availC) refC = -1;
+    if (refA < 0) a[0] = a[1] = 0;                     /* intra / other list: no vector */
+    if (refB < 0) b[0] = b[1] = 0;
+    if (refC < 0) c[0] = c[1] = 0;
+    /* directional prediction of 16x8 and 8x16 */
+    if (blocktype == 2) {
+        if (part == 0 && refB == ref_idx) { pred[0] = (int16_t)b[0]; pred[1] = (int16_t)b[1]; return JMME_OK; }
+        if (part == 1 && refA == ref_idx) { pred[0] = (int16_t)a[0]; pred[1] = (int16_t)a[1]; return JMME_OK; }
+    } else if (blocktype == 3) {
+        if (part == 0 && refA == ref_idx) { pred[0] = (int16_t)a[0]; pred[1] = (int16_t)a[1]; return JMME_OK; }
+        if (part == 1 && refC == ref_idx) { pred[0] = (int16_t)c[0]; pred[1] = (int16_t)c[1]; return JMME_OK; }
+    }
+    /* median prediction */
+    if (!availB && !availC && availA) {
+        b[0] = c[0] = a[0]; b[1] = c[1] = a[1]; refB = refC = refA;
+    }
+    n = (refA == ref_idx) + (refB == ref_idx) + (refC == ref_idx);
+    if (n == 1) {
+        const int *m = refA == ref_idx ? a : (refB == ref_idx ? b : c);
+        pred[0] = (int16_t)m[0]; pred[1] = (int16_t)m[1];
+    } else {
+        pred[0] = (int16_t)median3(a[0], b[0], c[0]);
+        pred[1] = (int16_t)median3(a[1], b[1], c[1]);
+    }
+    return JMME_OK;
+}
+
+/* Is field cell (x,y) (4x4 units, frame coordinates) decoded before block `blk` of MB (mbx,mby)? */
+static int cell_available(const jmme_ctx *c, int x, int y, int mbx, int mby, int t, int x0, int y0)
+{
+    int mx, my, lx, ly, w = blc_w[t], h = blc_h[t];
+    if (x < 0 || y < 0 || x >= 4 * c->mb_w || y >= 4 * c->mb_h) return 0;
+    mx = x >> 2; my = y >> 2;
+    if (my != mby) return my < mby;                 /* rows above: decoded; rows below: not */
+    if (mx != mbx) return mx < mbx;                 /* same row: only MBs to the left */
+    lx = (x & 3) * 4; ly = (y & 3) * 4;             /* same MB: partition decoding order */
+    if (t == 1) return 0;
+    if (t == 2) return (ly >= 8) < (y0 >= 8);
+    if (t == 3) return (lx >= 8) < (x0 >= 8);
+    {
+        int q = 2 * (y0 >= 8) + (x0 >= 8), qc = 2 * (ly >= 8) + (lx >= 8);
+        int s = ((y0 & 7) / h) * (8 / w) + ((x0 & 7) / w), sc = ((ly & 7) / h) * (8 / w) + ((lx & 7) / w);
+        if (qc != q) return qc < q;
+        return sc < s;
+    }
+}
+
+int jmme_predict_frame(jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int16_t *pred)
+{
+    int r, mb, t, fw;
+    static const int16_t zero[2] = {0, 0};
+    if (!c || !mv4 || !ref4 || !pred) return JMME_ERR_PARAM;
+    fw = 4 * c->mb_w;
+    for (r = 0; r < c->p.num_refs; r++)
+        for (mb = 0; mb < c->mb_w * c->mb_h; mb++) {
+            const int mbx = mb % c->mb_w, mby = mb / c->mb_w;
+            for (t = 1; t <= 7; t++) {
+                const int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh;
+                int j, i;
+                for (j = 0; j < nby; j++)
+                    for (i = 0; i < nbx; i++) {
+                        const int blk = blk_base[t] + j * nbx + i, x0 = i * bw, y0 = j * bh;
+                        const int cx = 4 * mbx + x0 / 4, cy = 4 * mby + y0 / 4, wc = bw / 4;
+                        const int nx[4] = {cx - 1, cx, cx + wc, cx - 1}, ny[4] = {cy, cy - 1, cy - 1, cy - 1};
+                        const int16_t *mv[4];
+                        int rf[4], av[4], k, part = t == 2 ? j : (t == 3 ? i : 0);
+                        int16_t *o = pred + (((size_t)r * c->mb_w * c->mb_h + mb) * JMME_BLOCKS_PER_MB + blk) * 2;
+                        for (k = 0; k < 4; k++) {
+                            av[k] = cell_available(c, nx[k], ny[k], mbx, mby, t, x0, y0);
+                            mv[k] = av[k] ? mv4 + ((size_t)ny[k] * fw + nx[k]) * 2 : zero;
+                            rf[k] = av[k] ? ref4[(size_t)ny[k] * fw + nx[k]] : -1;
+                        }
+                        if (!av[2]) { av[2] = av[3]; mv[2] = mv[3]; rf[2] = rf[3]; }     /* C := D */
+                        jmme_SetMotionVectorPredictor(t, part, r, mv[0], rf[0], av[0], mv[1], rf[1], av[1], mv[2], rf[2],
+                                                      av[2], o);
+                    }
+            }
+        }
+    return JMME_OK;
+}
+
+/* ME-only mode decision: DESIGN.md §2 */
+int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_t *ref4, uint8_t *mode)
+{
+    int mb, fw;
+    if (!c || !res || !mv4 || !ref4 || !mode) return JMME_ERR_PARAM;
+    fw = 4 * c->mb_w;
+    for (mb = 0; mb < c->mb_w * c->mb_h; mb++) {
+        const jmme_mbresult *m = &res[mb];
+        const int mbx = mb % c->mb_w, mby = mb / c->mb_w;
+        int64_t J[4], best;
+        int sub[4] = {0, 0, 0, 0}, q, t, k, md, cell;
+#define ON(tt) ((c->p.blocktype_mask >> (tt)) & 1)
+        J[0] = ON(1) ? m->cost[0] : INT64_MAX;
+        J[1] = ON(2) ? (int64_t)m->cost[1] + m->cost[2] : INT64_MAX;
+        J[2] = ON(3) ? (int64_t)m->cost[3] + m->cost[4] : INT64_MAX;
+        J[3] = 0;
+        for (q = 0; q < 4; q++) {
+            int64_t bq = INT64_MAX;
+            for (t = 4; t <= 7; t++) {
+                const int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, per = (8 / bw) * (8 / bh);
+                int64_t s = 0;
+                if (!ON(t)) continue;
+                for (k = 0; k < per; k++) {
+                    const int sx = (q & 1) * (8 / bw) + k % (8 / bw), sy = (q >> 1) * (8 / bh) + k / (8 / bw);
+                    s += m->cost[blk_base[t] + sy * nbx + sx];
+                }
+                if (s < bq) { bq = s; sub[q] = t; }
+            }
+            if (bq == INT64_MAX) { J[3] = INT64_MAX; break; }
+            J[3] += bq;
+        }
+        md = 0; best = J[0];
+        for (k = 1; k < 4; k++) if (J[k] < best) { best = J[k]; md = k; }
+        mode[5 * mb] = (uint8_t)(md == 3 ? 8 : md + 1);
+        for (q = 0; q < 4; q++) mode[5 * mb + 1 + q] = (uint8_t)(md == 3 ? sub[q] : 0);
+        for (cell = 0; cell < 16; cell++) {
+            const int cx4 = cell & 3, cy4 = cell >> 2, q8 = 2 * (cy4 >> 1) + (cx4 >> 1);
+            const int tt = md == 3 ? sub[q8] : md + 1;
+            const int bw = blc_w[tt], bh = blc_h[tt], nbx = 16 / bw;
+            const int blk = blk_base[tt] + ((4 * cy4) / bh) * nbx + (4 * cx4) / bw;
+            const size_t o = (size_t)(4 * mby + cy4) * fw + 4 * mbx + cx4;
+            mv4[2 * o] = m->mv[blk][0]; mv4[2 * o + 1] = m->mv[blk][1]; ref4[o] = m->ref_idx[blk];
+        }
+#undef ON
+    }
+    return JMME_OK;
+}
+
 /* ---- (a4,a5) PartitionMotionSearch / BlockMotionSearch over a frame ----------------------- */
 /* every (reference, blocktype, block) of one macroblock; bsad = scratch [41][ncand] (FASTFULL) */
 static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred, jmme_mbresult *out,

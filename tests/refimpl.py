@@ -121,3 +121,95 @@ def brute_search(cur, refp, pad, bx, by, bw, bh, cx, cy, px, py, R, f, bonus=0, 
         if best is None or c < best[2]:
             best = (mx, my, c)
     return best
+
+
+# ---- MV prediction (H.264 8.4.1.3) and the ME-only commit rule, restated independently --------------
+def mv_predict(t, part, ref, A, B, Cn):
+    """A, B, Cn = (mvx, mvy, ref, avail); Cn is D when C is unavailable."""
+    def norm(n):
+        return [n[0], n[1], n[2], n[3]] if (n[3] and n[2] >= 0) else [0, 0, -1, n[3]]
+    A, B, Cn = norm(A), norm(B), norm(Cn)
+    if t == 2 and part == 0 and B[2] == ref:
+        return B[0], B[1]
+    if t == 2 and part == 1 and A[2] == ref:
+        return A[0], A[1]
+    if t == 3 and part == 0 and A[2] == ref:
+        return A[0], A[1]
+    if t == 3 and part == 1 and Cn[2] == ref:
+        return Cn[0], Cn[1]
+    if not B[3] and not Cn[3] and A[3]:
+        B, Cn = list(A), list(A)
+    same = [n for n in (A, B, Cn) if n[2] == ref]
+    if len(same) == 1:
+        return same[0][0], same[0][1]
+    return sorted([A[0], B[0], Cn[0]])[1], sorted([A[1], B[1], Cn[1]])[1]
+
+
+def decode_rank(t, x, y):
+    """Decoding order of the partition of blocktype t that contains pixel (x, y) of the MB."""
+    from jmme import abi
+    w, h = abi.BLC[t]
+    if t <= 3:
+        return (y // h) * (16 // w) + x // w
+    return (2 * (y // 8) + x // 8) * 16 + ((y % 8) // h) * (8 // w) + (x % 8) // w
+
+
+def predict_frame(mv4, ref4, mb_w, mb_h, num_refs):
+    from jmme import abi
+    blocks = abi.block_table()
+    pred = np.zeros((num_refs, mb_w * mb_h, 41, 2), np.int16)
+    for r in range(num_refs):
+        for mb in range(mb_w * mb_h):
+            mbx, mby = mb % mb_w, mb // mb_w
+            for b, (t, x0, y0, w, h) in enumerate(blocks):
+                def nb(px, py):                                    # neighbour at MB-relative pixel (px, py)
+                    gx, gy = 16 * mbx + px, 16 * mby + py
+                    if gx < 0 or gy < 0 or gx >= 16 * mb_w or gy >= 16 * mb_h:
+                        return (0, 0, -1, 0)
+                    nmx, nmy = gx // 16, gy // 16
+                    if (nmy, nmx) > (mby, mbx):
+                        return (0, 0, -1, 0)                       # a later macroblock
+                    if (nmy, nmx) == (mby, mbx) and decode_rank(t, px, py) >= decode_rank(t, x0, y0):
+                        return (0, 0, -1, 0)                       # a later partition of this macroblock
+                    return (int(mv4[gy // 4, gx // 4, 0]), int(mv4[gy // 4, gx // 4, 1]), int(ref4[gy // 4, gx // 4]), 1)
+                A, B, Cc, D = nb(x0 - 1, y0), nb(x0, y0 - 1), nb(x0 + w, y0 - 1), nb(x0 - 1, y0 - 1)
+                part = (y0 // 8) if t == 2 else ((x0 // 8) if t == 3 else 0)
+                pred[r, mb, b] = mv_predict(t, part, r, A, B, Cc if Cc[3] else D)
+    return pred
+
+
+def commit_field(res, mb_w, mb_h, mask=0xFE):
+    from jmme import abi
+    blocks = abi.block_table()
+    mv4 = np.zeros((4 * mb_h, 4 * mb_w, 2), np.int16)
+    ref4 = np.zeros((4 * mb_h, 4 * mb_w), np.int8)
+    mode = np.zeros((mb_w * mb_h, 5), np.uint8)
+    INF = float("inf")
+    for mb in range(mb_w * mb_h):
+        cost = res[mb]["cost"].astype(np.int64)
+        of_type = lambda t: [b for b, blk in enumerate(blocks) if blk[0] == t]              # noqa: E731
+        J = [sum(cost[b] for b in of_type(t)) if (mask >> t) & 1 else INF for t in (1, 2, 3)]
+        sub, j8 = [0] * 4, 0
+        for q in range(4):
+            cands = []
+            for t in (4, 5, 6, 7):
+                if (mask >> t) & 1:
+                    inside = [b for b in of_type(t) if 2 * (blocks[b][2] // 8) + blocks[b][1] // 8 == q]
+                    cands.append((sum(cost[b] for b in inside), t))
+            if not cands:
+                j8 = INF
+                break
+            c, sub[q] = min(cands)                                   # ties -> lower blocktype
+            j8 += c
+        J.append(j8)
+        md = J.index(min(J))                                          # ties -> lower mode
+        mode[mb] = [8 if md == 3 else md + 1] + ([*sub] if md == 3 else [0, 0, 0, 0])
+        for cy in range(4):
+            for cx in range(4):
+                t = sub[2 * (cy // 2) + cx // 2] if md == 3 else md + 1
+                b = next(b for b in of_type(t) if blocks[b][1] <= 4 * cx < blocks[b][1] + blocks[b][3]
+                         and blocks[b][2] <= 4 * cy < blocks[b][2] + blocks[b][4])
+                mbx, mby = mb % mb_w, mb // mb_w
+                mv4[4 * mby + cy, 4 * mbx + cx] = res[mb]["mv"][b]
+                ref4[4 * mby + cy, 4 * mbx + cx] = res[mb]["ref_idx"][b]
+    return mv4, ref4, mode

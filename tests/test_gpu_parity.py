@@ -310,3 +310,34 @@ def test_full_search_with_per_block_windows(cuda, oracle, rdopt, subpel):
     assert_same(g, o, "best")
     kw["blocktype_mask"] = 0x8A                                  # 16x16, 8x16, 4x4
     assert_same(run(cuda, cur, refs, pred, **kw), run(oracle, cur, refs, pred, **kw), "masked")
+
+
+def test_predictor_commit_and_closed_loop(cuda, oracle):
+    """a3: SetMotionVectorPredictor, the ME-only field commit and the frame-wide predictor kernel, then the
+    closed loop search -> commit -> predict -> search with per-block predictors, all against the oracle."""
+    rng = np.random.default_rng(9)
+    for _ in range(500):
+        nb = [(int(rng.integers(-64, 65)), int(rng.integers(-64, 65)), int(rng.integers(-1, 3)), int(rng.integers(0, 2)))
+              for _ in range(3)]
+        t, part, ref = int(rng.integers(1, 8)), int(rng.integers(0, 2)), int(rng.integers(0, 3))
+        assert cuda.set_motion_vector_predictor(t, part, ref, *nb) == oracle.set_motion_vector_predictor(t, part, ref, *nb)
+    w, h, R = 96, 80, 8
+    cur, refs = synth.frame_pair(w, h, seed=17, search_range=R, num_refs=2)
+    for mask in (abi.MASK_ALL, 0x92):
+        kw = dict(width=w, height=h, search_range=R, num_refs=2, qp=31, rdopt=1, subpel=1, blocktype_mask=mask)
+        with cuda.context(**kw) as g, oracle.context(**kw) as o:
+            for i, r in enumerate(refs):
+                g.set_reference(i, r)
+                o.set_reference(i, r)
+            rg, ro = g.search_frame(cur), o.search_frame(cur)
+            assert_same(rg, ro, "pass 1")
+            fg, fo = g.commit_field(rg), o.commit_field(ro)
+            for a, b in zip(fg, fo):
+                assert np.array_equal(a, b)
+            fo[1][3, 5] = -1
+            pg, po = g.predict_frame(fo[0], fo[1]), o.predict_frame(fo[0], fo[1])
+            assert np.array_equal(pg, po)
+        kw["pred_policy"] = abi.PRED_PER_BLOCK
+        assert_same(run(cuda, cur, refs, po, **{k: v for k, v in kw.items() if k not in ("width", "height", "num_refs")}),
+                    run(oracle, cur, refs, po, **{k: v for k, v in kw.items() if k not in ("width", "height", "num_refs")}),
+                    "pass 2")
