@@ -12,6 +12,8 @@
 namespace {
 
 __constant__ int8_t c_sp9[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
+// the same table as compile-time constants for the unrolled position loop
+__device__ constexpr int c_sp9h[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
 // block index of the 4x4 cell (cx4, cy4) for each blocktype
 __device__ __forceinline__ int block_of_cell(int t, int cx4, int cy4)
 {
@@ -74,14 +76,15 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
     const size_t psz = (size_t)P.pstride * P.pheight;
     const uint8_t *planes = P.planes[ref];
 
-    // this cell of the current MB, as 16 ints
-    int c[16];
+    // this cell of the current MB: raw words (SAD) and 16-bit lane pairs (c0|c2<<16), (c1|c3<<16) per row (SATD)
+    uint32_t cw[4], ca[4], cb[4];
     {
         const uint8_t *cp = P.cur + (size_t)(16 * mby + 4 * cy4) * P.cur_stride + 16 * mbx + 4 * cx4;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const uint32_t w = *(const uint32_t *)(cp + (size_t)y * P.cur_stride);
-            c[4 * y] = w & 255; c[4 * y + 1] = (w >> 8) & 255; c[4 * y + 2] = (w >> 16) & 255; c[4 * y + 3] = w >> 24;
+            cw[y] = *(const uint32_t *)(cp + (size_t)y * P.cur_stride);
+            ca[y] = __byte_perm(cw[y], 0, 0x4240);
+            cb[y] = __byte_perm(cw[y], 0, 0x4341);
         }
     }
     int mvx, mvy, mn, px = 0, py = 0;
@@ -97,32 +100,64 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
     }
     // reference position of this cell at MV (0,0), in padded-plane coordinates
     const int rx0 = P.pad + 16 * mbx + 4 * cx4, ry0 = P.pad + 16 * mby + 4 * cy4;
+    const int pw = P.pstride >> 2;
+    const unsigned lf = (unsigned)P.lambda_factor;       // lambda_factor * bits < 2^31: 32-bit product is exact
 
     for (int step = 2; step >= 1; step--) {
         const int pos0 = (step == 2 && P.use_hadamard) ? 0 : 1;
         const int ox = mvx, oy = mvy;
         int best = 0;
-        for (int pos = pos0; pos < 9; pos++) {
-            const int qx = ox + step * c_sp9[pos][0], qy = oy + step * c_sp9[pos][1];
+        // MV bits of the three x and three y offsets of this step (the nine positions combine them)
+        int bitx[3], bity[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            bitx[j] = d_se_bits(ox + (j - 1) * step - px);
+            bity[j] = d_se_bits(oy + (j - 1) * step - py);
+        }
+#pragma unroll
+        for (int pos = 0; pos < 9; pos++) {
+            if (pos < pos0) continue;
+            const int sx = c_sp9h[pos][0], sy = c_sp9h[pos][1];     // compile-time after unrolling
+            const int qx = ox + step * sx, qy = oy + step * sy;
             int v = 0;
             if (active) {
                 const size_t off = psz * ((qy & 3) * 4 + (qx & 3)) + (size_t)(ry0 + (qy >> 2)) * P.pstride + (rx0 + (qx >> 2));
                 const uint32_t *rp = (const uint32_t *)(planes + (off & ~(size_t)3));
-                const int sh = (int)(off & 3) * 8, pw = P.pstride >> 2;
-                int d[16];
+                const int sh = (int)(off & 3) * 8;
+                uint32_t w[4];
 #pragma unroll
-                for (int y = 0; y < 4; y++) {
-                    const uint32_t w = __funnelshift_r(__ldg(rp + y * pw), __ldg(rp + y * pw + 1), sh);
-                    d[4 * y] = c[4 * y] - (int)(w & 255);
-                    d[4 * y + 1] = c[4 * y + 1] - (int)((w >> 8) & 255);
-                    d[4 * y + 2] = c[4 * y + 2] - (int)((w >> 16) & 255);
-                    d[4 * y + 3] = c[4 * y + 3] - (int)(w >> 24);
-                }
+                for (int y = 0; y < 4; y++) w[y] = __funnelshift_r(__ldg(rp + y * pw), __ldg(rp + y * pw + 1), sh);
                 if (P.use_hadamard) {
-                    v = satd16(d, P.satd_round);
-                } else {
+                    // 4x4 Hadamard on 16-bit lane pairs held as plain integers (hi*65536 + lo, |lane| <= 2040):
+                    // ordinary 32-bit add/sub act on both lanes.  The last butterfly stage pairs the two
+                    // lanes of one register: |lo+hi| + |lo-hi| = 2 max(|lo|,|hi|), so SATD = sum of the maxima.
+                    int s4[4], t4[4];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) v += abs(d[k]);
+                    for (int y = 0; y < 4; y++) {
+                        const int da = (int)(ca[y] - __byte_perm(w[y], 0, 0x4240));   // (d0, d2)
+                        const int db = (int)(cb[y] - __byte_perm(w[y], 0, 0x4341));   // (d1, d3)
+                        s4[y] = da + db;                                               // (d0+d1, d2+d3)
+                        t4[y] = da - db;                                               // (d0-d1, d2-d3)
+                    }
+                    unsigned acc = 0;
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        const int *r4 = g ? t4 : s4;
+                        const int u0 = r4[0] + r4[1], u1 = r4[0] - r4[1], u2 = r4[2] + r4[3], u3 = r4[2] - r4[3];
+                        const int y4[4] = {u0 + u2, u0 - u2, u1 + u3, u1 - u3};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int lo = (int)(short)y4[k];
+                            const int hi = (y4[k] - lo) >> 16;
+                            acc += (unsigned)max(abs(lo), abs(hi));
+                        }
+                    }
+                    v = (int)acc;                        // = sum|coef| / 2 exactly, for both satd_round settings
+                } else {
+                    unsigned acc = 0;
+#pragma unroll
+                    for (int y = 0; y < 4; y++) acc = sad4(cw[y], w[y], acc);
+                    v = (int)acc;
                 }
             }
             // sum the cells of this block: masked XOR butterfly inside the half-warp
@@ -131,7 +166,7 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
                 const int u = __shfl_xor_sync(0xFFFFFFFFu, v, o);
                 if (need & o) v += u;
             }
-            int cst = d_weighted_cost(P.lambda_factor, d_se_bits(qx - px) + d_se_bits(qy - py)) + v;
+            int cst = (int)((lf * (unsigned)(bitx[sx + 1] + bity[sy + 1])) >> 16) + v;
             if (qx == 0 && qy == 0) cst -= bonus;
             if (cst < mn) { mn = cst; best = pos; }
         }
