@@ -36,6 +36,8 @@ struct jmme_ctx {
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
     int device, num_sms, K;
     cudaStream_t stream;
+    cudaStream_t copy_stream;             // host->device copy of the current picture, overlaps the plane kernel
+    cudaEvent_t ev_copy;
     uint8_t *d_raw;                       // staging for the raw current picture (width x height)
     uint8_t *d_raw_ref[JMME_MAX_REFS];    // staging for the raw reference pictures
     uint8_t *d_planes[JMME_MAX_REFS];
@@ -100,6 +102,8 @@ void free_device(jmme_ctx *c)
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 2; j++)
             if (c->ev_prof[i][j]) cudaEventDestroy(c->ev_prof[i][j]);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -155,6 +159,8 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         CUC(cudaSetDevice(device));
         CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
         CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         CUC(cudaMalloc(&c->d_raw, (size_t)p->width * p->height));
         for (int r = 0; r < p->num_refs; r++) {
@@ -214,13 +220,18 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     const uint8_t *cur = d_cur;
     int cs = stride;
     // the search kernel fetches the current MB with 16-byte cp.async: rows must be 16-byte aligned
-    if (c->w16 != c->p.width || c->h16 != c->p.height || (stride & 15) || ((uintptr_t)d_cur & 15)) {
+    // (rows below the picture are handled in the kernels by clamping the row index: only a width that is
+    // not a multiple of 16 needs the padded copy)
+    int cur_h = c->p.height;
+    if (c->w16 != c->p.width || (stride & 15) || ((uintptr_t)d_cur & 15)) {
         CU(c, jmme_launch_pad_cur(d_cur, c->p.width, c->p.height, stride, c->w16, c->h16, c->d_cur16, st));
         c->launches++;
-        cur = c->d_cur16; cs = c->w16;
+        cur = c->d_cur16; cs = c->w16; cur_h = c->h16;
     }
     SearchParams P;
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
+    P.cur_h = cur_h;
+    P.fused_select = c->p.num_refs == 1 && c->p.subpel;
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
     if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[1][0], st));
     if (c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK)
@@ -235,10 +246,12 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[2][1], st)); c->prof_valid[2] = true; }
         c->launches++;
     }
-    if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[3][0], st));
-    CU(c, jmme_launch_select(P, st));
-    if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[3][1], st)); c->prof_valid[3] = true; }
-    c->launches++;
+    if (!P.fused_select) {
+        if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[3][0], st));
+        CU(c, jmme_launch_select(P, st));
+        if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[3][1], st)); c->prof_valid[3] = true; }
+        c->launches++;
+    }
     return JMME_OK;
 }
 
@@ -540,8 +553,11 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
             // only the current-picture rows of this stripe (row h-1 stands in for the replicated rows below it)
             const int s0 = std::min(16 * s->p.mb_row_begin, s->p.height - 1);
             const int s1 = std::min(16 * s->p.mb_row_end, s->p.height);
+            // on its own stream: overlaps a plane kernel still running from jmme_set_reference (async_reference)
             CU(c, cudaMemcpy2DAsync(s->d_raw + (size_t)s0 * s->p.width, s->p.width, cur + (size_t)s0 * stride, stride,
-                                    s->p.width, std::max(s1 - s0, 1), cudaMemcpyHostToDevice, s->stream));
+                                    s->p.width, std::max(s1 - s0, 1), cudaMemcpyHostToDevice, s->copy_stream));
+            CU(c, cudaEventRecord(s->ev_copy, s->copy_stream));
+            CU(c, cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
         }
         if (pred_elems)
             CU(c, cudaMemcpyAsync(s->d_pred, pred, pred_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));

@@ -22,6 +22,7 @@ struct __align__(8) BlkRes {
 struct SearchParams {
     const uint8_t *cur;                  // current luma, w16 x h16, stride cur_stride
     int cur_stride;
+    int cur_h;                           // valid rows of `cur`; MB rows below replicate row cur_h-1
     const uint8_t *planes[JMME_MAX_REFS];// per reference: n_planes padded planes, plane 0 = integer
     int pstride, pheight;                // padded plane geometry
     int pad;
@@ -40,6 +41,7 @@ struct SearchParams {
     BlkRes *res;                         // [ref][mb][41]
     jmme_mbresult *out;                  // [mb]
     jmme_mbresult *out_per_ref;          // [ref][mb] or null
+    int fused_select;                    // 1: the sub-pel kernel writes `out` itself (one reference)
 };
 
 __device__ __forceinline__ int d_se_bits(int v)

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
 
     if (tid < 64) {
         const int row = tid >> 2, w = tid & 3;
-        s_cur[tid] = *(const uint32_t *)(P.cur + (size_t)(16 * mby + row) * P.cur_stride + 16 * mbx + 4 * w);
+        s_cur[tid] = *(const uint32_t *)(P.cur + (size_t)min(16 * mby + row, P.cur_h - 1) * P.cur_stride + 16 * mbx + 4 * w);
     }
     if (tid < JMME_NBLK) s_best[tid] = ~0ull;
     __syncthreads();

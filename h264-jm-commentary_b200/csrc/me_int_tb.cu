@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                     cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
         }
         if (tid < 16)
-            cp_async16(s_cur2 + buf * 64 + 4 * tid, P.cur + (size_t)(16 * it.mby + tid) * P.cur_stride + 16 * it.mbx);
+            cp_async16(s_cur2 + buf * 64 + 4 * tid, P.cur + (size_t)min(16 * it.mby + tid, P.cur_h - 1) * P.cur_stride + 16 * it.mbx);
         cp_async_commit();
     };
     auto expand = [&](const Item &it) {

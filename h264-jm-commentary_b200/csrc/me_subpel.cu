@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
     // this cell of the current MB: raw words (SAD) and 16-bit lane pairs (c0|c2<<16), (c1|c3<<16) per row (SATD)
     uint32_t cw[4], ca[4], cb[4];
     {
-        const uint8_t *cp = P.cur + (size_t)(16 * mby + 4 * cy4) * P.cur_stride + 16 * mbx + 4 * cx4;
+        const uint8_t *cp = P.cur + 16 * mbx + 4 * cx4;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            cw[y] = *(const uint32_t *)(cp + (size_t)y * P.cur_stride);
+            cw[y] = *(const uint32_t *)(cp + (size_t)min(16 * mby + 4 * cy4 + y, P.cur_h - 1) * P.cur_stride);
             ca[y] = __byte_perm(cw[y], 0, 0x4240);
             cb[y] = __byte_perm(cw[y], 0, 0x4341);
         }
@@ -174,10 +174,30 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
         mvy = oy + step * c_sp9[best][1];
     }
     // the lane that owns the block's top-left cell publishes the result
-    if (active && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2)) {
+    const bool owner = t <= 7 && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2);
+    if (active && owner) {
         BlkRes r;
         r.mvx = (int16_t)mvx; r.mvy = (int16_t)mvy; r.cost = mn;
         res[b] = r;
+    }
+    if (P.fused_select) {
+        // one reference: nothing to choose, the record of select_ref_kernel is written here
+        jmme_mbresult *o = P.out + mb;
+        jmme_mbresult *q = P.out_per_ref ? P.out_per_ref + mb : nullptr;
+        if (owner) {
+            o->mv[b][0] = active ? (int16_t)mvx : (int16_t)0;
+            o->mv[b][1] = active ? (int16_t)mvy : (int16_t)0;
+            o->cost[b] = active ? mn + d_ref_cost(P.lambda_factor, P.rdopt, 0) : INT_MAX;
+            o->ref_idx[b] = active ? (int8_t)0 : (int8_t)-1;
+            if (q) {
+                q->mv[b][0] = o->mv[b][0]; q->mv[b][1] = o->mv[b][1];
+                q->cost[b] = active ? mn : INT_MAX; q->ref_idx[b] = o->ref_idx[b];
+            }
+        }
+        if (tid < 3) {
+            o->reserved[tid] = 0;
+            if (q) q->reserved[tid] = 0;
+        }
     }
 }
 
