@@ -78,6 +78,13 @@ int fail(jmme_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
 
 int pad_for(int R) { return (2 * R + 16 + 15) & ~15; }
 
+// rows of `width` bytes host -> device; one linear copy when the source rows are contiguous
+cudaError_t upload_rows(uint8_t *dst, const uint8_t *src, int stride, int width, int rows, cudaStream_t st)
+{
+    if (stride == width) return cudaMemcpyAsync(dst, src, (size_t)width * rows, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, width, src, stride, width, rows, cudaMemcpyHostToDevice, st);
+}
+
 // JM spiral order generated from its closed form: ring l = max(|dx|,|dy|), then the
 // top/bottom rows interleaved, then the left/right columns interleaved.
 int spiral_index(int dx, int dy)
@@ -395,8 +402,8 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
         const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
         const int s0 = std::min(std::max(yb - c->pad - 3, 0), c->p.height - 1);
         const int s1 = std::min(std::max(ye - c->pad + 3, 1), c->p.height);          // exclusive; clamps hit row h-1
-        CU(c, cudaMemcpy2DAsync(c->d_raw_ref[r] + (size_t)s0 * c->p.width, c->p.width, luma + (size_t)s0 * stride, stride,
-                                c->p.width, s1 - s0, cudaMemcpyHostToDevice, c->stream));
+        CU(c, upload_rows(c->d_raw_ref[r] + (size_t)s0 * c->p.width, luma + (size_t)s0 * stride, stride, c->p.width, s1 - s0,
+                          c->stream));
     }
     int rc = jmme_set_reference_dev(c, r, c->d_raw_ref[r], c->p.width, c->stream);
     if (rc != JMME_OK) return rc;
@@ -554,8 +561,8 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
             const int s0 = std::min(16 * s->p.mb_row_begin, s->p.height - 1);
             const int s1 = std::min(16 * s->p.mb_row_end, s->p.height);
             // on its own stream: overlaps a plane kernel still running from jmme_set_reference (async_reference)
-            CU(c, cudaMemcpy2DAsync(s->d_raw + (size_t)s0 * s->p.width, s->p.width, cur + (size_t)s0 * stride, stride,
-                                    s->p.width, std::max(s1 - s0, 1), cudaMemcpyHostToDevice, s->copy_stream));
+            CU(c, upload_rows(s->d_raw + (size_t)s0 * s->p.width, cur + (size_t)s0 * stride, stride, s->p.width,
+                              std::max(s1 - s0, 1), s->copy_stream));
             CU(c, cudaEventRecord(s->ev_copy, s->copy_stream));
             CU(c, cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
         }
