@@ -6,100 +6,138 @@
 // intermediates with (x+512)>>10, quarter-pel (p+q+1)>>1.
 //
 // HBM-bound pass: per padded pixel 1 byte read, 16 bytes written (17 B algorithmic).  A CTA
-// produces a 128x8 tile of all 16 planes from a (128+6)x(8+6) integer tile staged in shared
-// memory; the unrounded horizontal intermediates b1 are staged once and reused by the centre
-// filter; every thread packs 4 horizontally adjacent samples and stores one 32-bit word per plane
-// (a warp writes 128 contiguous bytes per plane row).
+// produces a 128x8 tile of all 16 planes from a (128+16)x(8+6) integer tile staged in shared
+// memory as words; the unrounded horizontal intermediates b1 are staged once and reused by the
+// centre filter; every thread owns 4 horizontally adjacent samples and stores one 32-bit word per
+// plane (a warp writes 128 contiguous bytes per plane row).
 #include "jmme_dev.cuh"
 
 namespace {
 
 constexpr int TW = 128, TH = 8;
-constexpr int GW = TW + 8, GH = TH + 6;      // integer tile: cols -2..TW+5, rows -2..TH+3
+constexpr int GH = TH + 6;                   // integer tile rows -2..TH+3
+constexpr int GWW = 36;                      // integer tile words per row: byte k = tile column k-4 (cols -4..139)
+constexpr int B1W = TW + 4;                  // b1 row stride (int16), multiple of 4 so that 4 values are one LDS.64
 
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f)
 {
-    return a - 5 * b + 20 * c + 20 * d - 5 * e + f;
+    return (a + f) - 5 * (b + e) + 20 * (c + d);
 }
 __device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int rnd5(int v) { return clip255((v + 16) >> 5); }
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d)
+{
+    return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+}
+// per-byte (a + b + 1) >> 1 of two packed words (5 ALU operations for 4 samples)
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) { return __vavgu4(a, b); }
 
-// src: raw picture w_in x h_in (stride), out: n_planes planes of ps x ph.
+// src: raw picture w_in x h_in (stride), out: n_planes planes of ps x ph; rows [y_begin, ...) are produced.
+// Thread (tx, ty) of the 32x8 CTA owns the 4 samples at tile columns 4tx..4tx+3 of tile row ty: everything it
+// needs comes from shared memory as aligned 32/64-bit words (integer tile: word tx+1 / tx+2 of six rows;
+// unrounded horizontal half-pels b1: four int16 = one LDS.64 of six rows); vertical 6-taps run on 16-bit lane
+// pairs (two columns per 32-bit operation); the twelve quarter-pel planes are byte-wise averages of packed words.
 __global__ void __launch_bounds__(256) interp_kernel(const uint8_t *__restrict__ src, int w_in, int h_in, int stride,
                                                      int pad, int ps, int ph, int n_planes, int y_begin,
                                                      uint8_t *__restrict__ out)
 {
-    __shared__ uint8_t Gs[GH][GW];
-    __shared__ int16_t B1s[GH][TW + 2];      // unrounded horizontal half-pel, cols 0..TW
+    __shared__ __align__(16) uint32_t Gs[GH][GWW];
+    __shared__ __align__(16) int16_t B1s[GH][B1W];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = y_begin + blockIdx.y * TH;   // padded-plane coordinates of the tile
+    const int sx0 = x0 - 4 - pad;                                     // picture column of tile byte 0
 
-    for (int i = tid; i < GH * GW; i += 256) {
-        int r = i / GW, c = i - r * GW;
-        int sx = d_clamp(x0 + c - 2 - pad, 0, w_in - 1), sy = d_clamp(y0 + r - 2 - pad, 0, h_in - 1);
-        Gs[r][c] = src[(size_t)sy * stride + sx];
-    }
-    __syncthreads();
-    if (n_planes == 1) {                     // integer plane only
-        const int tx = tid & 31, ty = tid >> 5;
-        const int x = x0 + 4 * tx, y = y0 + ty;
-        if (x < ps && y < ph) {
-            uint32_t v = Gs[ty + 2][4 * tx + 2] | (Gs[ty + 2][4 * tx + 3] << 8) | (Gs[ty + 2][4 * tx + 4] << 16) |
-                         (Gs[ty + 2][4 * tx + 5] << 24);
-            *(uint32_t *)(out + (size_t)y * ps + x) = v;
+    // ---- integer tile: rows are clamped (edge replication), columns use aligned words when the whole tile row
+    //      lies inside the picture, else clamped bytes --------------------------------------------------------
+    const bool words = sx0 >= 0 && sx0 + 4 * GWW <= w_in && !(stride & 3) && !((uintptr_t)src & 3);
+    if (words) {
+        for (int i = tid; i < GH * GWW; i += 256) {
+            const int r = i / GWW, k = i - r * GWW;
+            const int sy = d_clamp(y0 + r - 2 - pad, 0, h_in - 1);
+            Gs[r][k] = __ldg((const uint32_t *)(src + (size_t)sy * stride + sx0) + k);
         }
-        return;
-    }
-    for (int i = tid; i < GH * (TW + 1); i += 256) {
-        int r = i / (TW + 1), c = i - r * (TW + 1);           // b1 at tile column c, tile row r-2
-        const uint8_t *g = &Gs[r][c];                          // Gs column index = tile column + 2
-        B1s[r][c] = (int16_t)tap6(g[0], g[1], g[2], g[3], g[4], g[5]);
+    } else {
+        uint8_t *gb = (uint8_t *)&Gs[0][0];
+        for (int i = tid; i < GH * GWW * 4; i += 256) {
+            const int r = i / (GWW * 4), c = i - r * (GWW * 4);
+            const int sx = d_clamp(sx0 + c, 0, w_in - 1), sy = d_clamp(y0 + r - 2 - pad, 0, h_in - 1);
+            gb[i] = src[(size_t)sy * stride + sx];
+        }
     }
     __syncthreads();
-
     const int tx = tid & 31, ty = tid >> 5;
     const int x = x0 + 4 * tx, y = y0 + ty;
-    if (x >= ps || y >= ph) return;
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = 0;
-    int hprev;                                                  // h at column c (rounded)
-    {
-        const int c = 4 * tx + 2;
-        hprev = clip255((tap6(Gs[ty][c], Gs[ty + 1][c], Gs[ty + 2][c], Gs[ty + 3][c], Gs[ty + 4][c], Gs[ty + 5][c]) + 16) >> 5);
+    if (n_planes == 1) {                     // integer plane only
+        if (x < ps && y < ph) *(uint32_t *)(out + (size_t)y * ps + x) = Gs[ty + 2][tx + 1];
+        return;
     }
+    // ---- b1: unrounded horizontal half-pel of tile columns 0..TW-1, all GH rows, four per thread and pass -----
+    for (int i = tid; i < GH * (TW / 4); i += 256) {
+        const int r = i >> 5, q = i & 31;                    // tile columns 4q..4q+3 need bytes 4q+2..4q+10
+        const uint32_t w0 = Gs[r][q], w1 = Gs[r][q + 1], w2 = Gs[r][q + 2];
+        int e[9];
+        e[0] = (w0 >> 16) & 255; e[1] = w0 >> 24;
+        e[2] = w1 & 255; e[3] = (w1 >> 8) & 255; e[4] = (w1 >> 16) & 255; e[5] = w1 >> 24;
+        e[6] = w2 & 255; e[7] = (w2 >> 8) & 255; e[8] = (w2 >> 16) & 255;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = tap6(e[k], e[k + 1], e[k + 2], e[k + 3], e[k + 4], e[k + 5]);
+        uint2 pk;
+        pk.x = (uint32_t)(v[0] & 0xFFFF) | ((uint32_t)v[1] << 16);
+        pk.y = (uint32_t)(v[2] & 0xFFFF) | ((uint32_t)v[3] << 16);
+        *(uint2 *)&B1s[r][4 * q] = pk;
+    }
+    __syncthreads();
+    if (x >= ps || y >= ph) return;
+
+    const int r = ty + 2;                                    // tile row ty in Gs / B1s
+    // integer words of rows ty..ty+5 (tile rows ty-2..ty+3): columns 4tx..4tx+3 and 4tx+4..4tx+7
+    uint32_t wa[6], wb0[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { wa[k] = Gs[ty + k][tx + 1]; wb0[k] = Gs[ty + k][tx + 2] & 255; }
+    // vertical 6-tap on 16-bit lane pairs (columns 0|2 and 1|3), column 4 scalar
+    int h02, h13, h4;
+    {
+        int p02[6], p13[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { p02[k] = (int)__byte_perm(wa[k], 0, 0x4240); p13[k] = (int)__byte_perm(wa[k], 0, 0x4341); }
+        h02 = tap6(p02[0], p02[1], p02[2], p02[3], p02[4], p02[5]);
+        h13 = tap6(p13[0], p13[1], p13[2], p13[3], p13[4], p13[5]);
+        h4 = tap6((int)wb0[0], (int)wb0[1], (int)wb0[2], (int)wb0[3], (int)wb0[4], (int)wb0[5]);
+    }
+    int hv[5];
+    {
+        const int l02 = (int)(short)h02, l13 = (int)(short)h13;
+        hv[0] = rnd5(l02); hv[2] = rnd5((h02 - l02) >> 16);
+        hv[1] = rnd5(l13); hv[3] = rnd5((h13 - l13) >> 16);
+        hv[4] = rnd5(h4);
+    }
+    // b1 of rows r-2..r+3 at this thread's four columns
+    int b1v[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const uint2 p = *(const uint2 *)&B1s[ty + k][4 * tx];
+        b1v[k][0] = (int)(short)p.x; b1v[k][1] = (int)p.x >> 16;
+        b1v[k][2] = (int)(short)p.y; b1v[k][3] = (int)p.y >> 16;
+    }
+    int bv[4], sv[4], jv[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int tc = 4 * tx + q;           // tile column
-        const int c = tc + 2;                // Gs column
-        const int r = ty + 2;                // Gs / B1s row
-        const int g = Gs[r][c], gr = Gs[r][c + 1], gd = Gs[r + 1][c];
-        const int b = clip255((B1s[r][tc] + 16) >> 5);
-        const int s = clip255((B1s[r + 1][tc] + 16) >> 5);
-        const int h = hprev;
-        const int m = clip255((tap6(Gs[ty][c + 1], Gs[ty + 1][c + 1], Gs[ty + 2][c + 1], Gs[ty + 3][c + 1],
-                                    Gs[ty + 4][c + 1], Gs[ty + 5][c + 1]) + 16) >> 5);
-        hprev = m;
-        const int j = clip255((tap6(B1s[r - 2][tc], B1s[r - 1][tc], B1s[r][tc], B1s[r + 1][tc], B1s[r + 2][tc],
-                                    B1s[r + 3][tc]) + 512) >> 10);
-        const int sh = 8 * q;
-        // plane index = yfrac*4 + xfrac
-        w[0] |= (uint32_t)g << sh;
-        w[1] |= (uint32_t)((g + b + 1) >> 1) << sh;            // a (1,0)
-        w[2] |= (uint32_t)b << sh;                              // b (2,0)
-        w[3] |= (uint32_t)((gr + b + 1) >> 1) << sh;           // c (3,0)
-        w[4] |= (uint32_t)((g + h + 1) >> 1) << sh;            // d (0,1)
-        w[5] |= (uint32_t)((b + h + 1) >> 1) << sh;            // e (1,1)
-        w[6] |= (uint32_t)((b + j + 1) >> 1) << sh;            // f (2,1)
-        w[7] |= (uint32_t)((b + m + 1) >> 1) << sh;            // g (3,1)
-        w[8] |= (uint32_t)h << sh;                              // h (0,2)
-        w[9] |= (uint32_t)((h + j + 1) >> 1) << sh;            // i (1,2)
-        w[10] |= (uint32_t)j << sh;                             // j (2,2)
-        w[11] |= (uint32_t)((j + m + 1) >> 1) << sh;           // k (3,2)
-        w[12] |= (uint32_t)((gd + h + 1) >> 1) << sh;          // n (0,3)
-        w[13] |= (uint32_t)((h + s + 1) >> 1) << sh;           // p (1,3)
-        w[14] |= (uint32_t)((j + s + 1) >> 1) << sh;           // q (2,3)
-        w[15] |= (uint32_t)((m + s + 1) >> 1) << sh;           // r (3,3)
+        bv[q] = rnd5(b1v[2][q]);
+        sv[q] = rnd5(b1v[3][q]);
+        jv[q] = clip255((tap6(b1v[0][q], b1v[1][q], b1v[2][q], b1v[3][q], b1v[4][q], b1v[5][q]) + 512) >> 10);
     }
+    const uint32_t G = wa[2];
+    const uint32_t GR = __funnelshift_r(wa[2], Gs[r][tx + 2], 8);
+    const uint32_t GD = wa[3];
+    const uint32_t B = pack4(bv[0], bv[1], bv[2], bv[3]), S = pack4(sv[0], sv[1], sv[2], sv[3]);
+    const uint32_t H = pack4(hv[0], hv[1], hv[2], hv[3]), M = pack4(hv[1], hv[2], hv[3], hv[4]);
+    const uint32_t J = pack4(jv[0], jv[1], jv[2], jv[3]);
+    uint32_t w[16];                                          // plane index = yfrac*4 + xfrac
+    w[0] = G;           w[1] = avg4(G, B);  w[2] = B;   w[3] = avg4(GR, B);
+    w[4] = avg4(G, H);  w[5] = avg4(B, H);  w[6] = avg4(B, J);  w[7] = avg4(B, M);
+    w[8] = H;           w[9] = avg4(H, J);  w[10] = J;  w[11] = avg4(J, M);
+    w[12] = avg4(GD, H); w[13] = avg4(H, S); w[14] = avg4(J, S); w[15] = avg4(M, S);
     const size_t psz = (size_t)ps * ph;
     uint8_t *o = out + (size_t)y * ps + x;
 #pragma unroll
