@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -92,6 +92,15 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        d = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())[kernel]
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def int_peak_live():
@@ -261,6 +270,9 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
 
     # ---- device-resident timing ----------------------------------------------------------------
+    sampler = ClockSampler(local_rank)      # started early: nvidia-smi needs a moment before its first line
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
@@ -296,9 +308,6 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(3):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = ds.launch_count()
     barrier()
@@ -406,11 +415,14 @@ def run_ours(args, rank, world, local_rank):
             "kernel_ms": {"interp": k_itp, "me_int": k_int, "me_subpel": k_sub, "select_ref": k_sel,
                           "share_me_int": k_int / max(k_itp + k_int + k_sub + k_sel, 1e-9)},
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic("me_int_tb_kernel") if (world == 1 and args.workload.startswith("1080p_r32")) else None,
                          "kernel": "me_int_tb_kernel" if (R <= 32 and mask != 0x02) else "me_int_kernel",
                          "algorithmic_ops_per_candidate": ops_cand, "peak_source": peak_src},
             "roofline_interp": {"bound": "hbm", "achieved": itp_gbs, "peak": hbm, "unit": "GB/s",
-                                "frac": (itp_gbs / hbm) if itp_gbs else None, "traffic": None,
+                                "frac": (itp_gbs / hbm) if itp_gbs else None,
+                                "traffic": ncu_traffic("interp_kernel") if (world == 1 and args.workload.startswith("1080p_r32")) else None,
+                                "note": "the planes (41.5 MB) stay in the 126 MB L2 and are read from there by the sub-pel kernel",
                                 "kernel": "interp_kernel", "algorithmic_bytes_per_pixel": 17, "peak_source": hbm_src},
             "clocks": clocks,
         }

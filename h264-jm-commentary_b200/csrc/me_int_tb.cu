@@ -20,8 +20,8 @@ namespace {
 
 struct TbLayout {
     int RS, rows, RAWW;                 // window row stride (words, == 2 mod 4), rows, raw row words
-    int off_win, off_raw, off_cur, off_T, off_best, off_task, off_key, off_bx, off_by, total_words;
-    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem, int K)
+    int off_win, off_raw, off_cur, off_T, off_best, off_task, off_key, off_bx, off_by, off_kr, total_words;
+    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem, int K, bool kr_table = false)
     {
         const int ncols = 2 * R + 1;
         RS = 2 * R + 13;                // word positions 0 .. 2R+12
@@ -38,7 +38,8 @@ struct TbLayout {
         off_bx = off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0);
         const int nb = per_block ? JMME_NBLK : 1;
         off_by = off_bx + (nb * ncols + 3) / 4;
-        total_words = off_by + (nb * ncols + 3) / 4;
+        off_kr = off_by + (nb * ncols + 3) / 4;         // rate+key of every candidate (zero predictors only)
+        total_words = off_kr + (kr_table ? ncols * ncols : 0);
     }
 };
 
@@ -63,11 +64,13 @@ struct Item {
 // RS_CT: compile-time window row stride (0 = from the layout at run time): row addresses become immediates
 // KEYG: read the spiral keys from global memory (L1) instead of a shared-memory copy — frees 33 KB at R = 64
 // so that two CTAs fit on an SM
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG>
+// KRTAB: zero predictors (P.pred == nullptr): centre and rate are the same for every item, so rate + key of
+// all (2R+1)^2 candidates is tabulated once per CTA and a candidate costs one LDS instead of three
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const TbLayout L(P.R, PER_BLOCK, !KEYG, K);
+    const TbLayout L(P.R, PER_BLOCK, !KEYG, K, KRTAB);
     uint32_t *s_win = smem + L.off_win;
     uint32_t *s_raw = smem + L.off_raw;
     uint32_t *s_cur2 = smem + L.off_cur;
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     uint16_t *s_key = (uint16_t *)(smem + L.off_key);
     uint8_t *s_bx = (uint8_t *)(smem + L.off_bx);
     uint8_t *s_by = (uint8_t *)(smem + L.off_by);
+    uint32_t *s_kr = smem + L.off_kr;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int half = lane >> 4, l16 = lane & 15;
@@ -109,6 +113,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     for (int i = tid; i < n_main; i += NW * 32) {
         const int run = i / nseg, seg = i - run * nseg;
         s_task[i] = (uint16_t)((min(run * K, ncols - K) << 8) | (16 * seg));
+    }
+    if constexpr (KRTAB) {                               // needs s_T and s_key: built after a barrier
+        __syncthreads();
+        const bool pt = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
+        for (int i = tid; i < ncand; i += NW * 32) {
+            const int yo = i / ncols, xo = i - yo * ncols;
+            const unsigned key = (pt && xo == R && yo == R) ? 0u : (unsigned)s_key[i];    // MV (0,0) pre-test
+            s_kr[i] = s_T[d_se_bits(4 * (xo - R)) + d_se_bits(4 * (yo - R))] + key;
+        }
     }
     int res_g = l16 / wr;                                // residual task: run offset and column of this lane
     int res_x = 16 * nseg + (l16 - res_g * wr);
@@ -251,11 +264,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc[k][i] = 0;
 
-            const unsigned bx0 = s_bx[xoff];
+            const unsigned bx0 = KRTAB ? 0u : (unsigned)s_bx[xoff];
             auto pack = [&](int k, unsigned (&pk)[NL]) {
                 const int yoff = ybase + k;
-                unsigned key;
-                if constexpr (KEYG) {
+                unsigned key = 0;
+                if constexpr (KRTAB) {
+                } else if constexpr (KEYG) {
                     const int ki = yoff * ncols + xoff;
                     key = (ki == patched) ? 0u : (unsigned)__ldg(P.spiral_key + ki);    // patched = MV (0,0) pre-test
                 } else {
@@ -279,7 +293,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                 o[20] = o[1] + pl;                                                    // 8x16 left
                 o[21] = o[2] + pr8;                                                   // 8x16 right
                 o[19] = o[20] + o[21];                                                // 16x16
-                if constexpr (!PER_BLOCK) {
+                if constexpr (KRTAB) {
+                    const unsigned kr = s_kr[yoff * ncols + xoff];
+#pragma unroll
+                    for (int b = 0; b < NL; b++) pk[b] = (o[b] << JMME_KEY_BITS) + kr;
+                } else if constexpr (!PER_BLOCK) {
                     const unsigned kr = s_T[bx0 + s_by[yoff]] + key;
 #pragma unroll
                     for (int b = 0; b < NL; b++) pk[b] = (o[b] << JMME_KEY_BITS) + kr;
@@ -371,12 +389,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG>
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
-    TbLayout L(P.R, PER_BLOCK, !KEYG, K);
+    TbLayout L(P.R, PER_BLOCK, !KEYG, K, KRTAB);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG>;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB>;
     // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
     static thread_local int c_dev = -1, c_occ = 0;
     static thread_local size_t c_bytes = 0;
@@ -411,6 +429,7 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
 #define TB(KK, SH, NWW, MB, KG)                                                            \
     if (K == KK && shape == SH) {                                                          \
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
+        if (P.R == 32 && !P.pred && !KG) return launch_tb<KK, NWW, MB, false, 78, false, true>(P, num_sms, st); \
         if (P.R == 32) return launch_tb<KK, NWW, MB, false, 78, KG>(P, num_sms, st);       \
         if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142, KG>(P, num_sms, st);      \
         return launch_tb<KK, NWW, MB, false, 0, KG>(P, num_sms, st);                       \
