@@ -105,3 +105,25 @@ def random_pred(num_refs, n_mb, nb, seed, max_qpel):
     k = splitmix64(np.arange(num_refs * n_mb * nb * 2, dtype=np.uint64) + np.uint64(seed) * np.uint64(104729))
     return ((k % np.uint64(2 * max_qpel + 1)).astype(np.int64) - max_qpel).astype(np.int16).reshape(
         num_refs, n_mb, nb, 2)
+
+
+# ---- planar YUV 4:2:0 files (the container JM's lencod reads with InputFile / SourceWidth / SourceHeight) ----
+def yuv420_frame_bytes(w, h):
+    return w * h + 2 * (((w + 1) // 2) * ((h + 1) // 2))
+
+
+def read_yuv420_luma(path, w, h, frame=0):
+    """Luma plane of frame `frame` of a planar 8-bit YUV 4:2:0 file."""
+    with open(path, "rb") as f:
+        f.seek(frame * yuv420_frame_bytes(w, h))
+        buf = f.read(w * h)
+    if len(buf) != w * h:
+        raise ValueError(f"{path}: frame {frame} of {w}x{h} is not in the file")
+    return np.frombuffer(buf, np.uint8).reshape(h, w).copy()
+
+
+def write_yuv420(path, lumas):
+    """Write luma planes as a planar YUV 4:2:0 sequence with flat chroma."""
+    with open(path, "wb") as f:
+        for y in lumas:
+            f.write(yuv420_frame(np.ascontiguousarray(y, np.uint8)).tobytes())
