@@ -14,6 +14,8 @@
 //   banks        the window row stride is == 2 (mod 4) words, so the B lanes (8 rows further down)
 //                sit 16 banks away from the T lanes: 16 + 16 consecutive banks, conflict-free
 //   K            up to 8 candidates per run: 4*(7+K)/K row words per thread and candidate
+#include <cstdlib>
+
 #include "jmme_dev.cuh"
 
 namespace {
@@ -21,19 +23,20 @@ namespace {
 struct TbLayout {
     int RS, rows, RAWW;                 // window row stride (words, == 2 mod 4), rows, raw row words
     int off_win, off_raw, off_cur, off_T, off_best, off_task, off_key, off_bx, off_by, off_kr, total_words;
-    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem, int K, bool kr_table = false)
+    // nmb: the item is nmb horizontally adjacent MBs sharing one (16*(nmb-1) columns wider) window
+    __host__ __device__ TbLayout(int R, bool per_block, bool key_in_smem, int K, bool kr_table = false, int nmb = 1)
     {
         const int ncols = 2 * R + 1;
-        RS = 2 * R + 13;                // word positions 0 .. 2R+12
+        RS = 2 * R + 13 + 16 * (nmb - 1);           // word positions 0 .. 2R+12 (+16 per further MB)
         while ((RS & 3) != 2) RS++;
         rows = 2 * R + 16;
         RAWW = ((15 + RS + 12 + 15) & ~15) >> 2;
         off_win = 0;
         off_raw = (off_win + rows * RS + 3) & ~3;
         off_cur = off_raw + rows * RAWW;
-        off_T = off_cur + 2 * 64;
+        off_T = off_cur + 2 * 64 * nmb;
         off_best = off_T + JMME_NT;
-        off_task = off_best + 48;                       // u16 (ybase << 8 | xbase) per main task
+        off_task = off_best + 48 * nmb;                       // u16 (ybase << 8 | xbase) per main task
         off_key = off_task + ((((ncols + K - 1) / K) * (ncols >> 4) + 1) >> 1);
         off_bx = off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0);
         const int nb = per_block ? JMME_NBLK : 1;
@@ -58,7 +61,7 @@ __device__ constexpr int kGT[NL] = {1, 5, 6, 9, 10, 11, 12, 17, 18, 19, 20, 25, 
 __device__ constexpr int kDL[NL] = {1, 2, 2, 4, 4, 4, 4, 4, 4, 4, 4, 8, 8, 8, 8, 8, 8, 8, 8, 0, 0, 0};
 
 struct Item {
-    int ref, mbx, mby, mb, cx, cy;
+    int ref, mbx, mby, mb, cx, cy, nmb;
 };
 
 // RS_CT: compile-time window row stride (0 = from the layout at run time): row addresses become immediates
@@ -66,11 +69,15 @@ struct Item {
 // so that two CTAs fit on an SM
 // KRTAB: zero predictors (P.pred == nullptr): centre and rate are the same for every item, so rate + key of
 // all (2R+1)^2 candidates is tabulated once per CTA and a candidate costs one LDS instead of three
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB>
+// NMB > 1 (with KRTAB): an item is NMB horizontally adjacent MBs.  Their windows overlap in all but 16 columns
+// each, so one prefetch + expansion (1.6x the work of one for NMB = 4) and one set of barriers serves all of
+// them, and the NMB x 45 tasks split evenly over the warps.
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const TbLayout L(P.R, PER_BLOCK, !KEYG, K, KRTAB);
+    const TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
+    constexpr int NM = NMB, CURW = 64 * NM;     // MBs per item, words of one current-MB stage
     uint32_t *s_win = smem + L.off_win;
     uint32_t *s_raw = smem + L.off_raw;
     uint32_t *s_cur2 = smem + L.off_cur;
@@ -89,10 +96,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int rows = L.rows, RAWW = L.RAWW;
     const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
-    const int n_items = n_mb_stripe * P.num_refs;
+    const int ppr = (P.mb_w + NM - 1) / NM;              // items per MB row
+    const int n_it_stripe = (P.mb_row_end - P.mb_row_begin) * ppr;
+    const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
-    if (!KEYG)
+    if (!KEYG && !KRTAB)
         for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
     const int bonus_base = P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16);
     const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
@@ -119,7 +128,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         const bool pt = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
         for (int i = tid; i < ncand; i += NW * 32) {
             const int yo = i / ncols, xo = i - yo * ncols;
-            const unsigned key = (pt && xo == R && yo == R) ? 0u : (unsigned)s_key[i];    // MV (0,0) pre-test
+            const unsigned key = (pt && xo == R && yo == R) ? 0u : (unsigned)P.spiral_key[i];    // MV (0,0) pre-test
             s_kr[i] = s_T[d_se_bits(4 * (xo - R)) + d_se_bits(4 * (yo - R))] + key;
         }
     }
@@ -128,10 +137,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     if (res_g >= G) { res_g = 0; res_x = 16 * nseg; }    // idle lanes repeat lane 0 (idempotent)
 
     auto decode_item = [&](int item, Item &it) {
-        it.ref = item / n_mb_stripe;
-        const int mbi = item - it.ref * n_mb_stripe;
-        it.mby = P.mb_row_begin + mbi / P.mb_w;
-        it.mbx = mbi % P.mb_w;
+        it.ref = item / n_it_stripe;
+        const int idx = item - it.ref * n_it_stripe;
+        it.mby = P.mb_row_begin + idx / ppr;
+        it.mbx = (idx % ppr) * NM;
+        it.nmb = min(NM, P.mb_w - it.mbx);
         it.mb = it.mby * P.mb_w + it.mbx;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
@@ -154,8 +164,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                 for (int row = tid >> 4; row < rows; row += NW * 2)
                     cp_async16(s_raw + row * RAWW + 4 * c, g + (size_t)row * P.pstride + 16 * c);
         }
-        if (tid < 16)
-            cp_async16(s_cur2 + buf * 64 + 4 * tid, P.cur + (size_t)min(16 * it.mby + tid, P.cur_h - 1) * P.cur_stride + 16 * it.mbx);
+        if (tid < 16 * it.nmb) {                         // current MB(s): 16 rows of 16 bytes each
+            const int m = tid >> 4, row = tid & 15;
+            cp_async16(s_cur2 + buf * CURW + 64 * m + 4 * row,
+                       P.cur + (size_t)min(16 * it.mby + row, P.cur_h - 1) * P.cur_stride + 16 * (it.mbx + m));
+        }
         cp_async_commit();
     };
     auto expand = [&](const Item &it) {
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                 *(uint2 *)(s_win + row * RS + 2 * xp) = v;
             }
         }
-        if (tid < 48) s_best[tid] = 0xFFFFFFFFu;
+        for (int i = tid; i < 48 * NM; i += NW * 32) s_best[i] = 0xFFFFFFFFu;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         for (int i = tid; i < NPB * ncols; i += NW * 32) {
             const int b = i / ncols, o = i - b * ncols;
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + o - R) - py);
         }
         const int idx00 = (R - it.cy) * ncols + (R - it.cx);
-        if (!KEYG && pretest && tid == 0) {              // "(0,0) first": key 0 wins every tie
+        if (!KEYG && !KRTAB && pretest && tid == 0) {    // "(0,0) first": key 0 wins every tie
             if (patched >= 0 && patched != idx00) s_key[patched] = P.spiral_key[patched];
             s_key[idx00] = 0;
         }
@@ -212,7 +225,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         const int cx = cur_it.cx, cy = cur_it.cy;
         const int bonus = (cur_it.ref == 0) ? bonus_base : 0;
         const int x00 = R - cx, y00 = R - cy;
-        const uint32_t *s_cur = s_cur2 + buf * 64;
+      for (int m = 0; m < cur_it.nmb; m++) {               // the MB(s) of this item, one after the other
+        const uint32_t *s_cur = s_cur2 + buf * CURW + 64 * m;
+        const int wx = 16 * m;                           // window column of this MB's offset 0
+        uint32_t *s_bestm = s_best + 48 * m;
 
         // The current MB is the same for every lane; an opaque zero lane offset keeps ptxas from
         // parking it in uniform registers (it then pays a UR->R move per VABSDIFF4 operand).
@@ -230,14 +246,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int i = lane + 32 * h, row = i >> 2, j = i & 3;
-                s = sad4(s_cur[i], s_win[(y00 + row) * RS + x00 + 4 * j], s);
+                s = sad4(s_cur[i], s_win[(y00 + row) * RS + x00 + wx + 4 * j], s);
             }
             s = __reduce_add_sync(0xFFFFFFFFu, s);
             if (lane == 0) {
                 const unsigned k00 = pretest ? 0u : (unsigned)P.spiral_key[y00 * ncols + x00];
                 const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + k00 -
                                    ((unsigned)bonus << JMME_KEY_BITS);
-                atomicMin(&s_best[0], v);
+                atomicMin(&s_bestm[0], v);
             }
         }
 
@@ -245,8 +261,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
         for (int b = 0; b < NL; b++) best[b] = 0xFFFFFFFFu;
 
-        unsigned e_next = warp < n_main ? s_task[warp] : 0u;     // task descriptor, fetched one task ahead
-        for (int task = warp; task < n_tasks; task += NW) {
+        // second MB: the warp that starts at task 0 (one task more than the others) rotates
+        const int t0 = (warp + NM * NW - m) % NW;
+        unsigned e_next = t0 < n_main ? s_task[t0] : 0u;         // task descriptor, fetched one task ahead
+        for (int task = t0; task < n_tasks; task += NW) {
             int ybase, xoff;
             if (task < n_main) {
                 ybase = e_next >> 8;
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                 xoff = res_x;
             }
             if (task + NW < n_main) e_next = s_task[task + NW];
-            const uint32_t *base = s_win + (ybase + 8 * half) * RS + xoff;
+            const uint32_t *base = s_win + (ybase + 8 * half) * RS + xoff + wx;
 
             unsigned acc[K][8];
 #pragma unroll
@@ -361,13 +379,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                     keep(kGT[b] + kDL[b], __reduce_min_sync(0xFFFFFFFFu, half == 1 ? best[b] : 0xFFFFFFFFu));
                 }
             }
-            atomicMin(&s_best[lane], m0);
-            if (lane < JMME_NBLK - 32) atomicMin(&s_best[32 + lane], m1);
+            atomicMin(&s_bestm[lane], m0);
+            if (lane < JMME_NBLK - 32) atomicMin(&s_bestm[32 + lane], m1);
         }
+      }
         cp_async_wait_all();
         __syncthreads();
-        if (tid < JMME_NBLK) {
-            const unsigned v = s_best[tid];
+        for (int i = tid; i < JMME_NBLK * cur_it.nmb; i += NW * 32) {
+            const int m = i / JMME_NBLK, b = i - JMME_NBLK * m;
+            const unsigned v = s_best[48 * m + b];
             const unsigned key = v & JMME_KEY_MASK;
             int mvx = 0, mvy = 0;
             if (key) {
@@ -378,7 +398,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             r.mvx = (int16_t)(4 * mvx);
             r.mvy = (int16_t)(4 * mvy);
             r.cost = (int)(v >> JMME_KEY_BITS) - (int)bias;
-            P.res[((size_t)cur_it.ref * n_mb + cur_it.mb) * JMME_NBLK + tid] = r;
+            P.res[((size_t)cur_it.ref * n_mb + cur_it.mb + m) * JMME_NBLK + b] = r;
         }
         if (!has_next) break;
         __syncthreads();
@@ -389,12 +409,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false>
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
-    TbLayout L(P.R, PER_BLOCK, !KEYG, K, KRTAB);
+    TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB>;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB>;
     // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
     static thread_local int c_dev = -1, c_occ = 0;
     static thread_local size_t c_bytes = 0;
@@ -410,7 +430,7 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         c_dev = dev; c_bytes = bytes; c_occ = occ;
     }
-    int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
+    int n_items = (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB) * P.num_refs;
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
@@ -429,7 +449,13 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
 #define TB(KK, SH, NWW, MB, KG)                                                            \
     if (K == KK && shape == SH) {                                                          \
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
-        if (P.R == 32 && !P.pred && !KG) return launch_tb<KK, NWW, MB, false, 78, false, true>(P, num_sms, st); \
+        if (P.R == 32 && !P.pred && !KG) {                                                                     \
+            const char *g_ = getenv("JMME_GROUP");                  /* MBs per item: tuning knob, default 2 */ \
+            const int grp = g_ ? atoi(g_) : 2;                                                                  \
+            if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4>(P, num_sms, st);            \
+            if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2>(P, num_sms, st);             \
+            return launch_tb<KK, NWW, MB, false, 78, false, true, 1>(P, num_sms, st);                           \
+        }                                                                                                       \
         if (P.R == 32) return launch_tb<KK, NWW, MB, false, 78, KG>(P, num_sms, st);       \
         if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142, KG>(P, num_sms, st);      \
         return launch_tb<KK, NWW, MB, false, 0, KG>(P, num_sms, st);                       \

@@ -126,6 +126,8 @@ CASES = [
     (80, 64, 9, dict(qp=20)),
     (96, 64, 16, dict(rdopt=1, qp=40)),
     (64, 64, 32, dict(qp=28)),
+    (80, 48, 32, dict(qp=30)),                                 # 5 MBs per row: item groups of 4 + 1
+    (112, 32, 32, dict(rdopt=1, qp=26, subpel=1)),            # 7 MBs per row
     (48, 48, 5, dict(subpel=1)),
     (64, 48, 8, dict(subpel=1, rdopt=1, qp=24, satd_round=1)),
     (64, 48, 6, dict(subpel=1, use_hadamard=0)),
