@@ -343,3 +343,26 @@ def test_predictor_commit_and_closed_loop(cuda, oracle):
         assert_same(run(cuda, cur, refs, po, **{k: v for k, v in kw.items() if k not in ("width", "height", "num_refs")}),
                     run(oracle, cur, refs, po, **{k: v for k, v in kw.items() if k not in ("width", "height", "num_refs")}),
                     "pass 2")
+
+
+def test_randomised_configurations(cuda, oracle):
+    """Seeded random sweep over sizes, search ranges, lambda, masks, policies, references and sub-pel options."""
+    rng = np.random.default_rng(2026)
+    for case in range(24):
+        w, h = int(rng.integers(17, 130)), int(rng.integers(17, 100))
+        R = int(rng.choice([1, 2, 3, 5, 8, 13, 16, 21, 32, 40]))
+        refs_n = int(rng.integers(1, 4))
+        mask = int(rng.choice([0xFE, 0x02, 0x92, 0x0E, 0xF0, 0x80, 0xFE]))
+        policy = int(rng.integers(0, 3))
+        mode = int(rng.integers(0, 2))
+        kw = dict(search_range=R, qp=int(rng.integers(0, 52)), rdopt=int(rng.integers(0, 2)), subpel=int(rng.integers(0, 2)),
+                  use_hadamard=int(rng.integers(0, 2)), satd_round=int(rng.integers(0, 2)), blocktype_mask=mask,
+                  pred_policy=policy, search_mode=mode)
+        kind = str(rng.choice(["texture", "noise", "gradient"]))
+        cur, refs = synth.frame_pair(w, h, seed=case + 1, search_range=R, kind=kind, num_refs=refs_n)
+        n_mb = ((w + 15) // 16) * ((h + 15) // 16)
+        pred = None if policy == 0 else synth.random_pred(refs_n, n_mb, 1 if policy == 1 else 41, case, 4 * R + 40)
+        g, gp = run(cuda, cur, refs, pred, True, **kw)
+        o, op = run(oracle, cur, refs, pred, True, **kw)
+        assert_same(gp, op, f"case {case} per-ref {w}x{h} {kw}")
+        assert_same(g, o, f"case {case} best {w}x{h} {kw}")
