@@ -38,6 +38,9 @@ struct jmme_ctx {
     cudaStream_t stream;
     cudaStream_t copy_stream;             // host->device copy of the current picture, overlaps the plane kernel
     cudaEvent_t ev_copy;
+    cudaStream_t part_stream[4];          // the pipelined host path searches the stripe in up to 4 parts
+    cudaEvent_t ev_ref;
+    int pipe_parts;
     uint8_t *d_raw;                       // staging for the raw current picture (width x height)
     uint8_t *d_raw_ref[JMME_MAX_REFS];    // staging for the raw reference pictures
     uint8_t *d_planes[JMME_MAX_REFS];
@@ -110,6 +113,9 @@ void free_device(jmme_ctx *c)
         for (int j = 0; j < 2; j++)
             if (c->ev_prof[i][j]) cudaEventDestroy(c->ev_prof[i][j]);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_ref) cudaEventDestroy(c->ev_ref);
+    for (int i = 0; i < 4; i++)
+        if (c->part_stream[i]) cudaStreamDestroy(c->part_stream[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
@@ -168,6 +174,12 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+        for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&c->part_stream[i], cudaStreamNonBlocking));
+        CUC(cudaEventCreateWithFlags(&c->ev_ref, cudaEventDisableTiming));
+        {
+            const char *ep = getenv("JMME_PIPE_PARTS");   // tuning knob: 1 = no pipelining
+            c->pipe_parts = ep ? std::min(std::max(atoi(ep), 1), 4) : 3;
+        }
         CUC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         CUC(cudaMalloc(&c->d_raw, (size_t)p->width * p->height));
         for (int r = 0; r < p->num_refs; r++) {
@@ -219,8 +231,9 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
 }
 
 // enqueue the whole search on `st`; nothing is synchronised here
+// rb/re: MB-row range to search (a sub-range of the context's stripe; -1 = the whole stripe)
 int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t *d_pred, jmme_mbresult *d_out,
-                   jmme_mbresult *d_out_per_ref, cudaStream_t st)
+                   jmme_mbresult *d_out_per_ref, cudaStream_t st, int rb = -1, int re = -1)
 {
     for (int r = 0; r < c->p.num_refs; r++)
         if (!c->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
@@ -239,6 +252,7 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
     P.cur_h = cur_h;
     P.fused_select = c->p.num_refs == 1 && c->p.subpel;
+    if (rb >= 0) { P.mb_row_begin = rb; P.mb_row_end = re; }
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
     if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[1][0], st));
     if (c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK)
@@ -551,6 +565,38 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
     for (size_t i = 0; i < pred_elems; i++)
         if (pred[i] > JMME_MAX_PRED_QPEL || pred[i] < -JMME_MAX_PRED_QPEL)
             return fail(c, JMME_ERR_PARAM, "pred out of range");
+
+    // Single device, host buffers: the stripe is searched in parts on separate streams, so that the upload of
+    // the later parts of the current picture and the download of the earlier parts of the MV field overlap
+    // the kernels of the other parts (the reference planes are shared).
+    if (ns == 1 && !c->profiling && c->pipe_parts > 1 && c->w16 == c->p.width && !(stride & 15) && !((uintptr_t)cur & 15) &&
+        c->p.mb_row_end - c->p.mb_row_begin >= 4 * c->pipe_parts) {
+        jmme_ctx *s = c;
+        CU(c, cudaSetDevice(s->device));
+        if (pred_elems)
+            CU(c, cudaMemcpyAsync(s->d_pred, pred, pred_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, cudaEventRecord(s->ev_ref, s->stream));          // planes (and predictors) are ready after this
+        const int np = s->pipe_parts, rows = s->p.mb_row_end - s->p.mb_row_begin;
+        for (int pt = 0; pt < np; pt++) {
+            const int rb = s->p.mb_row_begin + rows * pt / np, re = s->p.mb_row_begin + rows * (pt + 1) / np;
+            cudaStream_t st = s->part_stream[pt];
+            const int y0 = std::min(16 * rb, s->p.height - 1), y1 = std::min(16 * re, s->p.height);
+            CU(c, upload_rows(s->d_raw + (size_t)y0 * s->p.width, cur + (size_t)y0 * stride, stride, s->p.width,
+                              std::max(y1 - y0, 1), st));
+            CU(c, cudaStreamWaitEvent(st, s->ev_ref, 0));
+            int rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,
+                                    st, rb, re);
+            if (rc != JMME_OK) return rc;
+            const size_t off = (size_t)rb * s->mb_w, cnt = (size_t)(re - rb) * s->mb_w;
+            CU(c, cudaMemcpyAsync(out + off, s->d_out + off, cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, st));
+            if (out_per_ref)
+                for (int r = 0; r < c->p.num_refs; r++)
+                    CU(c, cudaMemcpyAsync(out_per_ref + r * n_mb + off, s->d_out_per_ref + r * n_mb + off,
+                                          cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, st));
+        }
+        for (int pt = 0; pt < np; pt++) CU(c, cudaStreamSynchronize(s->part_stream[pt]));
+        return JMME_OK;
+    }
 
     // enqueue on every device, then gather
     for (int g = 0; g < ns; g++) {
