@@ -38,10 +38,12 @@ struct TbLayout {
         off_best = off_T + JMME_NT;
         off_task = off_best + 48 * nmb;                       // u16 (ybase << 8 | xbase) per main task
         off_key = off_task + ((((ncols + K - 1) / K) * (ncols >> 4) + 1) >> 1);
-        off_bx = off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0);
-        const int nb = per_block ? JMME_NBLK : 1;
-        off_by = off_bx + (nb * ncols + 3) / 4;
-        off_kr = off_by + (nb * ncols + 3) / 4;         // rate+key of every candidate (zero predictors only)
+        off_bx = (off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0) + 1) & ~1;      // 8-byte aligned (LDS.64)
+        // one predictor: bits per column / row (bytes).  41 predictors: per (half, column|row) the 22 local
+        // blocks' bits * 4, padded to 24 bytes, so that a thread fetches all of them as six words
+        const int tw = per_block ? (2 * ncols * 24) / 4 : (ncols + 3) / 4;
+        off_by = (off_bx + tw + 1) & ~1;
+        off_kr = off_by + tw;         // rate+key of every candidate (zero predictors only)
         total_words = off_kr + (kr_table ? ncols * ncols : 0);
     }
 };
@@ -191,11 +193,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         }
         for (int i = tid; i < 48 * NM; i += NW * 32) s_best[i] = 0xFFFFFFFFu;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
-        for (int i = tid; i < NPB * ncols; i += NW * 32) {
-            const int b = i / ncols, o = i - b * ncols;
-            const int px = pr ? pr[2 * b] : 0, py = pr ? pr[2 * b + 1] : 0;
-            s_bx[i] = (uint8_t)d_se_bits(4 * (it.cx + o - R) - px);
-            s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + o - R) - py);
+        if constexpr (!PER_BLOCK) {
+            for (int i = tid; i < ncols; i += NW * 32) {
+                const int px = pr ? pr[0] : 0, py = pr ? pr[1] : 0;
+                s_bx[i] = (uint8_t)d_se_bits(4 * (it.cx + i - R) - px);
+                s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + i - R) - py);
+            }
+        } else {
+            for (int i = tid; i < 2 * ncols * 24; i += NW * 32) {      // [half][offset][local block], bits * 4
+                const int b = i % 24, o = (i / 24) % ncols, hf = i / (24 * ncols);
+                const int gb = b < NL ? kGT[b] + hf * kDL[b] : 0;
+                const int px = pr[2 * gb], py = pr[2 * gb + 1];
+                s_bx[i] = (uint8_t)(4 * d_se_bits(4 * (it.cx + o - R) - px));
+                s_by[i] = (uint8_t)(4 * d_se_bits(4 * (it.cy + o - R) - py));
+            }
         }
         const int idx00 = (R - it.cy) * ncols + (R - it.cx);
         if (!KEYG && !KRTAB && pretest && tid == 0) {    // "(0,0) first": key 0 wins every tie
@@ -251,7 +262,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             s = __reduce_add_sync(0xFFFFFFFFu, s);
             if (lane == 0) {
                 const unsigned k00 = pretest ? 0u : (unsigned)P.spiral_key[y00 * ncols + x00];
-                const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + k00 -
+                const unsigned bits00 = PER_BLOCK ? (s_bx[x00 * 24 + 19] + s_by[y00 * 24 + 19]) >> 2    // local 19 = 16x16
+                                                  : s_bx[x00] + s_by[y00];
+                const unsigned v = (s << JMME_KEY_BITS) + s_T[bits00] + k00 -
                                    ((unsigned)bonus << JMME_KEY_BITS);
                 atomicMin(&s_bestm[0], v);
             }
@@ -282,7 +295,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
                 for (int i = 0; i < 8; i++) acc[k][i] = 0;
 
-            const unsigned bx0 = KRTAB ? 0u : (unsigned)s_bx[xoff];
+            unsigned bx0 = 0;
+            uint32_t bxw[6];                             // PER_BLOCK: bits*4 of this column for the 22 local blocks
+            if constexpr (PER_BLOCK) {
+                const uint2 *q = (const uint2 *)(s_bx + (half * ncols + xoff) * 24);
+#pragma unroll
+                for (int i = 0; i < 3; i++) { const uint2 v = q[i]; bxw[2 * i] = v.x; bxw[2 * i + 1] = v.y; }
+            } else if constexpr (!KRTAB) {
+                bx0 = s_bx[xoff];
+            }
             auto pack = [&](int k, unsigned (&pk)[NL]) {
                 const int yoff = ybase + k;
                 unsigned key = 0;
@@ -320,10 +341,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
                     for (int b = 0; b < NL; b++) pk[b] = (o[b] << JMME_KEY_BITS) + kr;
                 } else {
+                    // byte-wise bits*4 sums of four blocks per add; each byte is the offset of its rate in s_T
+                    const uint2 *q = (const uint2 *)(s_by + (half * ncols + yoff) * 24);
+                    uint32_t sw[6];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { const uint2 v = q[i]; sw[2 * i] = v.x + bxw[2 * i]; sw[2 * i + 1] = v.y + bxw[2 * i + 1]; }
 #pragma unroll
                     for (int b = 0; b < NL; b++) {
-                        const int gb = kGT[b] + half * kDL[b];
-                        pk[b] = (o[b] << JMME_KEY_BITS) + s_T[s_bx[gb * ncols + xoff] + s_by[gb * ncols + yoff]] + key;
+                        const unsigned off = __byte_perm(sw[b >> 2], 0, 0x4440 | (b & 3));
+                        pk[b] = (o[b] << JMME_KEY_BITS) + *(const uint32_t *)((const char *)s_T + off) + key;
                     }
                 }
             };
