@@ -29,6 +29,9 @@ cudaError_t jmme_launch_predict(const int16_t *mv4, const int8_t *ref4, int mb_w
                                 cudaStream_t st);
 cudaError_t jmme_launch_commit(const jmme_mbresult *res, int mb_w, int mb_h, int mask, int16_t *mv4, int8_t *ref4,
                                uint8_t *mode, cudaStream_t st);
+cudaError_t jmme_launch_wave_step(const jmme_mbresult *res, const int *prev, int n_prev, const int *cur, int n_cur, int mb_w,
+                                  int mb_h, int num_refs, int mask, int slice_rows, int16_t *mv4, int8_t *ref4,
+                                  int16_t *pred, cudaStream_t st);
 cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st);
 
 struct jmme_ctx {
@@ -59,6 +62,13 @@ struct jmme_ctx {
     int profiling;                        // bracket kernels with events
     cudaEvent_t ev_prof[4][2];            // [interp, me_int, me_subpel, select][begin, end]
     bool prof_valid[4];
+    // JMME_PRED_MEDIAN: the field committed so far, and the MBs of every wavefront step of the stripe
+    int16_t *d_fmv;
+    int8_t *d_fref;
+    int *d_wave;                          // MB indices, step after step
+    int *wave_off;                        // [n_steps + 1] offsets into d_wave (host)
+    int n_steps;
+    bool searched;                        // d_pred holds the predictors of a finished median search
 };
 
 namespace {
@@ -108,6 +118,8 @@ void free_device(jmme_ctx *c)
     for (int r = 0; r < JMME_MAX_REFS; r++) { cudaFree(c->d_planes[r]); cudaFree(c->d_raw_ref[r]); }
     cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
+    cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave);
+    free(c->wave_off);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 2; j++)
@@ -125,8 +137,8 @@ int validate(const jmme_params *p)
     if (p->width <= 0 || p->height <= 0 || p->search_range < 1 || p->search_range > JMME_MAX_SEARCH_RANGE ||
         p->num_refs < 1 || p->num_refs > JMME_MAX_REFS || (p->blocktype_mask & ~JMME_MASK_ALL) ||
         !(p->blocktype_mask & JMME_MASK_ALL) || p->qp < 0 || p->qp > 51 || p->lambda_factor < 0 ||
-        p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 2 || p->satd_round < 0 ||
-        p->satd_round > 1 || p->n_gpus < 0 || p->n_gpus > JMME_MAX_GPUS)
+        p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 3 || p->satd_round < 0 ||
+        p->satd_round > 1 || p->n_gpus < 0 || p->n_gpus > JMME_MAX_GPUS || p->slice_rows < 0)
         return JMME_ERR_PARAM;
     if (p->cost_domain != 0) return JMME_ERR_UNSUPPORTED;
     return JMME_OK;
@@ -144,6 +156,10 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
     if (c->p.mb_row_end == 0) c->p.mb_row_end = c->mb_h;
     if (c->p.mb_row_begin < 0 || c->p.mb_row_end > c->mb_h || c->p.mb_row_begin >= c->p.mb_row_end) {
         delete c; return JMME_ERR_PARAM;
+    }
+    if (p->pred_policy == JMME_PRED_MEDIAN) {     // stripes start and end on slice boundaries
+        const int k = p->slice_rows ? p->slice_rows : c->mb_h;
+        if (c->p.mb_row_begin % k || (c->p.mb_row_end % k && c->p.mb_row_end != c->mb_h)) { delete c; return JMME_ERR_PARAM; }
     }
     c->pad = pad_for(p->search_range);
     c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
@@ -203,6 +219,30 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
             }
         CUC(cudaMemcpy(c->d_spiral_key, key.data(), sizeof(uint16_t) * c->ncand, cudaMemcpyHostToDevice));
         CUC(cudaMemcpy(c->d_spiral_xy, xy.data(), sizeof(int16_t) * 2 * c->ncand, cudaMemcpyHostToDevice));
+        if (p->pred_policy == JMME_PRED_MEDIAN) {
+            // 2:1 wavefront inside every slice: MB (x, y) of a slice that starts at row y0 is decided in step
+            // x + 2 (y - y0), after its left, upper-left, upper and upper-right neighbours
+            const int rb = c->p.mb_row_begin, re = c->p.mb_row_end;
+            const int k = p->slice_rows ? p->slice_rows : c->mb_h;
+            std::vector<int> list;
+            c->n_steps = c->mb_w + 2 * (std::min(k, re - rb) - 1);
+            c->wave_off = (int *)malloc(sizeof(int) * (c->n_steps + 1));
+            if (!c->wave_off) { rc = JMME_ERR_NOMEM; goto bad; }
+            for (int t = 0; t < c->n_steps; t++) {
+                c->wave_off[t] = (int)list.size();
+                for (int y = rb; y < re; y++) {
+                    const int x = t - 2 * ((y - rb) % k);
+                    if (x >= 0 && x < c->mb_w) list.push_back(y * c->mb_w + x);
+                }
+            }
+            c->wave_off[c->n_steps] = (int)list.size();
+            CUC(cudaMalloc(&c->d_wave, sizeof(int) * list.size()));
+            CUC(cudaMemcpy(c->d_wave, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice));
+            CUC(cudaMalloc(&c->d_fmv, sizeof(int16_t) * 2 * 16 * n_mb));
+            CUC(cudaMalloc(&c->d_fref, 16 * n_mb));
+            CUC(cudaMemset(c->d_fmv, 0, sizeof(int16_t) * 2 * 16 * n_mb));
+            CUC(cudaMemset(c->d_fref, 0xFF, 16 * n_mb));
+        }
     }
 #undef CUC
     *out = c;
@@ -254,6 +294,25 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     P.fused_select = c->p.num_refs == 1 && c->p.subpel;
     if (rb >= 0) { P.mb_row_begin = rb; P.mb_row_end = re; }
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
+    if (c->p.pred_policy == JMME_PRED_MEDIAN) {
+        // predict -> search -> commit, one wavefront step after the other; the kernels of a step work on
+        // that step's list of MBs with the per-block predictors wave_step_kernel has just written
+        P.pred = c->d_pred; P.pred_policy = JMME_PRED_PER_BLOCK;
+        for (int t = 0; t < c->n_steps; t++) {
+            const int *prev = t ? c->d_wave + c->wave_off[t - 1] : nullptr;
+            const int n_prev = t ? c->wave_off[t] - c->wave_off[t - 1] : 0;
+            P.mb_list = c->d_wave + c->wave_off[t]; P.n_list = c->wave_off[t + 1] - c->wave_off[t];
+            CU(c, jmme_launch_wave_step(d_out, prev, n_prev, P.mb_list, P.n_list, c->mb_w, c->mb_h, c->p.num_refs,
+                                        c->p.blocktype_mask, c->p.slice_rows, c->d_fmv, c->d_fref, c->d_pred, st));
+            if (c->p.search_mode == JMME_SEARCH_FULL) CU(c, jmme_launch_me_full(P, st));
+            else CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
+            c->launches += 2;
+            if (c->p.subpel) { CU(c, jmme_launch_subpel(P, st)); c->launches++; }
+            if (!P.fused_select) { CU(c, jmme_launch_select(P, st)); c->launches++; }
+        }
+        c->searched = true;
+        return JMME_OK;
+    }
     if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[1][0], st));
     if (c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK)
         CU(c, jmme_launch_me_full(P, st));           // a window per block: nothing to share (me_full.cu)
@@ -311,12 +370,15 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
     if (!c) return JMME_ERR_NOMEM;
     memset(c, 0, sizeof *c);
     c->p = *p; c->device = -1;
-    const int rows = re - rb, n = std::min(p->n_gpus, rows);
+    // (in-frame median: whole slices per device, so the result does not depend on the device count)
+    const int unit = p->pred_policy == JMME_PRED_MEDIAN ? (p->slice_rows ? p->slice_rows : mb_h) : 1;
+    if (unit > 1 && (rb % unit || (re % unit && re != mb_h))) { delete c; return JMME_ERR_PARAM; }
+    const int rows = (re - rb + unit - 1) / unit, n = std::min(p->n_gpus, rows);
     int r0 = rb;
     for (int g = 0; g < n; g++) {
         jmme_params q = *p;
         q.n_gpus = 1;
-        q.mb_row_begin = r0; q.mb_row_end = r0 + rows / n + (g < rows % n ? 1 : 0);
+        q.mb_row_begin = r0; q.mb_row_end = std::min(re, r0 + unit * (rows / n + (g < rows % n ? 1 : 0)));
         r0 = q.mb_row_end;
         rc = create_single(&c->sub[g], &q, p->device_ids[g]);
         if (rc != JMME_OK) { jmme_destroy(c); return rc; }
@@ -452,6 +514,26 @@ int jmme_get_kernel_times(jmme_ctx *c, float ms[4])
     return JMME_OK;
 }
 
+int jmme_get_predictors(jmme_ctx *c, int16_t *pred)
+{
+    if (!c || !pred) return JMME_ERR_PARAM;
+    if (c->p.pred_policy != JMME_PRED_MEDIAN) return fail(c, JMME_ERR_STATE, "no median search yet");
+    jmme_ctx *subs1[1] = {c};
+    jmme_ctx **subs = c->n_sub ? c->sub : subs1;
+    const size_t n_mb = (size_t)c->mb_w * c->mb_h, per_mb = 2 * JMME_NBLK;
+    for (int g = 0; g < (c->n_sub ? c->n_sub : 1); g++) {         // every device holds its own stripe's predictors
+        jmme_ctx *s = subs[g];
+        if (!s->searched) return fail(c, JMME_ERR_STATE, "no median search yet");
+        CU(c, cudaSetDevice(s->device));
+        const size_t off = (size_t)s->p.mb_row_begin * s->mb_w, cnt = (size_t)(s->p.mb_row_end - s->p.mb_row_begin) * s->mb_w;
+        for (int r = 0; r < c->p.num_refs; r++)
+            CU(c, cudaMemcpyAsync(pred + (r * n_mb + off) * per_mb, s->d_pred + (r * n_mb + off) * per_mb,
+                                  cnt * per_mb * sizeof(int16_t), cudaMemcpyDeviceToHost, s->stream));
+        CU(c, cudaStreamSynchronize(s->stream));
+    }
+    return JMME_OK;
+}
+
 int jmme_get_subimage(jmme_ctx *c, int r, int xf, int yf, uint8_t *dst, int dst_stride)
 {
     if (!c || !dst || r < 0 || r >= c->p.num_refs || xf < 0 || xf > 3 || yf < 0 || yf > 3 || dst_stride < c->pstride)
@@ -472,7 +554,8 @@ int jmme_search_frame_dev(jmme_ctx *c, const void *d_cur, int stride, const void
 {
     if (!c || !d_cur || !d_out || stride < c->p.width) return JMME_ERR_PARAM;
     if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
-    if (c->p.pred_policy != JMME_PRED_ZERO && !d_pred) return fail(c, JMME_ERR_PARAM, "pred required");
+    if (c->p.pred_policy != JMME_PRED_ZERO && c->p.pred_policy != JMME_PRED_MEDIAN && !d_pred)
+        return fail(c, JMME_ERR_PARAM, "pred required");
     CU(c, cudaSetDevice(c->device));
     return enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
                           (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
@@ -553,13 +636,14 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
                       jmme_mbresult *out_per_ref)
 {
     if (!c || !cur || !out || stride < c->p.width) return JMME_ERR_PARAM;
-    if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return fail(c, JMME_ERR_PARAM, "pred required");
+    if (c->p.pred_policy == JMME_PRED_MEDIAN) pred = nullptr;
+    else if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return fail(c, JMME_ERR_PARAM, "pred required");
     jmme_ctx *subs1[1] = {c};
     jmme_ctx **subs = c->n_sub ? c->sub : subs1;
     const int ns = c->n_sub ? c->n_sub : 1;
     const size_t n_mb = (size_t)c->mb_w * c->mb_h;
     const int npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
-    const size_t pred_elems = c->p.pred_policy == JMME_PRED_ZERO ? 0 : (size_t)c->p.num_refs * n_mb * npb * 2;
+    const size_t pred_elems = !pred ? 0 : (size_t)c->p.num_refs * n_mb * npb * 2;
     for (int r = 0; r < c->p.num_refs; r++)
         if (!subs[0]->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
     for (size_t i = 0; i < pred_elems; i++)
@@ -569,7 +653,7 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
     // Single device, host buffers: the stripe is searched in parts on separate streams, so that the upload of
     // the later parts of the current picture and the download of the earlier parts of the MV field overlap
     // the kernels of the other parts (the reference planes are shared).
-    if (ns == 1 && !c->profiling && c->pipe_parts > 1 && c->w16 == c->p.width && !(stride & 15) && !((uintptr_t)cur & 15) &&
+    if (ns == 1 && !c->profiling && c->pipe_parts > 1 && c->p.pred_policy != JMME_PRED_MEDIAN && c->w16 == c->p.width && !(stride & 15) && !((uintptr_t)cur & 15) &&
         c->p.mb_row_end - c->p.mb_row_begin >= 4 * c->pipe_parts) {
         jmme_ctx *s = c;
         CU(c, cudaSetDevice(s->device));

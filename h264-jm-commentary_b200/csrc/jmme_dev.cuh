@@ -42,7 +42,19 @@ struct SearchParams {
     jmme_mbresult *out;                  // [mb]
     jmme_mbresult *out_per_ref;          // [ref][mb] or null
     int fused_select;                    // 1: the sub-pel kernel writes `out` itself (one reference)
+    const int *mb_list;                  // non-null: search these n_list MBs (frame MB indices) instead of the
+    int n_list;                          //           stripe's rows: one step of the in-frame median wavefront
 };
+
+// the MBs one launch works on: a stripe of MB rows, or an explicit list
+__host__ __device__ inline int d_n_units(const SearchParams &P)
+{
+    return P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * P.mb_w;
+}
+__device__ __forceinline__ int d_unit_mb(const SearchParams &P, int i)
+{
+    return P.mb_list ? P.mb_list[i] : P.mb_row_begin * P.mb_w + i;
+}
 
 __device__ __forceinline__ int d_se_bits(int v)
 {

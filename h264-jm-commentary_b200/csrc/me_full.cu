@@ -18,13 +18,12 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int R = P.R, ncols = P.ncols, ncand = ncols * ncols;
-    const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
+    const int n_mb_stripe = d_n_units(P);
     const int n_mb = P.mb_w * P.mb_h;
     const int item = blockIdx.x;
     const int ref = item / n_mb_stripe;
-    const int mbi = item - ref * n_mb_stripe;
-    const int mby = P.mb_row_begin + mbi / P.mb_w, mbx = mbi % P.mb_w;
-    const int mb = mby * P.mb_w + mbx;
+    const int mb = d_unit_mb(P, item - ref * n_mb_stripe);
+    const int mby = mb / P.mb_w, mbx = mb - mby * P.mb_w;
     const int npb = P.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
     const int16_t *pr = P.pred ? P.pred + ((size_t)ref * n_mb + mb) * npb * 2 : nullptr;
     const int bonus16 = (!P.rdopt && ref == 0) ? d_weighted_cost(P.lambda_factor, 16) : 0;
@@ -88,7 +87,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
 
 cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st)
 {
-    const int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
+    const int n_items = d_n_units(P) * P.num_refs;
     me_full_kernel<<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
 }

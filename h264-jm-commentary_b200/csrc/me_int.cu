@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
     const int R = P.R, ncols = P.ncols, ncand = ncols * ncols;
     const int RS = RS_CT ? RS_CT : L.RS;
     const int rows = L.rows, RAWW = L.RAWW;
-    const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
+    const int n_mb_stripe = d_n_units(P);
     const int n_mb = P.mb_w * P.mb_h;
     const int n_items = n_mb_stripe * P.num_refs;
     constexpr int NB = ONLY16 ? 1 : JMME_NBLK;
@@ -134,10 +134,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
 
     auto decode_item = [&](int item, Item &it) {
         it.ref = item / n_mb_stripe;
-        const int mbi = item - it.ref * n_mb_stripe;
-        it.mby = P.mb_row_begin + mbi / P.mb_w;
-        it.mbx = mbi % P.mb_w;
-        it.mb = it.mby * P.mb_w + it.mbx;
+        it.mb = d_unit_mb(P, item - it.ref * n_mb_stripe);
+        it.mby = it.mb / P.mb_w;
+        it.mbx = it.mb - it.mby * P.mb_w;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
         it.cx = d_clamp(p16x / 4, -R, R);
@@ -379,7 +378,7 @@ cudaError_t launch_one(const SearchParams &P, int num_sms, cudaStream_t st)
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         c_dev = dev; c_bytes = bytes; c_occ = occ;
     }
-    int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
+    int n_items = d_n_units(P) * P.num_refs;
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
@@ -406,7 +405,9 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st)
 {
-    if (variant <= 0) variant = P.R <= 32 ? 68 : 51;   // default: measured best per search range
+    // default: measured best per search range; a wavefront step has fewer MBs than SMs, so
+    // it takes the widest CTA (12 warps per MB)
+    if (variant <= 0) variant = P.R <= 32 ? (P.mb_list ? 64 : 68) : 51;
     int K = variant / 10, c = variant % 10;
     if (c >= 4) {                                   // two-threads-per-candidate kernel (me_int_tb.cu)
         if (P.blocktype_mask != JMME_MASK_16x16 && K <= P.ncols) return jmme_launch_me_int_tb(P, num_sms, K, c, st);

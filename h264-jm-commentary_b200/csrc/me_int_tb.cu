@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
     const int ppr = (P.mb_w + NM - 1) / NM;              // items per MB row
-    const int n_it_stripe = (P.mb_row_end - P.mb_row_begin) * ppr;
+    const int n_it_stripe = P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ppr;   // a list: one MB per item
     const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
@@ -141,10 +141,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     auto decode_item = [&](int item, Item &it) {
         it.ref = item / n_it_stripe;
         const int idx = item - it.ref * n_it_stripe;
-        it.mby = P.mb_row_begin + idx / ppr;
-        it.mbx = (idx % ppr) * NM;
-        it.nmb = min(NM, P.mb_w - it.mbx);
-        it.mb = it.mby * P.mb_w + it.mbx;
+        if (P.mb_list) {
+            it.mb = P.mb_list[idx];
+            it.mby = it.mb / P.mb_w;
+            it.mbx = it.mb - it.mby * P.mb_w;
+            it.nmb = 1;
+        } else {
+            it.mby = P.mb_row_begin + idx / ppr;
+            it.mbx = (idx % ppr) * NM;
+            it.nmb = min(NM, P.mb_w - it.mbx);
+            it.mb = it.mby * P.mb_w + it.mbx;
+        }
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
         it.cx = d_clamp(p16x / 4, -R, R);
@@ -456,7 +463,7 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         c_dev = dev; c_bytes = bytes; c_occ = occ;
     }
-    int n_items = (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB) * P.num_refs;
+    int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();

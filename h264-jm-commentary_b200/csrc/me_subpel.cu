@@ -61,13 +61,12 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = 2 * warp + (lane >> 4) + 1;            // blocktype 1..7 (8 = idle)
     const int cell = lane & 15, cx4 = cell & 3, cy4 = cell >> 2;
-    const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
+    const int n_mb_stripe = d_n_units(P);
     const int n_mb = P.mb_w * P.mb_h;
     const int item = blockIdx.x;
     const int ref = item / n_mb_stripe;
-    const int mbi = item - ref * n_mb_stripe;
-    const int mby = P.mb_row_begin + mbi / P.mb_w, mbx = mbi % P.mb_w;
-    const int mb = mby * P.mb_w + mbx;
+    const int mb = d_unit_mb(P, item - ref * n_mb_stripe);
+    const int mby = mb / P.mb_w, mbx = mb - mby * P.mb_w;
     const bool active = t <= 7 && ((P.blocktype_mask >> t) & 1);
     const int b = t <= 7 ? block_of_cell(t, cx4, cy4) : 0;
     const int need = t <= 7 ? need_of_type(t) : 0;
@@ -204,12 +203,12 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
 // per (MB, block): add the reference rate and keep the cheapest reference (lowest index on ties)
 __global__ void select_ref_kernel(const SearchParams P)
 {
-    const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
+    const int n_mb_stripe = d_n_units(P);
     const int n_mb = P.mb_w * P.mb_h;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_mb_stripe * 48) return;
     const int mbi = i / 48, b = i - mbi * 48;
-    const int mb = P.mb_row_begin * P.mb_w + mbi;
+    const int mb = d_unit_mb(P, mbi);
     jmme_mbresult *o = P.out + mb;
     if (b >= JMME_NBLK) {                                  // 3 spare lanes clear the reserved bytes
         if (b < JMME_NBLK + 3) {
@@ -260,14 +259,14 @@ cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_ds
 
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
 {
-    int n_items = (P.mb_row_end - P.mb_row_begin) * P.mb_w * P.num_refs;
+    int n_items = d_n_units(P) * P.num_refs;
     me_subpel_kernel<<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
 }
 
 cudaError_t jmme_launch_select(const SearchParams &P, cudaStream_t st)
 {
-    int n = (P.mb_row_end - P.mb_row_begin) * P.mb_w * 48;
+    int n = d_n_units(P) * 48;
     select_ref_kernel<<<(n + 255) / 256, 256, 0, st>>>(P);
     return cudaGetLastError();
 }

@@ -18,7 +18,7 @@ INT32_MAX = 2**31 - 1
 
 OK, ERR_PARAM, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE, ERR_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 SEARCH_FASTFULL, SEARCH_FULL = 0, 1
-PRED_ZERO, PRED_PER_MB, PRED_PER_BLOCK = 0, 1, 2
+PRED_ZERO, PRED_PER_MB, PRED_PER_BLOCK, PRED_MEDIAN = 0, 1, 2, 3
 MASK_16x16, MASK_ALL = 0x02, 0xFE
 
 # block geometry (JM blc_size): blocktype -> (w, h); result index bases
@@ -42,7 +42,7 @@ class Params(C.Structure):
         "width", "height", "search_range", "num_refs", "blocktype_mask", "lambda_factor", "qp", "rdopt",
         "use_hadamard", "subpel", "search_mode", "pred_policy", "satd_round", "cost_domain",
         "mb_row_begin", "mb_row_end", "n_gpus")] + [("device_ids", C.c_int32 * MAX_GPUS),
-                                                     ("async_reference", C.c_int32)]
+                                                     ("async_reference", C.c_int32), ("slice_rows", C.c_int32)]
 
 
 MBRESULT_DTYPE = np.dtype([("mv", np.int16, (BLOCKS_PER_MB, 2)), ("cost", np.int32, (BLOCKS_PER_MB,)),
@@ -52,7 +52,7 @@ assert MBRESULT_DTYPE.itemsize == 372, MBRESULT_DTYPE.itemsize
 EXPORTS = [
     "jmme_default_params", "jmme_create", "jmme_destroy", "jmme_strerror", "jmme_last_error", "jmme_backend",
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
-    "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_subimage",
+    "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
     "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_push_stripe_dev", "jmme_launch_count",
     "jmme_set_profiling",
     "jmme_get_kernel_times", "jmme_InitMotionSearchModule", "jmme_SetMotionVectorPredictor",
@@ -95,6 +95,7 @@ class Lib:
             "jmme_lambda_factor": (i32, [i32, i32]),
             "jmme_set_reference": (i32, [vp, i32, pu8, i32]),
             "jmme_search_frame": (i32, [vp, pu8, i32, pi16, vp, vp]),
+            "jmme_get_predictors": (i32, [vp, pi16]),
             "jmme_get_subimage": (i32, [vp, i32, i32, i32, pu8, i32]),
             "jmme_set_reference_dev": (i32, [vp, i32, vp, i32, vp]),
             "jmme_search_frame_dev": (i32, [vp, vp, i32, vp, vp, vp, vp]),
@@ -302,6 +303,13 @@ class Context:
         self.lib.check(self.lib.dll.jmme_predict_frame(self.handle, mv4.ctypes.data_as(C.POINTER(C.c_int16)),
                                                        ref4.ctypes.data_as(C.POINTER(C.c_int8)),
                                                        pred.ctypes.data_as(C.POINTER(C.c_int16))), self.handle)
+        return pred
+
+    def get_predictors(self):
+        """Predictors used by the last PRED_MEDIAN search: int16 [num_refs, n_mb, 41, 2]."""
+        pred = np.zeros((self.num_refs, self.mb_w * self.mb_h, BLOCKS_PER_MB, 2), np.int16)
+        self.lib.check(self.lib.dll.jmme_get_predictors(self.handle, pred.ctypes.data_as(C.POINTER(C.c_int16))),
+                       self.handle)
         return pred
 
     def get_subimage(self, ref_idx, xfrac, yfrac):

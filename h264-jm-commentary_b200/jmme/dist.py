@@ -10,13 +10,15 @@ from . import abi
 REC = abi.MBRESULT_DTYPE.itemsize
 
 
-def stripe_of(rank: int, world: int, mb_h: int):
+def stripe_of(rank: int, world: int, mb_h: int, unit: int = 1):
     """Contiguous MB rows [begin, end) of `rank`.  Every stripe has ceil(mb_h/world) rows except the
     last non-empty one: the largest stripe is as small as an even split would make
     it, and rank r's rows start at r*ceil(mb_h/world), so that the stripes, padded to that size, tile
     the all-gather buffer in frame order and the gather needs no re-packing.  A rank past the end of
-    the frame gets an empty stripe (begin == end)."""
-    rows = -(-mb_h // world)
+    the frame gets an empty stripe (begin == end).
+    unit > 1: stripes are whole groups of `unit` rows (the slices of JMME_PRED_MEDIAN, whose stripes must
+    start and end on slice boundaries)."""
+    rows = -(-(-(-mb_h // unit)) // world) * unit
     b = min(rank * rows, mb_h)
     return b, min(b + rows, mb_h)
 

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define JMME_ABI_VERSION     1
+#define JMME_ABI_VERSION     2
 #define JMME_BLOCKS_PER_MB   41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 */
 #define JMME_MAX_REFS        4
 #define JMME_MAX_SEARCH_RANGE 64
@@ -63,6 +63,9 @@ extern "C" {
 #define JMME_PRED_ZERO       0      /* (0,0) everywhere                                         */
 #define JMME_PRED_PER_MB     1      /* caller passes one predictor per (ref, MB)                */
 #define JMME_PRED_PER_BLOCK  2      /* caller passes 41 predictors per (ref, MB)                */
+#define JMME_PRED_MEDIAN     3      /* closed loop inside the frame: H.264 8.4.1.3 median of the */
+                                    /* MVs committed for the left / upper MBs of the same slice  */
+                                    /* (params.slice_rows); DESIGN.md §2 "in-frame median"       */
 
 /* blocktypes 1..7 = 16x16,16x8,8x16,8x8,8x4,4x8,4x4 (JM blc_size); bit t of blocktype_mask */
 #define JMME_MASK_16x16      0x02
@@ -89,6 +92,9 @@ typedef struct jmme_params {
     int32_t async_reference;     /* 1: jmme_set_reference returns once its copy and kernel are   */
                                  /* queued; the luma buffer must stay unchanged until the next  */
                                  /* jmme_search_frame / jmme_get_subimage returns (pinned memory) */
+    int32_t slice_rows;          /* JMME_PRED_MEDIAN: MB rows per slice (neighbours outside the  */
+                                 /* slice are unavailable); 0 = one slice = the frame.  Stripes  */
+                                 /* (mb_row_begin/end, n_gpus) start and end on slice boundaries */
 } jmme_params;
 
 /* One macroblock's result.  Block order: blocktype 1..7, raster order inside the MB
@@ -126,13 +132,17 @@ int         jmme_lambda_factor(int qp, int rdopt);     /* (int)(65536*lambda_mot
 int jmme_set_reference(jmme_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
 
 /* Search every MB of the context's stripe against every reference.
- *   pred         NULL for JMME_PRED_ZERO, else int16 [num_refs][mb_count][nb][2] in
+ *   pred         NULL for JMME_PRED_ZERO / JMME_PRED_MEDIAN, else int16 [num_refs][mb_count][nb][2] in
  *                quarter-pel units, nb = 1 (PER_MB) or 41 (PER_BLOCK); mb_count = whole frame
  *   out          [mb_w*mb_h] (whole-frame indexing; only the stripe's rows are written)
  *   out_per_ref  NULL or [num_refs][mb_w*mb_h]: per-reference winners, cost without reference
  *                rate (JM all_mv / motion_cost) */
 int jmme_search_frame(jmme_ctx *ctx, const uint8_t *cur_luma, int stride,
                       const int16_t *pred, jmme_mbresult *out, jmme_mbresult *out_per_ref);
+
+/* The predictors the last jmme_search_frame of a JMME_PRED_MEDIAN context used:
+ * int16 [num_refs][mb_w*mb_h][41][2] (only the stripe's rows are meaningful). */
+int jmme_get_predictors(jmme_ctx *ctx, int16_t *pred);
 
 /* Copy one quarter-pel plane (xfrac,yfrac in 0..3) of reference ref_idx back to the host,
  * padded size (W16+2*pad) x (H16+2*pad), for parity checks of (a12). */

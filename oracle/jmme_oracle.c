@@ -47,6 +47,9 @@ struct jmme_ctx {
     int32_t *mvbits;                 /* centred table, index v + MAX_MVD */
     int16_t *spx, *spy;              /* spiral */
     int ncand;
+    int16_t *med_pred;               /* JMME_PRED_MEDIAN: predictors [ref][mb][41][2] of the last search */
+    int16_t *fmv;                    /* ... and the field committed so far: [4*mb_h][4*mb_w][2] */
+    int8_t *fref;                    /*                                     [4*mb_h][4*mb_w]    */
     char err[256];
 };
 
@@ -257,8 +260,8 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
         p->search_range > JMME_MAX_SEARCH_RANGE || p->num_refs < 1 || p->num_refs > JMME_MAX_REFS ||
         (p->blocktype_mask & ~JMME_MASK_ALL) || !(p->blocktype_mask & JMME_MASK_ALL) ||
         p->qp < 0 || p->qp > 51 || p->lambda_factor < 0 ||
-        p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 2 ||
-        p->satd_round < 0 || p->satd_round > 1)
+        p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 3 ||
+        p->satd_round < 0 || p->satd_round > 1 || p->slice_rows < 0)
         return JMME_ERR_PARAM;
     if (p->cost_domain != 0) return JMME_ERR_UNSUPPORTED;
     c = (jmme_ctx *)calloc(1, sizeof *c);
@@ -269,6 +272,12 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
     if (c->p.mb_row_end == 0) c->p.mb_row_end = c->mb_h;
     if (c->p.mb_row_begin < 0 || c->p.mb_row_end > c->mb_h || c->p.mb_row_begin >= c->p.mb_row_end) {
         free(c); return JMME_ERR_PARAM;
+    }
+    if (p->pred_policy == JMME_PRED_MEDIAN) {       /* stripes start and end on slice boundaries */
+        const int k = p->slice_rows ? p->slice_rows : c->mb_h;
+        if (c->p.mb_row_begin % k || (c->p.mb_row_end % k && c->p.mb_row_end != c->mb_h)) {
+            free(c); return JMME_ERR_PARAM;
+        }
     }
     c->pad = pad_for(p->search_range);
     c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
@@ -290,6 +299,7 @@ int jmme_destroy(jmme_ctx *c)
     int r;
     if (!c) return JMME_OK;
     for (r = 0; r < JMME_MAX_REFS; r++) free(c->planes[r]);
+    free(c->med_pred); free(c->fmv); free(c->fref);
     free(c->mvbits); free(c->spx); free(c->spy); free(c);
     return JMME_OK;
 }
@@ -631,48 +641,60 @@ static int cell_available(const jmme_ctx *c, int x, int y, int mbx, int mby, int
     }
 }
 
+/* Predictor of block (t; i,j) of MB (mbx,mby) for reference r from the field (mv4, ref4).
+ * slice_top: first MB row of the slice (rows above it are unavailable).
+ * p16: NULL = neighbour cells inside this MB are read from the field (a field of an earlier pass);
+ *      else they carry (p16, r): the in-frame median policy, DESIGN.md §2. */
+static void predict_block(const jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int r, int mbx, int mby, int t,
+                          int i, int j, int slice_top, const int16_t *p16, int16_t *o)
+{
+    static const int16_t zero[2] = {0, 0};
+    const int fw = 4 * c->mb_w, bw = blc_w[t], bh = blc_h[t];
+    const int x0 = i * bw, y0 = j * bh;
+    const int cx = 4 * mbx + x0 / 4, cy = 4 * mby + y0 / 4, wc = bw / 4;
+    const int nx[4] = {cx - 1, cx, cx + wc, cx - 1}, ny[4] = {cy, cy - 1, cy - 1, cy - 1};
+    const int16_t *mv[4];
+    int rf[4], av[4], k, part = t == 2 ? j : (t == 3 ? i : 0);
+    for (k = 0; k < 4; k++) {
+        av[k] = cell_available(c, nx[k], ny[k], mbx, mby, t, x0, y0) && ny[k] >= 4 * slice_top;
+        mv[k] = av[k] ? mv4 + ((size_t)ny[k] * fw + nx[k]) * 2 : zero;
+        rf[k] = av[k] ? ref4[(size_t)ny[k] * fw + nx[k]] : -1;
+        if (av[k] && p16 && (nx[k] >> 2) == mbx && (ny[k] >> 2) == mby) { mv[k] = p16; rf[k] = r; }
+    }
+    if (!av[2]) { av[2] = av[3]; mv[2] = mv[3]; rf[2] = rf[3]; }     /* C := D */
+    jmme_SetMotionVectorPredictor(t, part, r, mv[0], rf[0], av[0], mv[1], rf[1], av[1], mv[2], rf[2], av[2], o);
+}
+
+/* all 41 predictors of one MB and reference; o = int16 [41][2] */
+static void predict_mb(const jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int r, int mbx, int mby,
+                       int slice_top, int in_frame, int16_t *o)
+{
+    int t, i, j;
+    for (t = 1; t <= 7; t++) {
+        const int nbx = 16 / blc_w[t], nby = 16 / blc_h[t];
+        for (j = 0; j < nby; j++)
+            for (i = 0; i < nbx; i++)     /* block 0 (16x16) comes first: o[0..1] is p16 for the others */
+                predict_block(c, mv4, ref4, r, mbx, mby, t, i, j, slice_top, in_frame && t > 1 ? o : NULL,
+                              o + 2 * (blk_base[t] + j * nbx + i));
+    }
+}
+
 int jmme_predict_frame(jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int16_t *pred)
 {
-    int r, mb, t, fw;
-    static const int16_t zero[2] = {0, 0};
+    int r, mb;
     if (!c || !mv4 || !ref4 || !pred) return JMME_ERR_PARAM;
-    fw = 4 * c->mb_w;
     for (r = 0; r < c->p.num_refs; r++)
-        for (mb = 0; mb < c->mb_w * c->mb_h; mb++) {
-            const int mbx = mb % c->mb_w, mby = mb / c->mb_w;
-            for (t = 1; t <= 7; t++) {
-                const int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh;
-                int j, i;
-                for (j = 0; j < nby; j++)
-                    for (i = 0; i < nbx; i++) {
-                        const int blk = blk_base[t] + j * nbx + i, x0 = i * bw, y0 = j * bh;
-                        const int cx = 4 * mbx + x0 / 4, cy = 4 * mby + y0 / 4, wc = bw / 4;
-                        const int nx[4] = {cx - 1, cx, cx + wc, cx - 1}, ny[4] = {cy, cy - 1, cy - 1, cy - 1};
-                        const int16_t *mv[4];
-                        int rf[4], av[4], k, part = t == 2 ? j : (t == 3 ? i : 0);
-                        int16_t *o = pred + (((size_t)r * c->mb_w * c->mb_h + mb) * JMME_BLOCKS_PER_MB + blk) * 2;
-                        for (k = 0; k < 4; k++) {
-                            av[k] = cell_available(c, nx[k], ny[k], mbx, mby, t, x0, y0);
-                            mv[k] = av[k] ? mv4 + ((size_t)ny[k] * fw + nx[k]) * 2 : zero;
-                            rf[k] = av[k] ? ref4[(size_t)ny[k] * fw + nx[k]] : -1;
-                        }
-                        if (!av[2]) { av[2] = av[3]; mv[2] = mv[3]; rf[2] = rf[3]; }     /* C := D */
-                        jmme_SetMotionVectorPredictor(t, part, r, mv[0], rf[0], av[0], mv[1], rf[1], av[1], mv[2], rf[2],
-                                                      av[2], o);
-                    }
-            }
-        }
+        for (mb = 0; mb < c->mb_w * c->mb_h; mb++)
+            predict_mb(c, mv4, ref4, r, mb % c->mb_w, mb / c->mb_w, 0, 0,
+                       pred + ((size_t)r * c->mb_w * c->mb_h + mb) * JMME_BLOCKS_PER_MB * 2);
     return JMME_OK;
 }
 
 /* ME-only mode decision: DESIGN.md §2 */
-int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_t *ref4, uint8_t *mode)
+static void commit_mb(const jmme_ctx *c, const jmme_mbresult *m, int mb, int16_t *mv4, int8_t *ref4, uint8_t *mode)
 {
-    int mb, fw;
-    if (!c || !res || !mv4 || !ref4 || !mode) return JMME_ERR_PARAM;
-    fw = 4 * c->mb_w;
-    for (mb = 0; mb < c->mb_w * c->mb_h; mb++) {
-        const jmme_mbresult *m = &res[mb];
+    const int fw = 4 * c->mb_w;
+    {
         const int mbx = mb % c->mb_w, mby = mb / c->mb_w;
         int64_t J[4], best;
         int sub[4] = {0, 0, 0, 0}, q, t, k, md, cell;
@@ -698,8 +720,10 @@ int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_
         }
         md = 0; best = J[0];
         for (k = 1; k < 4; k++) if (J[k] < best) { best = J[k]; md = k; }
-        mode[5 * mb] = (uint8_t)(md == 3 ? 8 : md + 1);
-        for (q = 0; q < 4; q++) mode[5 * mb + 1 + q] = (uint8_t)(md == 3 ? sub[q] : 0);
+        if (mode) {
+            mode[5 * mb] = (uint8_t)(md == 3 ? 8 : md + 1);
+            for (q = 0; q < 4; q++) mode[5 * mb + 1 + q] = (uint8_t)(md == 3 ? sub[q] : 0);
+        }
         for (cell = 0; cell < 16; cell++) {
             const int cx4 = cell & 3, cy4 = cell >> 2, q8 = 2 * (cy4 >> 1) + (cx4 >> 1);
             const int tt = md == 3 ? sub[q8] : md + 1;
@@ -710,6 +734,12 @@ int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_
         }
 #undef ON
     }
+}
+int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_t *ref4, uint8_t *mode)
+{
+    int mb;
+    if (!c || !res || !mv4 || !ref4 || !mode) return JMME_ERR_PARAM;
+    for (mb = 0; mb < c->mb_w * c->mb_h; mb++) commit_mb(c, &res[mb], mb, mv4, ref4, mode);
     return JMME_OK;
 }
 
@@ -719,7 +749,7 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
                       jmme_mbresult *out_per_ref, int mbx, int mby, int32_t *bsad)
 {
     const int R = c->p.search_range, nmb = c->mb_w * c->mb_h, mb = mby * c->mb_w + mbx;
-    const int npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
+    const int npb = c->p.pred_policy >= JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
     const int bonus_base = c->p.rdopt ? 0 : weighted_cost(c->lambda_factor, 16);
     jmme_mbresult *o = &out[mb];
     int r, t, b;
@@ -790,11 +820,18 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
     int r, x, y, nmb, npb, n_stripe, fail = 0;
     uint8_t *cur;                    /* current picture padded to x16 by replication */
     if (!c || !cur_in || !out || stride < c->p.width) return JMME_ERR_PARAM;
-    if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return set_err(c, JMME_ERR_PARAM, "pred required");
+    if (c->p.pred_policy == JMME_PRED_MEDIAN) pred = NULL;
+    else if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return set_err(c, JMME_ERR_PARAM, "pred required");
     for (r = 0; r < c->p.num_refs; r++)
         if (!c->ref_set[r]) return set_err(c, JMME_ERR_STATE, "reference not set");
     nmb = c->mb_w * c->mb_h;
     npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
+    if (c->p.pred_policy == JMME_PRED_MEDIAN && !c->med_pred) {
+        c->med_pred = (int16_t *)calloc((size_t)c->p.num_refs * nmb * JMME_BLOCKS_PER_MB * 2, sizeof(int16_t));
+        c->fmv = (int16_t *)calloc((size_t)nmb * 16 * 2, sizeof(int16_t));
+        c->fref = (int8_t *)malloc((size_t)nmb * 16);
+        if (!c->med_pred || !c->fmv || !c->fref) return JMME_ERR_NOMEM;
+    }
     if (pred && c->p.pred_policy != JMME_PRED_ZERO) {
         size_t i, n = (size_t)c->p.num_refs * nmb * npb * 2;
         for (i = 0; i < n; i++)
@@ -820,7 +857,27 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
             }
         }
 #pragma omp barrier
-        if (!fail) {
+        if (!fail && c->p.pred_policy == JMME_PRED_MEDIAN) {
+            /* in-frame median: slices are independent, MBs of a slice in raster order:
+             * predict from the field committed so far -> search -> commit */
+            const int k = c->p.slice_rows ? c->p.slice_rows : c->mb_h;
+            const int n_slices = (c->p.mb_row_end - c->p.mb_row_begin + k - 1) / k;
+#pragma omp for schedule(dynamic, 1)
+            for (i = 0; i < n_slices; i++) {
+                const int top = c->p.mb_row_begin + i * k;
+                const int bot = top + k < c->p.mb_row_end ? top + k : c->p.mb_row_end;
+                int mbx, mby, rr;
+                for (mby = top; mby < bot; mby++)
+                    for (mbx = 0; mbx < c->mb_w; mbx++) {
+                        const int mb = mby * c->mb_w + mbx;
+                        for (rr = 0; rr < c->p.num_refs; rr++)
+                            predict_mb(c, c->fmv, c->fref, rr, mbx, mby, top, 1,
+                                       c->med_pred + ((size_t)rr * nmb + mb) * JMME_BLOCKS_PER_MB * 2);
+                        search_mb(c, cur, c->med_pred, out, out_per_ref, mbx, mby, bsad);
+                        commit_mb(c, &out[mb], mb, c->fmv, c->fref, NULL);
+                    }
+            }
+        } else if (!fail) {
 #pragma omp for schedule(dynamic, 4)
             for (i = 0; i < n_stripe; i++)
                 search_mb(c, cur, pred, out, out_per_ref, i % c->mb_w, c->p.mb_row_begin + i / c->mb_w, bsad);
@@ -829,4 +886,12 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
     }
     free(cur);
     return fail ? JMME_ERR_NOMEM : JMME_OK;
+}
+
+int jmme_get_predictors(jmme_ctx *c, int16_t *pred)
+{
+    if (!c || !pred) return JMME_ERR_PARAM;
+    if (c->p.pred_policy != JMME_PRED_MEDIAN || !c->med_pred) return set_err(c, JMME_ERR_STATE, "no median search yet");
+    memcpy(pred, c->med_pred, sizeof(int16_t) * 2 * JMME_BLOCKS_PER_MB * (size_t)c->p.num_refs * c->mb_w * c->mb_h);
+    return JMME_OK;
 }

@@ -154,23 +154,32 @@ def decode_rank(t, x, y):
     return (2 * (y // 8) + x // 8) * 16 + ((y % 8) // h) * (8 // w) + (x % 8) // w
 
 
-def predict_frame(mv4, ref4, mb_w, mb_h, num_refs):
+def predict_frame(mv4, ref4, mb_w, mb_h, num_refs, slice_rows=None):
+    """slice_rows=None: predictors from a field of an earlier pass (jmme_predict_frame).
+    slice_rows=k (0 = whole frame): the in-frame median policy (JMME_PRED_MEDIAN): rows above the slice are
+    unavailable and the already-decoded partitions of the MB itself carry the MB's own 16x16 predictor."""
     from jmme import abi
     blocks = abi.block_table()
     pred = np.zeros((num_refs, mb_w * mb_h, 41, 2), np.int16)
+    in_frame = slice_rows is not None
+    k = (slice_rows or mb_h) if in_frame else mb_h
     for r in range(num_refs):
         for mb in range(mb_w * mb_h):
             mbx, mby = mb % mb_w, mb // mb_w
+            top = (mby // k) * k if in_frame else 0
             for b, (t, x0, y0, w, h) in enumerate(blocks):
                 def nb(px, py):                                    # neighbour at MB-relative pixel (px, py)
                     gx, gy = 16 * mbx + px, 16 * mby + py
                     if gx < 0 or gy < 0 or gx >= 16 * mb_w or gy >= 16 * mb_h:
                         return (0, 0, -1, 0)
                     nmx, nmy = gx // 16, gy // 16
-                    if (nmy, nmx) > (mby, mbx):
-                        return (0, 0, -1, 0)                       # a later macroblock
-                    if (nmy, nmx) == (mby, mbx) and decode_rank(t, px, py) >= decode_rank(t, x0, y0):
-                        return (0, 0, -1, 0)                       # a later partition of this macroblock
+                    if (nmy, nmx) > (mby, mbx) or nmy < top:
+                        return (0, 0, -1, 0)                       # a later macroblock / another slice
+                    if (nmy, nmx) == (mby, mbx):
+                        if decode_rank(t, px, py) >= decode_rank(t, x0, y0):
+                            return (0, 0, -1, 0)                   # a later partition of this macroblock
+                        if in_frame:
+                            return (int(pred[r, mb, 0, 0]), int(pred[r, mb, 0, 1]), r, 1)
                     return (int(mv4[gy // 4, gx // 4, 0]), int(mv4[gy // 4, gx // 4, 1]), int(ref4[gy // 4, gx // 4]), 1)
                 A, B, Cc, D = nb(x0 - 1, y0), nb(x0, y0 - 1), nb(x0 + w, y0 - 1), nb(x0 - 1, y0 - 1)
                 part = (y0 // 8) if t == 2 else ((x0 // 8) if t == 3 else 0)

@@ -37,7 +37,7 @@ def assert_same(got, exp, what=""):
 
 def test_library_is_the_cuda_backend(cuda):
     assert cuda.backend() == "cuda-sm_100a"
-    assert cuda.dll.jmme_abi_version() == 1
+    assert cuda.dll.jmme_abi_version() == 2
 
 
 def test_tables_leaf(cuda, oracle):
@@ -366,3 +366,90 @@ def test_randomised_configurations(cuda, oracle):
         o, op = run(oracle, cur, refs, pred, True, **kw)
         assert_same(gp, op, f"case {case} per-ref {w}x{h} {kw}")
         assert_same(g, o, f"case {case} best {w}x{h} {kw}")
+
+
+# ---- JMME_PRED_MEDIAN: predictor loop closed inside the frame (wavefront on the GPU, raster order in the oracle) ----
+def run_median(lib, cur, refs, **kw):
+    h, w = cur.shape
+    with lib.context(width=w, height=h, num_refs=len(refs), pred_policy=abi.PRED_MEDIAN, **kw) as ctx:
+        for i, r in enumerate(refs):
+            ctx.set_reference(i, r)
+        out, opr = ctx.search_frame(cur, None, True)
+        return out, opr, ctx.get_predictors()
+
+
+MEDIAN_CASES = [
+    (80, 64, 6, dict(slice_rows=0, qp=30, subpel=1), 2),
+    (80, 64, 6, dict(slice_rows=1, qp=30, subpel=1), 1),
+    (96, 80, 8, dict(slice_rows=2, qp=26, subpel=1, rdopt=1), 2),
+    (72, 56, 5, dict(slice_rows=0, qp=36, subpel=0), 1),                       # sizes not multiples of 16
+    (64, 48, 5, dict(slice_rows=0, qp=34, rdopt=1, search_mode=abi.SEARCH_FULL, subpel=1), 1),
+    (64, 48, 5, dict(slice_rows=2, qp=28, blocktype_mask=0x92, subpel=1), 2),
+    (64, 48, 5, dict(slice_rows=0, blocktype_mask=abi.MASK_16x16, subpel=1), 1),
+    (176, 144, 16, dict(slice_rows=3, qp=28, subpel=1), 1),
+    (128, 96, 32, dict(slice_rows=0, qp=32, subpel=1, use_hadamard=0), 1),
+    (64, 64, 40, dict(slice_rows=0, qp=30, subpel=0), 1),                      # R > 32: the me_int.cu kernel
+]
+
+
+@pytest.mark.parametrize("w,h,R,kw,nref", MEDIAN_CASES)
+def test_in_frame_median_matches_oracle(cuda, oracle, w, h, R, kw, nref):
+    cur, refs = synth.frame_pair(w, h, seed=w + R, search_range=R, num_refs=nref)
+    g, gp, gpred = run_median(cuda, cur, refs, search_range=R, **kw)
+    o, op, opred = run_median(oracle, cur, refs, search_range=R, **kw)
+    assert np.array_equal(gpred, opred), "predictors"
+    assert_same(gp, op, "per-ref")
+    assert_same(g, o, "best")
+
+
+@pytest.mark.parametrize("variant", [68, 64, 65, 47, 32])
+def test_in_frame_median_kernel_variants(cuda, oracle, variant):
+    w, h, R = 96, 64, 8
+    cur, refs = synth.frame_pair(w, h, seed=3, search_range=R)
+    kw = dict(search_range=R, slice_rows=2, qp=30, subpel=1)
+    os.environ["JMME_VARIANT"] = str(variant)
+    try:
+        g, _, gpred = run_median(cuda, cur, refs, **kw)
+    finally:
+        del os.environ["JMME_VARIANT"]
+    o, _, opred = run_median(oracle, cur, refs, **kw)
+    assert np.array_equal(gpred, opred)
+    assert_same(g, o, f"variant {variant}")
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_in_frame_median_stripes_and_virtual_devices(cuda, oracle, n):
+    """Whole slices per device: the result does not depend on the device count; stripes that cut a slice
+    are refused like the oracle refuses them."""
+    import torch
+    ndev = torch.cuda.device_count()
+    w, h, R = 64, 112, 6                                     # 7 MB rows, slices of 2 rows -> 4 slices
+    cur, refs = synth.frame_pair(w, h, seed=9, search_range=R, num_refs=2)
+    kw = dict(search_range=R, slice_rows=2, qp=30, subpel=1)
+    o, op, opred = run_median(oracle, cur, refs, **kw)
+    g, gp, gpred = run_median(cuda, cur, refs, n_gpus=n, device_ids=[i % ndev for i in range(n)], **kw)
+    assert np.array_equal(gpred, opred)
+    assert_same(gp, op, f"per-ref n_gpus={n}")
+    assert_same(g, o, f"best n_gpus={n}")
+    for lib in (cuda, oracle):
+        with pytest.raises(abi.JmmeError) as e:
+            lib.context(width=w, height=h, pred_policy=abi.PRED_MEDIAN, mb_row_begin=1, mb_row_end=4, **kw)
+        assert e.value.code == abi.ERR_PARAM
+
+
+def test_in_frame_median_device_api_and_repeat(cuda, oracle):
+    """Device-resident entry point, two frames in a row through one context (the field of the first frame
+    must not leak into the second)."""
+    import torch
+    from jmme.torch_api import DeviceSearch
+    w, h, R = 96, 64, 8
+    kw = dict(width=w, height=h, search_range=R, pred_policy=abi.PRED_MEDIAN, slice_rows=0, qp=30, subpel=1)
+    ds = DeviceSearch(cuda, **kw)
+    for seed in (5, 6):
+        cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R)
+        ds.set_reference(0, torch.from_numpy(refs[0]).cuda())
+        got = ds.to_numpy(ds.search(torch.from_numpy(cur).cuda()))
+        torch.cuda.synchronize()
+        o, _, _ = run_median(oracle, cur, refs, **{k: v for k, v in kw.items() if k not in ("width", "height", "pred_policy")})
+        assert_same(got, o, f"seed {seed}")
+    ds.close()

@@ -7,7 +7,7 @@ import refimpl
 
 def test_backend_and_abi(oracle):
     assert oracle.backend() == "cpu-oracle"
-    assert oracle.dll.jmme_abi_version() == 1
+    assert oracle.dll.jmme_abi_version() == 2
 
 
 def test_mvbits_known_answers(oracle):
