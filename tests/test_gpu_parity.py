@@ -453,3 +453,25 @@ def test_in_frame_median_device_api_and_repeat(cuda, oracle):
         o, _, _ = run_median(oracle, cur, refs, **{k: v for k, v in kw.items() if k not in ("width", "height", "pred_policy")})
         assert_same(got, o, f"seed {seed}")
     ds.close()
+
+
+def test_yuv_sequence_pass_matches_oracle(cuda, oracle, tmp_path):
+    """encoder.cfg + planar YUV file -> IPPP ME pass (jmme/cfg.py, jmme/sequence.py), GPU against oracle."""
+    from jmme.cfg import EncoderCfg
+    from jmme.sequence import search_sequence, yuv_frames
+    w, h, R = 96, 80, 8
+    lumas = [synth.gen_luma(w, h, 5)] + [synth.frame_pair(w, h, seed=5, search_range=R + k)[0] for k in range(3)]
+    synth.write_yuv420(tmp_path / "seq.yuv", lumas)
+    (tmp_path / "encoder.cfg").write_text(
+        f"InputFile = seq.yuv\nFramesToBeEncoded = 4\nSourceWidth = {w}\nSourceHeight = {h}\nSearchRange = {R}\n"
+        "NumberReferenceFrames = 2\nQPPSlice = 30\nSliceMode = 1\nSliceArgument = 12\n")
+    cfg = EncoderCfg.load(tmp_path / "encoder.cfg")
+    kw = cfg.params()
+    kw.pop("width"), kw.pop("height")
+    for policy in (abi.PRED_ZERO, abi.PRED_MEDIAN):
+        k2 = dict(kw) if policy == abi.PRED_MEDIAN else {k: v for k, v in kw.items() if k != "slice_rows"}
+        a = list(search_sequence(cuda, yuv_frames(tmp_path / "seq.yuv", w, h, cfg.frames), policy, **k2))
+        b = list(search_sequence(oracle, yuv_frames(tmp_path / "seq.yuv", w, h, cfg.frames), policy, **k2))
+        assert len(a) == len(b) == 3
+        for (n, ga, _), (_, gb, _) in zip(a, b):
+            assert_same(ga, gb, f"policy {policy} frame {n}")
