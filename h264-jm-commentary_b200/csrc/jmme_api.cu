@@ -29,9 +29,8 @@ cudaError_t jmme_launch_predict(const int16_t *mv4, const int8_t *ref4, int mb_w
                                 cudaStream_t st);
 cudaError_t jmme_launch_commit(const jmme_mbresult *res, int mb_w, int mb_h, int mask, int16_t *mv4, int8_t *ref4,
                                uint8_t *mode, cudaStream_t st);
-cudaError_t jmme_launch_wave_step(const jmme_mbresult *res, const int *prev, int n_prev, const int *cur, int n_cur, int mb_w,
-                                  int mb_h, int num_refs, int mask, int slice_rows, int16_t *mv4, int8_t *ref4,
-                                  int16_t *pred, cudaStream_t st);
+cudaError_t jmme_launch_wave_step(const int *cur, int n_cur, int mb_w, int mb_h, int num_refs, int slice_rows,
+                                  const int16_t *mv4, const int8_t *ref4, int16_t *pred, cudaStream_t st);
 cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st);
 
 struct jmme_ctx {
@@ -297,13 +296,13 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     if (c->p.pred_policy == JMME_PRED_MEDIAN) {
         // predict -> search -> commit, one wavefront step after the other; the kernels of a step work on
         // that step's list of MBs with the per-block predictors wave_step_kernel has just written
+        // (the kernel that writes the records of a step — sub-pel or reference selection — commits its MBs)
         P.pred = c->d_pred; P.pred_policy = JMME_PRED_PER_BLOCK;
+        P.field_mv = c->d_fmv; P.field_ref = c->d_fref;
         for (int t = 0; t < c->n_steps; t++) {
-            const int *prev = t ? c->d_wave + c->wave_off[t - 1] : nullptr;
-            const int n_prev = t ? c->wave_off[t] - c->wave_off[t - 1] : 0;
             P.mb_list = c->d_wave + c->wave_off[t]; P.n_list = c->wave_off[t + 1] - c->wave_off[t];
-            CU(c, jmme_launch_wave_step(d_out, prev, n_prev, P.mb_list, P.n_list, c->mb_w, c->mb_h, c->p.num_refs,
-                                        c->p.blocktype_mask, c->p.slice_rows, c->d_fmv, c->d_fref, c->d_pred, st));
+            CU(c, jmme_launch_wave_step(P.mb_list, P.n_list, c->mb_w, c->mb_h, c->p.num_refs, c->p.slice_rows, c->d_fmv,
+                                        c->d_fref, c->d_pred, st));
             if (c->p.search_mode == JMME_SEARCH_FULL) CU(c, jmme_launch_me_full(P, st));
             else CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
             c->launches += 2;

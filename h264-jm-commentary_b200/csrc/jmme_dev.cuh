@@ -44,6 +44,8 @@ struct SearchParams {
     int fused_select;                    // 1: the sub-pel kernel writes `out` itself (one reference)
     const int *mb_list;                  // non-null: search these n_list MBs (frame MB indices) instead of the
     int n_list;                          //           stripe's rows: one step of the in-frame median wavefront
+    int16_t *field_mv;                   // non-null (in-frame median): the kernel that writes `out` also commits the
+    int8_t *field_ref;                   //           MB to the 4x4-granular field [4 mb_h][4 mb_w]([2])
 };
 
 // the MBs one launch works on: a stripe of MB rows, or an explicit list
@@ -77,6 +79,65 @@ __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c)
     unsigned d;
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+// ---- ME-only mode decision, shared by commit_kernel and the in-frame median epilogues ----
+// index base of blocktype t in the result order: 0,0,1,3,5,9,17,25
+__device__ __forceinline__ int blk_base_of(int t) { return (int)((0x1911090503010000ull >> (8 * t)) & 0xFF); }
+
+// cost[41] of one MB -> low 2 bits = 0..2 for 16x16 / 16x8 / 8x16, 3 = P8x8; bits 4+4q.. = sub-type of 8x8
+// number q.  (One packed word, no local arrays: this runs on the serial path of the wavefront.)
+__device__ inline int mb_mode(const int32_t *cost, int mask)
+{
+    const long long INF = 0x7FFFFFFFFFFFFFFFll;
+    const long long J0 = (mask >> 1) & 1 ? (long long)cost[0] : INF;
+    const long long J1 = (mask >> 2) & 1 ? (long long)cost[1] + cost[2] : INF;
+    const long long J2 = (mask >> 3) & 1 ? (long long)cost[3] + cost[4] : INF;
+    long long J3 = 0;
+    int subs = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        long long bq = INF;
+        int st = 0;
+#pragma unroll
+        for (int t = 4; t <= 7; t++) {
+            if (!((mask >> t) & 1)) continue;
+            const int bw = t <= 5 ? 8 : 4, bh = (t == 4 || t == 6) ? 8 : 4, nbx = 16 / bw;
+            long long s = 0;
+#pragma unroll
+            for (int sy = (q >> 1) * (8 / bh); sy < ((q >> 1) + 1) * (8 / bh); sy++)      // blocks of type t in 8x8 q
+#pragma unroll
+                for (int sx = (q & 1) * (8 / bw); sx < ((q & 1) + 1) * (8 / bw); sx++) s += cost[blk_base_of(t) + sy * nbx + sx];
+            if (s < bq) { bq = s; st = t; }
+        }
+        subs |= st << (4 + 4 * q);
+        if (J3 != INF) J3 = bq == INF ? INF : J3 + bq;
+    }
+    int md = 0;                                            // lower mode wins ties
+    long long best = J0;
+    if (J1 < best) { best = J1; md = 1; }
+    if (J2 < best) { best = J2; md = 2; }
+    if (J3 < best) md = 3;
+    return md | subs;
+}
+// field cell (cx4, cy4) of an MB decided as `mode`: the block that covers it
+__device__ inline int cell_block(int mode, int cx4, int cy4)
+{
+    const int md = mode & 3;
+    const int t = md == 3 ? (mode >> (4 + 4 * (2 * (cy4 >> 1) + (cx4 >> 1)))) & 15 : md + 1;
+    const int lw = (t == 1 || t == 2) ? 2 : (t <= 5 ? 1 : 0), lh = (t == 1 || t == 3) ? 2 : ((t == 2 || t == 4 || t == 6) ? 1 : 0);
+    return blk_base_of(t) + ((cy4 >> lh) << (2 - lw)) + (cx4 >> lw);      // (4cy4 / bh) * (16 / bw) + 4cx4 / bw
+}
+// commit field cell `cell` (0..15) of MB `mb` from the MB's 41 (cost, packed mv, ref) triples
+__device__ inline void commit_cell(const SearchParams &P, int mb, int cell, const int32_t *cost, const uint32_t *mv,
+                                   const int8_t *ref)
+{
+    const int cx4 = cell & 3, cy4 = cell >> 2;
+    const int blk = cell_block(mb_mode(cost, P.blocktype_mask), cx4, cy4);
+    const int mby = mb / P.mb_w, mbx = mb - mby * P.mb_w;
+    const size_t o = (size_t)(4 * mby + cy4) * (4 * P.mb_w) + 4 * mbx + cx4;
+    *(uint32_t *)(P.field_mv + 2 * o) = mv[blk];
+    P.field_ref[o] = ref[blk];
 }
 
 // block geometry, result order (blocktype 1..7, raster inside the MB)

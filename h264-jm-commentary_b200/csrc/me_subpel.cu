@@ -197,30 +197,44 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
             o->reserved[tid] = 0;
             if (q) q->reserved[tid] = 0;
         }
+        if (P.field_mv) {                                  // in-frame median: commit this MB (uniform branch)
+            __shared__ int32_t s_cost[JMME_NBLK];
+            __shared__ uint32_t s_mv[JMME_NBLK];
+            __shared__ int8_t s_ref[JMME_NBLK];
+            if (owner) {
+                s_cost[b] = active ? mn + d_ref_cost(P.lambda_factor, P.rdopt, 0) : INT_MAX;
+                s_mv[b] = active ? ((uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16)) : 0u;
+                s_ref[b] = active ? (int8_t)0 : (int8_t)-1;
+            }
+            __syncthreads();
+            if (tid < 16) commit_cell(P, mb, tid, s_cost, s_mv, s_ref);
+        }
     }
 }
 
 // per (MB, block): add the reference rate and keep the cheapest reference (lowest index on ties)
 __global__ void select_ref_kernel(const SearchParams P)
 {
+    // 192 threads = 4 MBs x 48 lanes: an MB never straddles two CTAs (the commit below needs all its blocks)
+    __shared__ int32_t s_cost[4][JMME_NBLK];
+    __shared__ uint32_t s_mv[4][JMME_NBLK];
+    __shared__ int8_t s_ref[4][JMME_NBLK];
     const int n_mb_stripe = d_n_units(P);
     const int n_mb = P.mb_w * P.mb_h;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_mb_stripe * 48) return;
-    const int mbi = i / 48, b = i - mbi * 48;
-    const int mb = d_unit_mb(P, mbi);
+    const int mbi = i / 48, b = i - mbi * 48, g = threadIdx.x / 48;
+    const bool live = mbi < n_mb_stripe;
+    const int mb = live ? d_unit_mb(P, mbi) : 0;
     jmme_mbresult *o = P.out + mb;
-    if (b >= JMME_NBLK) {                                  // 3 spare lanes clear the reserved bytes
-        if (b < JMME_NBLK + 3) {
-            o->reserved[b - JMME_NBLK] = 0;
-            if (P.out_per_ref)
-                for (int r = 0; r < P.num_refs; r++) P.out_per_ref[(size_t)r * n_mb + mb].reserved[b - JMME_NBLK] = 0;
-        }
-        return;
+    if (live && b >= JMME_NBLK && b < JMME_NBLK + 3) {     // 3 spare lanes clear the reserved bytes
+        o->reserved[b - JMME_NBLK] = 0;
+        if (P.out_per_ref)
+            for (int r = 0; r < P.num_refs; r++) P.out_per_ref[(size_t)r * n_mb + mb].reserved[b - JMME_NBLK] = 0;
     }
-    const bool on = (P.blocktype_mask >> c_blk_type[b]) & 1;
+    const bool work = live && b < JMME_NBLK;
+    const bool on = work && ((P.blocktype_mask >> c_blk_type[b]) & 1);
     int bc = INT_MAX, br = -1, bx = 0, by = 0;
-    for (int r = 0; r < P.num_refs; r++) {
+    for (int r = 0; work && r < P.num_refs; r++) {
         BlkRes v = P.res[((size_t)r * n_mb + mb) * JMME_NBLK + b];
         if (P.out_per_ref) {
             jmme_mbresult *q = P.out_per_ref + (size_t)r * n_mb + mb;
@@ -230,7 +244,15 @@ __global__ void select_ref_kernel(const SearchParams P)
         const int tot = v.cost + d_ref_cost(P.lambda_factor, P.rdopt, r);
         if (on && tot < bc) { bc = tot; br = r; bx = v.mvx; by = v.mvy; }
     }
-    o->mv[b][0] = (int16_t)bx; o->mv[b][1] = (int16_t)by; o->cost[b] = bc; o->ref_idx[b] = (int8_t)br;
+    if (work) { o->mv[b][0] = (int16_t)bx; o->mv[b][1] = (int16_t)by; o->cost[b] = bc; o->ref_idx[b] = (int8_t)br; }
+    if (P.field_mv) {                                      // in-frame median: commit the MBs of this CTA (uniform branch)
+        if (work) {
+            s_cost[g][b] = bc; s_ref[g][b] = (int8_t)br;
+            s_mv[g][b] = (uint32_t)(uint16_t)bx | ((uint32_t)(uint16_t)by << 16);
+        }
+        __syncthreads();
+        if (live && b < 16) commit_cell(P, mb, b, s_cost[g], s_mv[g], s_ref[g]);
+    }
 }
 
 // stripe of the MV field -> the same offsets of up to 8 peer buffers (NVLink peer stores, 4-byte words)
@@ -267,6 +289,6 @@ cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
 cudaError_t jmme_launch_select(const SearchParams &P, cudaStream_t st)
 {
     int n = d_n_units(P) * 48;
-    select_ref_kernel<<<(n + 255) / 256, 256, 0, st>>>(P);
+    select_ref_kernel<<<(n + 191) / 192, 192, 0, st>>>(P);
     return cudaGetLastError();
 }

@@ -98,52 +98,6 @@ __global__ void predict_kernel(const int16_t *__restrict__ mv4, const int8_t *__
     pred[2 * (size_t)i + 1] = (int16_t)py;
 }
 
-// index base of blocktype t in the result order: 0,0,1,3,5,9,17,25
-__device__ __forceinline__ int blk_base_of(int t) { return (int)((0x1911090503010000ull >> (8 * t)) & 0xFF); }
-
-// ME-only mode decision of one MB: low 2 bits = 0..2 for 16x16 / 16x8 / 8x16, 3 = P8x8; bits 4+4q.. = sub-type of
-// 8x8 number q.  (One packed word, no local arrays: this runs on the serial path of the wavefront.)
-__device__ inline int mb_mode(const jmme_mbresult &m, int mask)
-{
-    const long long INF = 0x7FFFFFFFFFFFFFFFll;
-    long long J[4];
-    J[0] = (mask >> 1) & 1 ? (long long)m.cost[0] : INF;
-    J[1] = (mask >> 2) & 1 ? (long long)m.cost[1] + m.cost[2] : INF;
-    J[2] = (mask >> 3) & 1 ? (long long)m.cost[3] + m.cost[4] : INF;
-    J[3] = 0;
-    int subs = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        long long bq = INF;
-        int st = 0;
-#pragma unroll
-        for (int t = 4; t <= 7; t++) {
-            if (!((mask >> t) & 1)) continue;
-            const int bw = t <= 5 ? 8 : 4, bh = (t == 4 || t == 6) ? 8 : 4, nbx = 16 / bw;
-            long long s = 0;
-#pragma unroll
-            for (int sy = (q >> 1) * (8 / bh); sy < ((q >> 1) + 1) * (8 / bh); sy++)      // blocks of type t in 8x8 q
-#pragma unroll
-                for (int sx = (q & 1) * (8 / bw); sx < ((q & 1) + 1) * (8 / bw); sx++) s += m.cost[blk_base_of(t) + sy * nbx + sx];
-            if (s < bq) { bq = s; st = t; }
-        }
-        subs |= st << (4 + 4 * q);
-        if (J[3] != INF) J[3] = bq == INF ? INF : J[3] + bq;
-    }
-    int md = 0;
-#pragma unroll
-    for (int k = 1; k < 4; k++) if (J[k] < J[md]) md = k;
-    return md | subs;
-}
-// field cell (cx4, cy4) of an MB decided as `mode`: the block that covers it
-__device__ inline int cell_block(int mode, int cx4, int cy4)
-{
-    const int md = mode & 3;
-    const int t = md == 3 ? (mode >> (4 + 4 * (2 * (cy4 >> 1) + (cx4 >> 1)))) & 15 : md + 1;
-    const int lw = (t == 1 || t == 2) ? 2 : (t <= 5 ? 1 : 0), lh = (t == 1 || t == 3) ? 2 : ((t == 2 || t == 4 || t == 6) ? 1 : 0);
-    return blk_base_of(t) + ((cy4 >> lh) << (2 - lw)) + (cx4 >> lw);      // (4cy4 / bh) * (16 / bw) + 4cx4 / bw
-}
-
 // one thread per MB: cheapest of 16x16 / 16x8 / 8x16 / P8x8 (sub-type per 8x8), then the 16 field cells
 __global__ void commit_kernel(const jmme_mbresult *__restrict__ res, int mb_w, int mb_h, int mask,
                               int16_t *__restrict__ mv4, int8_t *__restrict__ ref4, uint8_t *__restrict__ mode)
@@ -151,7 +105,7 @@ __global__ void commit_kernel(const jmme_mbresult *__restrict__ res, int mb_w, i
     const int mb = blockIdx.x * blockDim.x + threadIdx.x;
     if (mb >= mb_w * mb_h) return;
     const jmme_mbresult &m = res[mb];
-    const int mo = mb_mode(m, mask), md = mo & 3;
+    const int mo = mb_mode(m.cost, mask), md = mo & 3;
     mode[5 * mb] = (uint8_t)(md == 3 ? 8 : md + 1);
     for (int q = 0; q < 4; q++) mode[5 * mb + 1 + q] = (uint8_t)(md == 3 ? (mo >> (4 + 4 * q)) & 15 : 0);
     const int mbx = mb % mb_w, mby = mb / mb_w, fw = 4 * mb_w;
@@ -163,27 +117,24 @@ __global__ void commit_kernel(const jmme_mbresult *__restrict__ res, int mb_w, i
     }
 }
 
-// In-frame median (JMME_PRED_MEDIAN), one step of the 2:1 wavefront, a single CTA.  The step is on the serial
-// path of the frame (predict -> search -> commit, step after step), so every phase fetches what it needs
-// with one round of independent loads into shared memory and computes from there:
-//   1. the records of the MBs searched in the previous step -> mode decision -> their 16 field cells,
-//   2. the 10 neighbour cells (4 left, 6 above) of every MB of this step,
-//   3. the 16x16 predictor of every (reference, MB) of this step,
-//   4. the other 40 predictors, whose in-MB neighbours carry that 16x16 predictor.
-#define WAVE_CH 96                                        // MBs per chunk
+// In-frame median (JMME_PRED_MEDIAN), the predictors of one step of the 2:1 wavefront, a single CTA.  (The
+// MBs of the previous step were committed to the field by the kernels that wrote their records: me_subpel.cu.)
+// The step is on the serial path of the frame (predict -> search -> commit, step after step), so every phase
+// fetches what it needs with one round of independent loads into shared memory and computes from there:
+//   1. the 10 neighbour cells (4 left, 6 above) of every MB of this step,
+//   2. the 16x16 predictor of every (reference, MB) of this step,
+//   3. the other 40 predictors, whose in-MB neighbours carry that 16x16 predictor.
+#define WAVE_CH 128                                       // MBs per chunk
 struct WaveNb { int16_t x, y; int16_t ref, avail; };
 // where the neighbours A, B, C, D of each block come from: 0..9 = slot of the MB's outer neighbour cells
 // (0..3 left column, 4..9 the row above from x-1), 10 = a partition of this MB decoded earlier (carries the
 // 16x16 predictor), 11 = a partition of this MB decoded later (unavailable); tp = blocktype | part << 3
 struct WaveTab { uint8_t src[JMME_NBLK][4]; uint8_t tp[JMME_NBLK]; };
 
-__global__ void __launch_bounds__(1024) wave_step_kernel(const jmme_mbresult *__restrict__ res, const int *__restrict__ prev,
-                                                         int n_prev, const int *__restrict__ cur, int n_cur, int mb_w,
-                                                         int mb_h, int num_refs, int mask, int slice_rows, int16_t *mv4,
-                                                         int8_t *ref4, int16_t *pred, const WaveTab tab)
+__global__ void __launch_bounds__(1024) wave_step_kernel(const int *__restrict__ cur, int n_cur, int mb_w, int mb_h,
+                                                         int num_refs, int slice_rows, const int16_t *mv4,
+                                                         const int8_t *ref4, int16_t *pred, const WaveTab tab)
 {
-    constexpr int RW = sizeof(jmme_mbresult) / 4;          // 93 words per record
-    __shared__ uint32_t s_rec[WAVE_CH * RW];
     __shared__ WaveNb s_nb[WAVE_CH][10];
     __shared__ int16_t s_p16[JMME_MAX_REFS][WAVE_CH][2];
     __shared__ int s_mb[WAVE_CH];
@@ -191,34 +142,13 @@ __global__ void __launch_bounds__(1024) wave_step_kernel(const jmme_mbresult *__
     const int tid = threadIdx.x, n_mb = mb_w * mb_h, fw = 4 * mb_w, fh = 4 * mb_h;
     if (tid < JMME_NBLK * 4) s_src[tid >> 2][tid & 3] = tab.src[tid >> 2][tid & 3];
     if (tid < JMME_NBLK) s_tp[tid] = tab.tp[tid];
-    for (int c0 = 0; c0 < n_prev; c0 += WAVE_CH) {
-        const int n = min(WAVE_CH, n_prev - c0);
-        if (tid < n) s_mb[tid] = prev[c0 + tid];
-        __syncthreads();
-#pragma unroll 3
-        for (int i = tid; i < n * RW; i += 1024) {
-            const int j = i / RW;
-            s_rec[i] = ((const uint32_t *)(res + s_mb[j]))[i - j * RW];
-        }
-        __syncthreads();
-        for (int i = tid; i < 16 * n; i += 1024) {
-            const int mb = s_mb[i >> 4], cx4 = i & 3, cy4 = (i >> 2) & 3;
-            const jmme_mbresult &m = *(const jmme_mbresult *)(s_rec + (i >> 4) * RW);
-            const int blk = cell_block(mb_mode(m, mask), cx4, cy4);
-            const int mby = mb / mb_w, mbx = mb - mby * mb_w;
-            const size_t o = (size_t)(4 * mby + cy4) * fw + 4 * mbx + cx4;
-            *(uint32_t *)(mv4 + 2 * o) = *(const uint32_t *)m.mv[blk];
-            ref4[o] = m.ref_idx[blk];
-        }
-        __syncthreads();
-    }
     const int k = slice_rows ? slice_rows : mb_h;
     for (int c0 = 0; c0 < n_cur; c0 += WAVE_CH) {
         const int n = min(WAVE_CH, n_cur - c0);
         if (tid < n) s_mb[tid] = cur[c0 + tid];
         __syncthreads();
-        if (tid < 10 * n) {                                // slot 0..3: left column, 4..9: the row above from x-1
-            const int j = tid / 10, sl = tid - 10 * j, mb = s_mb[j], mby = mb / mb_w, mbx = mb - mby * mb_w;
+        for (int i = tid; i < 10 * n; i += 1024) {         // slot 0..3: left column, 4..9: the row above from x-1
+            const int j = i / 10, sl = i - 10 * j, mb = s_mb[j], mby = mb / mb_w, mbx = mb - mby * mb_w;
             const int x = sl < 4 ? 4 * mbx - 1 : 4 * mbx - 1 + (sl - 4), y = sl < 4 ? 4 * mby + sl : 4 * mby - 1;
             WaveNb v = {0, 0, -1, 0};                      // outside the picture or the slice: unavailable
             if (x >= 0 && x < fw && y >= 4 * ((mby / k) * k) && y < fh) {
@@ -244,8 +174,8 @@ __global__ void __launch_bounds__(1024) wave_step_kernel(const jmme_mbresult *__
             const int tp = s_tp[blk];
             mv_predict(tp & 7, tp >> 3, ref, nb[0], nb[1], nb[2], px, py);
         };
-        if (tid < n * num_refs) {
-            const int ref = tid / n, j = tid - ref * n;
+        for (int i = tid; i < n * num_refs; i += 1024) {
+            const int ref = i / n, j = i - ref * n;
             int px, py;
             predict(j, 0, ref, 0, 0, px, py);
             s_p16[ref][j][0] = (int16_t)px; s_p16[ref][j][1] = (int16_t)py;
@@ -311,12 +241,10 @@ cudaError_t jmme_launch_commit(const jmme_mbresult *res, int mb_w, int mb_h, int
     return cudaGetLastError();
 }
 
-cudaError_t jmme_launch_wave_step(const jmme_mbresult *res, const int *prev, int n_prev, const int *cur, int n_cur, int mb_w,
-                                  int mb_h, int num_refs, int mask, int slice_rows, int16_t *mv4, int8_t *ref4,
-                                  int16_t *pred, cudaStream_t st)
+cudaError_t jmme_launch_wave_step(const int *cur, int n_cur, int mb_w, int mb_h, int num_refs, int slice_rows,
+                                  const int16_t *mv4, const int8_t *ref4, int16_t *pred, cudaStream_t st)
 {
-    wave_step_kernel<<<1, 1024, 0, st>>>(res, prev, n_prev, cur, n_cur, mb_w, mb_h, num_refs, mask, slice_rows, mv4, ref4,
-                                         pred, wave_tab());
+    wave_step_kernel<<<1, 1024, 0, st>>>(cur, n_cur, mb_w, mb_h, num_refs, slice_rows, mv4, ref4, pred, wave_tab());
     return cudaGetLastError();
 }
 
