@@ -16,6 +16,8 @@
 //   K            up to 8 candidates per run: 4*(7+K)/K row words per thread and candidate
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "jmme_dev.cuh"
 
 namespace {
@@ -37,7 +39,7 @@ struct TbLayout {
         off_T = off_cur + 2 * 64 * nmb;
         off_best = off_T + JMME_NT;
         off_task = off_best + 48 * nmb;                       // u16 (ybase << 8 | xbase) per main task
-        off_key = off_task + ((((ncols + K - 1) / K) * (ncols >> 4) + 1) >> 1);
+        off_key = (off_task + ((((ncols + K - 1) / K) * (ncols >> 4) + 1) >> 1) + 3) & ~3;   // 16-byte aligned (uint4 copy)
         off_bx = (off_key + (key_in_smem ? (ncols * ncols + 1) / 2 : 0) + 1) & ~1;      // 8-byte aligned (LDS.64)
         // one predictor: bits per column / row (bytes).  41 predictors: per (half, column|row) the 22 local
         // blocks' bits * 4, padded to 24 bytes, so that a thread fetches all of them as six words
@@ -74,10 +76,14 @@ struct Item {
 // NMB > 1 (with KRTAB): an item is NMB horizontally adjacent MBs.  Their windows overlap in all but 16 columns
 // each, so one prefetch + expansion (1.6x the work of one for NMB = 4) and one set of barriers serves all of
 // them, and the NMB x 45 tasks split evenly over the warps.
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB>
+// CL > 1 (MB lists of the in-frame median wavefront, where a step has fewer MBs than the GPU has SMs): a
+// thread-block cluster of CL CTAs works on one item; every CTA stages the window, takes every CL-th group of
+// tasks, and the partial minima meet in CTA 0's shared memory (distributed shared memory atomicMin).
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     extern __shared__ __align__(16) uint32_t smem[];
+    const unsigned crank = CL > 1 ? cooperative_groups::this_cluster().block_rank() : 0u;
     const TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     constexpr int NM = NMB, CURW = 64 * NM;     // MBs per item, words of one current-MB stage
     uint32_t *s_win = smem + L.off_win;
@@ -103,8 +109,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
-    if (!KEYG && !KRTAB)
-        for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
+    if (!KEYG && !KRTAB) {                               // 8 keys per load: one round trip instead of ncand / threads
+        const uint4 *src = (const uint4 *)P.spiral_key;
+        for (int i = tid; i < (ncand >> 3); i += NW * 32) ((uint4 *)s_key)[i] = src[i];
+        for (int i = (ncand & ~7) + tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
+    }
     const int bonus_base = P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16);
     const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
     for (int i = tid; i < JMME_NT; i += NW * 32)
@@ -207,12 +216,31 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                 s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + i - R) - py);
             }
         } else {
-            for (int i = tid; i < 2 * ncols * 24; i += NW * 32) {      // [half][offset][local block], bits * 4
-                const int b = i % 24, o = (i / 24) % ncols, hf = i / (24 * ncols);
-                const int gb = b < NL ? kGT[b] + hf * kDL[b] : 0;
-                const int px = pr[2 * gb], py = pr[2 * gb + 1];
-                s_bx[i] = (uint8_t)(4 * d_se_bits(4 * (it.cx + o - R) - px));
-                s_by[i] = (uint8_t)(4 * d_se_bits(4 * (it.cy + o - R) - py));
+            // [half][offset][local block] bits * 4.  thread = (word q of a row = 4 local blocks, row slot): the
+            // eight predictors it needs (4 blocks x 2 halves) are loaded once, no division in the loop
+            constexpr int TPR = NW * 32 / 6;                            // rows per pass
+            const int q = tid % 6, r0 = tid / 6;
+            if (r0 < TPR) {
+                int px[2][4], py[2][4];
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int b = 4 * q + j, gb = b < NL ? kGT[b] + hf * kDL[b] : 0;
+                        px[hf][j] = pr[2 * gb]; py[hf][j] = pr[2 * gb + 1];
+                    }
+                for (int row = r0; row < 2 * ncols; row += TPR) {
+                    const int hf = row >= ncols, o = row - (hf ? ncols : 0);
+                    const int vx = 4 * (it.cx + o - R), vy = 4 * (it.cy + o - R);
+                    uint32_t wx = 0, wy = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        wx |= (uint32_t)(4 * d_se_bits(vx - (hf ? px[1][j] : px[0][j]))) << (8 * j);
+                        wy |= (uint32_t)(4 * d_se_bits(vy - (hf ? py[1][j] : py[0][j]))) << (8 * j);
+                    }
+                    ((uint32_t *)s_bx)[row * 6 + q] = wx;
+                    ((uint32_t *)s_by)[row * 6 + q] = wy;
+                }
             }
         }
         const int idx00 = (R - it.cy) * ncols + (R - it.cx);
@@ -224,8 +252,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     };
 
     Item cur_it, nxt_it;
-    int item = blockIdx.x, buf = 0;
-    if (item >= n_items) return;
+    int item = blockIdx.x / CL, buf = 0;
+    const int item_stride = gridDim.x / CL;
+    if (item >= n_items) return;                         // (the same for every CTA of a cluster)
     decode_item(item, cur_it);
     prefetch(cur_it, 0);
     cp_async_wait_all();
@@ -233,8 +262,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     expand(cur_it);
     __syncthreads();
 
-    for (; item < n_items; item += gridDim.x) {
-        const int nxt = item + gridDim.x;
+    for (; item < n_items; item += item_stride) {
+        const int nxt = item + item_stride;
         const bool has_next = nxt < n_items;
         if (has_next) {
             decode_item(nxt, nxt_it);
@@ -259,7 +288,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
         }
 
-        if (bonus != 0 && warp == 0) {                   // 16x16 at MV (0,0) with its bonus
+        if (bonus != 0 && warp == 0 && crank == 0) {     // 16x16 at MV (0,0) with its bonus
             unsigned s = 0;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -282,9 +311,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         for (int b = 0; b < NL; b++) best[b] = 0xFFFFFFFFu;
 
         // second MB: the warp that starts at task 0 (one task more than the others) rotates
-        const int t0 = (warp + NM * NW - m) % NW;
+        const int t0 = (warp + NM * NW - m) % NW + (int)crank * NW;
+        constexpr int TS = NW * CL;                              // task stride
         unsigned e_next = t0 < n_main ? s_task[t0] : 0u;         // task descriptor, fetched one task ahead
-        for (int task = t0; task < n_tasks; task += NW) {
+        for (int task = t0; task < n_tasks; task += TS) {
             int ybase, xoff;
             if (task < n_main) {
                 ybase = e_next >> 8;
@@ -293,7 +323,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                 ybase = min(min((task - n_main) * G + res_g, nruns - 1) * K, ncols - K);
                 xoff = res_x;
             }
-            if (task + NW < n_main) e_next = s_task[task + NW];
+            if (task + TS < n_main) e_next = s_task[task + TS];
             const uint32_t *base = s_win + (ybase + 8 * half) * RS + xoff + wx;
 
             unsigned acc[K][8];
@@ -418,6 +448,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
       }
         cp_async_wait_all();
         __syncthreads();
+        if constexpr (CL > 1) {                          // partial minima of the other CTAs -> CTA 0
+            auto cluster = cooperative_groups::this_cluster();
+            cluster.sync();
+            if (crank != 0 && tid < JMME_NBLK) atomicMin(cluster.map_shared_rank(&s_best[tid], 0), s_best[tid]);
+            cluster.sync();
+        }
+        if (crank == 0)
         for (int i = tid; i < JMME_NBLK * cur_it.nmb; i += NW * 32) {
             const int m = i / JMME_NBLK, b = i - JMME_NBLK * m;
             const unsigned v = s_best[48 * m + b];
@@ -442,12 +479,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1>
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1, int CL = 1>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB>;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL>;
     // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
     static thread_local int c_dev = -1, c_occ = 0;
     static thread_local size_t c_bytes = 0;
@@ -464,6 +501,16 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
         c_dev = dev; c_bytes = bytes; c_occ = occ;
     }
     int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
+    if constexpr (CL > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(CL * min(n_items, max(num_sms * c_occ / CL, 1))));
+        cfg.blockDim = dim3(NW * 32);
+        cfg.dynamicSmemBytes = bytes; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, P);
+    }
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
@@ -479,6 +526,13 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st)
 {
     const bool pb = P.pred_policy == JMME_PRED_PER_BLOCK;
+    if (pb && P.mb_list && K == 6 && shape == 4) {       // a wavefront step: spread each MB over a cluster
+        const int n_items = P.n_list * P.num_refs;
+        const char *ec = getenv("JMME_CLUSTER");             // tuning knob: 1 = no clusters
+        const int cmax = ec ? atoi(ec) : 4;
+        if (cmax >= 4 && 4 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4>(P, num_sms, st);
+        if (cmax >= 2 && 2 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2>(P, num_sms, st);
+    }
 #define TB(KK, SH, NWW, MB, KG)                                                            \
     if (K == KK && shape == SH) {                                                          \
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
