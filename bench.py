@@ -39,6 +39,7 @@ WORKLOADS = {
     "720p_r32_41blk_int_1ref": (1280, 720, 32, 1, 0, 0xFE),             # config 2
     "1080p_r64_41blk_int_4ref": (1920, 1080, 64, 4, 0, 0xFE),           # config 4
     "cif_r16_16x16_int_1ref": (352, 288, 16, 1, 0, 0x02),               # config 1
+    "2160p_r64_41blk_qpel_4ref": (3840, 2160, 64, 4, 1, 0xFE),          # config 5
 }
 OPS_PER_CAND_41 = 171      # 64 VABSDIFF4.ACC + 25 partition adds + 41 x (pack + min), SURVEY §8(d)
 OPS_PER_CAND_16 = 66
@@ -398,6 +399,8 @@ def run_ours(args, rank, world, local_rank):
         ref_rows = min(max(ye - pad + 3, 1), h) - min(max(yb - pad - 3, 0), h - 1)
         cur_rows = max(min(16 * re, h) - min(16 * rb, h - 1), 1)
         h2d_bytes = (refs * ref_rows + cur_rows) * w
+        pad_ = (2 * R + 16 + 15) & ~15
+        plane_mb = (16 if subpel else 1) * (((w + 15) & ~15) + 2 * pad_) * (((h + 15) & ~15) + 2 * pad_) / 1e6
         line = {
             "metric": "ME macroblocks/sec", "value": n_mb / (ms_dev * 1e-3), "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
@@ -422,7 +425,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline_interp": {"bound": "hbm", "achieved": itp_gbs, "peak": hbm, "unit": "GB/s",
                                 "frac": (itp_gbs / hbm) if itp_gbs else None,
                                 "traffic": ncu_traffic("interp_kernel") if (world == 1 and args.workload.startswith("1080p_r32")) else None,
-                                "note": "the planes (41.5 MB) stay in the 126 MB L2 and are read from there by the sub-pel kernel",
+                                "note": (f"{plane_mb:.1f} MB of planes per reference are written; they stay in the 126 MB L2 for the "
+                                         "sub-pel kernel when they fit" if subpel else "integer plane only"),
                                 "kernel": "interp_kernel", "algorithmic_bytes_per_pixel": 17, "peak_source": hbm_src},
             "clocks": clocks,
         }

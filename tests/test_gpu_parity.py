@@ -271,6 +271,33 @@ def test_config3_1080p_subpel_properties(cuda, oracle):
     assert s[30 * 120:41 * 120].tobytes() == g[30 * 120:41 * 120].tobytes()
 
 
+@pytest.mark.parametrize("w,h,subpel,row", [(1920, 1080, 0, 33), (3840, 2160, 1, 134)])
+def test_config4_and_config5_r64_four_refs(cuda, oracle, w, h, subpel, row):
+    """BASELINE configs 4 (1080p, integer) and 5 (4K, quarter-pel): R = 64, 4 references, at full size on the
+    GPU; the oracle (all host threads) on one MB row; two stripes reproduce the whole-frame field."""
+    import ctypes
+    R, nref = 64, 4
+    cur, refs = synth.frame_pair(w, h, seed=4, search_range=R, num_refs=nref)
+    kw = dict(search_range=R, qp=28, subpel=subpel)
+    mb_w, mb_h = (w + 15) // 16, (h + 15) // 16
+    g, gp = run(cuda, cur, refs, None, True, **kw)
+    oracle.dll.jmme_oracle_set_threads.restype = ctypes.c_int
+    oracle.dll.jmme_oracle_set_threads(0)
+    try:
+        o, op = run(oracle, cur, refs, None, True, mb_row_begin=row, mb_row_end=row + 1, **kw)
+    finally:
+        oracle.dll.jmme_oracle_set_threads(1)
+    sl = slice(row * mb_w, (row + 1) * mb_w)
+    assert_same(gp[:, sl], op[:, sl], f"per-ref row {row}")
+    assert_same(g[sl], o[sl], f"best row {row}")
+    assert len(np.unique(g["ref_idx"])) > 1                           # more than one reference wins somewhere
+    half = mb_h // 2
+    s0 = run(cuda, cur, refs, mb_row_begin=0, mb_row_end=half, **kw)
+    s1 = run(cuda, cur, refs, mb_row_begin=half, mb_row_end=mb_h, **kw)
+    assert s0[:half * mb_w].tobytes() == g[:half * mb_w].tobytes()
+    assert s1[half * mb_w:].tobytes() == g[half * mb_w:].tobytes()
+
+
 def test_launch_counter_counts_kernels(cuda):
     cur, refs = synth.frame_pair(64, 48, seed=1, search_range=4)
     with cuda.context(width=64, height=48, search_range=4, subpel=1) as ctx:
