@@ -16,6 +16,9 @@
 #include <vector>
 
 #include "jmme_dev.cuh"
+#include "wave.cuh"
+
+const WaveTab &jmme_wave_tab();
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st);
 cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st);
@@ -64,6 +67,7 @@ struct jmme_ctx {
     // JMME_PRED_MEDIAN: the field committed so far, and the MBs of every wavefront step of the stripe
     int16_t *d_fmv;
     int8_t *d_fref;
+    WaveTab *d_wave_tab;                  // neighbour-source table of the predictor code (wave.cuh)
     int *d_wave;                          // MB indices, step after step
     int *wave_off;                        // [n_steps + 1] offsets into d_wave (host)
     int n_steps;
@@ -117,7 +121,7 @@ void free_device(jmme_ctx *c)
     for (int r = 0; r < JMME_MAX_REFS; r++) { cudaFree(c->d_planes[r]); cudaFree(c->d_raw_ref[r]); }
     cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
-    cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave);
+    cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave); cudaFree(c->d_wave_tab);
     free(c->wave_off);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     for (int i = 0; i < 4; i++)
@@ -241,6 +245,8 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
             CUC(cudaMalloc(&c->d_fref, 16 * n_mb));
             CUC(cudaMemset(c->d_fmv, 0, sizeof(int16_t) * 2 * 16 * n_mb));
             CUC(cudaMemset(c->d_fref, 0xFF, 16 * n_mb));
+            CUC(cudaMalloc(&c->d_wave_tab, sizeof(WaveTab)));
+            CUC(cudaMemcpy(c->d_wave_tab, &jmme_wave_tab(), sizeof(WaveTab), cudaMemcpyHostToDevice));
         }
     }
 #undef CUC
@@ -298,14 +304,22 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         // that step's list of MBs with the per-block predictors wave_step_kernel has just written
         // (the kernel that writes the records of a step — sub-pel or reference selection — commits its MBs)
         P.pred = c->d_pred; P.pred_policy = JMME_PRED_PER_BLOCK;
-        P.field_mv = c->d_fmv; P.field_ref = c->d_fref;
+        P.field_mv = c->d_fmv; P.field_ref = c->d_fref; P.slice_rows = c->p.slice_rows;
+        // the default integer kernel of a wavefront step (me_int_tb.cu, 12 warps, clusters) predicts in its own
+        // prologue; the other kernels read the predictors wave_step_kernel writes
+        const bool in_kernel = c->K == 0 && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
+                               c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !getenv("JMME_WAVE_STEP");
+        P.wave_tab = in_kernel ? c->d_wave_tab : nullptr;
         for (int t = 0; t < c->n_steps; t++) {
             P.mb_list = c->d_wave + c->wave_off[t]; P.n_list = c->wave_off[t + 1] - c->wave_off[t];
-            CU(c, jmme_launch_wave_step(P.mb_list, P.n_list, c->mb_w, c->mb_h, c->p.num_refs, c->p.slice_rows, c->d_fmv,
-                                        c->d_fref, c->d_pred, st));
+            if (!in_kernel) {
+                CU(c, jmme_launch_wave_step(P.mb_list, P.n_list, c->mb_w, c->mb_h, c->p.num_refs, c->p.slice_rows,
+                                            c->d_fmv, c->d_fref, c->d_pred, st));
+                c->launches++;
+            }
             if (c->p.search_mode == JMME_SEARCH_FULL) CU(c, jmme_launch_me_full(P, st));
             else CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
-            c->launches += 2;
+            c->launches++;
             if (c->p.subpel) { CU(c, jmme_launch_subpel(P, st)); c->launches++; }
             if (!P.fused_select) { CU(c, jmme_launch_select(P, st)); c->launches++; }
         }

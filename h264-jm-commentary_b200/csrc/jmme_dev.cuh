@@ -18,6 +18,8 @@ struct __align__(8) BlkRes {
     int32_t cost;                        // distortion + MV rate (no reference rate)
 };
 
+struct WaveTab;                          // wave.cuh
+
 // launch-constant parameters of a search
 struct SearchParams {
     const uint8_t *cur;                  // current luma, w16 x h16, stride cur_stride
@@ -46,6 +48,8 @@ struct SearchParams {
     int n_list;                          //           stripe's rows: one step of the in-frame median wavefront
     int16_t *field_mv;                   // non-null (in-frame median): the kernel that writes `out` also commits the
     int8_t *field_ref;                   //           MB to the 4x4-granular field [4 mb_h][4 mb_w]([2])
+    const WaveTab *wave_tab;             // non-null: the search kernel predicts its MB's 41 vectors itself from the
+    int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
 };
 
 // the MBs one launch works on: a stripe of MB rows, or an explicit list

@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 
 #include "jmme_dev.cuh"
+#include "wave.cuh"
 
 namespace {
 
@@ -79,9 +80,14 @@ struct Item {
 // CL > 1 (MB lists of the in-frame median wavefront, where a step has fewer MBs than the GPU has SMs): a
 // thread-block cluster of CL CTAs works on one item; every CTA stages the window, takes every CL-th group of
 // tasks, and the partial minima meet in CTA 0's shared memory (distributed shared memory atomicMin).
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL>
+// WP (with PER_BLOCK and an MB list): the kernel computes the 41 median predictors of its MB from the committed
+// field itself (wave.cuh) instead of reading P.pred, which it fills for the sub-pel kernel.
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL, bool WP>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
+    __shared__ WaveNb s_wnb[WP ? 10 : 1];
+    __shared__ int16_t s_wpred[WP ? 2 * JMME_NBLK : 2];
+    __shared__ uint8_t s_wsrc[WP ? JMME_NBLK : 1][4], s_wtp[WP ? JMME_NBLK : 1];
     extern __shared__ __align__(16) uint32_t smem[];
     const unsigned crank = CL > 1 ? cooperative_groups::this_cluster().block_rank() : 0u;
     const TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
@@ -147,7 +153,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     int res_x = 16 * nseg + (l16 - res_g * wr);
     if (res_g >= G) { res_g = 0; res_x = 16 * nseg; }    // idle lanes repeat lane 0 (idempotent)
 
-    auto decode_item = [&](int item, Item &it) {
+    if constexpr (WP) {                                  // (first used after the barriers inside decode_item)
+        if (tid < JMME_NBLK * 4) s_wsrc[tid >> 2][tid & 3] = P.wave_tab->src[tid >> 2][tid & 3];
+        if (tid < JMME_NBLK) s_wtp[tid] = P.wave_tab->tp[tid];
+    }
+    auto decode_item = [&](int item, Item &it) {           // called by all threads of the CTA together
         it.ref = item / n_it_stripe;
         const int idx = item - it.ref * n_it_stripe;
         if (P.mb_list) {
@@ -162,6 +172,30 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             it.mb = it.mby * P.mb_w + it.mbx;
         }
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
+        if constexpr (WP) {
+            const int ks = P.slice_rows ? P.slice_rows : P.mb_h;
+            if (tid < 10) {
+                int x, y;
+                wave_slot_xy(it.mbx, it.mby, tid, x, y);
+                s_wnb[tid] = wave_load_nb(P.field_mv, P.field_ref, 4 * P.mb_w, 4 * P.mb_h, 4 * ((it.mby / ks) * ks), x, y);
+            }
+            __syncthreads();
+            int px = 0, py = 0;
+            if (tid == 0) {
+                wave_predict_block(s_wnb, s_wsrc[0], s_wtp[0], it.ref, 0, 0, px, py);
+                s_wpred[0] = (int16_t)px; s_wpred[1] = (int16_t)py;
+            }
+            __syncthreads();
+            if (tid >= 1 && tid < JMME_NBLK) {
+                wave_predict_block(s_wnb, s_wsrc[tid], s_wtp[tid], it.ref, s_wpred[0], s_wpred[1], px, py);
+                s_wpred[2 * tid] = (int16_t)px; s_wpred[2 * tid + 1] = (int16_t)py;
+            }
+            __syncthreads();
+            if (crank == 0 && tid < JMME_NBLK)             // for the sub-pel kernel and jmme_get_predictors
+                *(uint32_t *)(P.pred + (((size_t)it.ref * n_mb + it.mb) * JMME_NBLK + tid) * 2) =
+                    (uint32_t)(uint16_t)s_wpred[2 * tid] | ((uint32_t)(uint16_t)s_wpred[2 * tid + 1] << 16);
+            pr = s_wpred;
+        }
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
         it.cx = d_clamp(p16x / 4, -R, R);
         it.cy = d_clamp(p16y / 4, -R, R);
@@ -208,7 +242,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             }
         }
         for (int i = tid; i < 48 * NM; i += NW * 32) s_best[i] = 0xFFFFFFFFu;
-        const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
+        const int16_t *pr = WP ? s_wpred : (P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr);
         if constexpr (!PER_BLOCK) {
             for (int i = tid; i < ncols; i += NW * 32) {
                 const int px = pr ? pr[0] : 0, py = pr ? pr[1] : 0;
@@ -479,12 +513,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1, int CL = 1>
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1, int CL = 1,
+          bool WP = false>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL>;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL, WP>;
     // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
     static thread_local int c_dev = -1, c_occ = 0;
     static thread_local size_t c_bytes = 0;
@@ -530,9 +565,15 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
         const int n_items = P.n_list * P.num_refs;
         const char *ec = getenv("JMME_CLUSTER");             // tuning knob: 1 = no clusters
         const int cmax = ec ? atoi(ec) : 4;
+        if (P.wave_tab) {                                    // predictors computed in the kernel
+            if (cmax >= 4 && 4 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4, true>(P, num_sms, st);
+            if (cmax >= 2 && 2 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2, true>(P, num_sms, st);
+            return launch_tb<6, 12, 1, true, 0, false, false, 1, 1, true>(P, num_sms, st);
+        }
         if (cmax >= 4 && 4 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4>(P, num_sms, st);
         if (cmax >= 2 && 2 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2>(P, num_sms, st);
     }
+    if (P.wave_tab) return cudaErrorInvalidValue;            // the host asks for in-kernel prediction only with this shape
 #define TB(KK, SH, NWW, MB, KG)                                                            \
     if (K == KK && shape == SH) {                                                          \
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \

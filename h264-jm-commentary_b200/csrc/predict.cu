@@ -10,34 +10,9 @@
 #include <cstdlib>
 
 #include "jmme_dev.cuh"
+#include "wave.cuh"
 
 namespace {
-
-struct Nb {          // one neighbour: vector, reference index (-1 = none), availability
-    int x, y, ref, avail;
-};
-
-__host__ __device__ inline int med3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
-
-// 8.4.1.3: directional rules of 16x8 / 8x16, else 8.4.1.3.1 median rules.  C is already D when C is missing.
-__host__ __device__ inline void mv_predict(int t, int part, int ref, Nb A, Nb B, Nb C, int &px, int &py)
-{
-    if (!A.avail || A.ref < 0) { A.x = A.y = 0; A.ref = -1; }
-    if (!B.avail || B.ref < 0) { B.x = B.y = 0; B.ref = -1; }
-    if (!C.avail || C.ref < 0) { C.x = C.y = 0; C.ref = -1; }
-    const Nb *dir = nullptr;
-    if (t == 2) dir = part == 0 ? &B : &A;
-    if (t == 3) dir = part == 0 ? &A : &C;
-    if (dir && dir->ref == ref) { px = dir->x; py = dir->y; return; }
-    if (!B.avail && !C.avail && A.avail) { B = A; C = A; }
-    const int hit = (A.ref == ref) + (B.ref == ref) + (C.ref == ref);
-    if (hit == 1) {
-        const Nb &m = A.ref == ref ? A : (B.ref == ref ? B : C);
-        px = m.x; py = m.y;
-    } else {
-        px = med3(A.x, B.x, C.x); py = med3(A.y, B.y, C.y);
-    }
-}
 
 // decoded-before test of field cell (x,y) for the block (t, x0, y0) of MB (mbx, mby)
 __host__ __device__ inline int cell_ready(int x, int y, int fw, int fh, int mbx, int mby, int t, int x0, int y0)
@@ -125,12 +100,6 @@ __global__ void commit_kernel(const jmme_mbresult *__restrict__ res, int mb_w, i
 //   2. the 16x16 predictor of every (reference, MB) of this step,
 //   3. the other 40 predictors, whose in-MB neighbours carry that 16x16 predictor.
 #define WAVE_CH 128                                       // MBs per chunk
-struct WaveNb { int16_t x, y; int16_t ref, avail; };
-// where the neighbours A, B, C, D of each block come from: 0..9 = slot of the MB's outer neighbour cells
-// (0..3 left column, 4..9 the row above from x-1), 10 = a partition of this MB decoded earlier (carries the
-// 16x16 predictor), 11 = a partition of this MB decoded later (unavailable); tp = blocktype | part << 3
-struct WaveTab { uint8_t src[JMME_NBLK][4]; uint8_t tp[JMME_NBLK]; };
-
 __global__ void __launch_bounds__(1024) wave_step_kernel(const int *__restrict__ cur, int n_cur, int mb_w, int mb_h,
                                                          int num_refs, int slice_rows, const int16_t *mv4,
                                                          const int8_t *ref4, int16_t *pred, const WaveTab tab)
@@ -149,30 +118,13 @@ __global__ void __launch_bounds__(1024) wave_step_kernel(const int *__restrict__
         __syncthreads();
         for (int i = tid; i < 10 * n; i += 1024) {         // slot 0..3: left column, 4..9: the row above from x-1
             const int j = i / 10, sl = i - 10 * j, mb = s_mb[j], mby = mb / mb_w, mbx = mb - mby * mb_w;
-            const int x = sl < 4 ? 4 * mbx - 1 : 4 * mbx - 1 + (sl - 4), y = sl < 4 ? 4 * mby + sl : 4 * mby - 1;
-            WaveNb v = {0, 0, -1, 0};                      // outside the picture or the slice: unavailable
-            if (x >= 0 && x < fw && y >= 4 * ((mby / k) * k) && y < fh) {
-                const size_t o = (size_t)y * fw + x;
-                const uint32_t w = *(const uint32_t *)(mv4 + 2 * o);
-                v.ref = ref4[o]; v.avail = 1;
-                if (v.ref >= 0) { v.x = (int16_t)(w & 0xFFFF); v.y = (int16_t)(w >> 16); }
-            }
-            s_nb[j][sl] = v;
+            int x, y;
+            wave_slot_xy(mbx, mby, sl, x, y);
+            s_nb[j][sl] = wave_load_nb(mv4, ref4, fw, fh, 4 * ((mby / k) * k), x, y);
         }
         __syncthreads();
         auto predict = [&](int j, int blk, int ref, int p16x, int p16y, int &px, int &py) {
-            Nb nb[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int src = s_src[blk][q];
-                const WaveNb v = s_nb[j][min(src, 9)];
-                if (src < 10) nb[q] = Nb{v.x, v.y, v.ref, v.avail};
-                else if (src == 10) nb[q] = Nb{p16x, p16y, ref, 1};
-                else nb[q] = Nb{0, 0, -1, 0};
-            }
-            if (!nb[2].avail) nb[2] = nb[3];
-            const int tp = s_tp[blk];
-            mv_predict(tp & 7, tp >> 3, ref, nb[0], nb[1], nb[2], px, py);
+            wave_predict_block(s_nb[j], s_src[blk], s_tp[blk], ref, p16x, p16y, px, py);
         };
         for (int i = tid; i < n * num_refs; i += 1024) {
             const int ref = i / n, j = i - ref * n;
@@ -217,11 +169,13 @@ WaveTab build_wave_tab()
             }
     return T;
 }
-const WaveTab &wave_tab()
+}  // namespace
+const WaveTab &jmme_wave_tab()
 {
     static const WaveTab T = build_wave_tab();                // thread-safe one-time initialisation
     return T;
 }
+namespace {
 
 }  // namespace
 
@@ -244,7 +198,7 @@ cudaError_t jmme_launch_commit(const jmme_mbresult *res, int mb_w, int mb_h, int
 cudaError_t jmme_launch_wave_step(const int *cur, int n_cur, int mb_w, int mb_h, int num_refs, int slice_rows,
                                   const int16_t *mv4, const int8_t *ref4, int16_t *pred, cudaStream_t st)
 {
-    wave_step_kernel<<<1, 1024, 0, st>>>(cur, n_cur, mb_w, mb_h, num_refs, slice_rows, mv4, ref4, pred, wave_tab());
+    wave_step_kernel<<<1, 1024, 0, st>>>(cur, n_cur, mb_w, mb_h, num_refs, slice_rows, mv4, ref4, pred, jmme_wave_tab());
     return cudaGetLastError();
 }
 
