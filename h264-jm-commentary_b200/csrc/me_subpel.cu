@@ -56,6 +56,9 @@ __device__ __forceinline__ int need_of_type(int t) { return (0x0415D7F0u >> (4 *
 // position the thread computes its cell's SATD (or SAD) from four unaligned 32-bit reference reads,
 // the cells of a block are summed with a masked XOR-shuffle butterfly, and every lane of the block
 // runs the same strict-< scan over the positions — no shared memory, no barriers, no atomics.
+// LAT (the MB lists of the in-frame median wavefront: a few dozen CTAs on the whole GPU, nothing to hide the
+// L2 latency behind): the plane words of all nine positions of a step are requested before the first is used.
+template <bool LAT>
 __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -113,6 +116,18 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
             bitx[j] = d_se_bits(ox + (j - 1) * step - px);
             bity[j] = d_se_bits(oy + (j - 1) * step - py);
         }
+        uint32_t raw[LAT ? 9 : 1][8];
+        if constexpr (LAT) {
+#pragma unroll
+            for (int pos = 0; pos < 9; pos++) {
+                if (pos < pos0 || !active) continue;
+                const int qx = ox + step * c_sp9h[pos][0], qy = oy + step * c_sp9h[pos][1];
+                const size_t off = psz * ((qy & 3) * 4 + (qx & 3)) + (size_t)(ry0 + (qy >> 2)) * P.pstride + (rx0 + (qx >> 2));
+                const uint32_t *rp = (const uint32_t *)(planes + (off & ~(size_t)3));
+#pragma unroll
+                for (int y = 0; y < 4; y++) { raw[pos][2 * y] = __ldg(rp + y * pw); raw[pos][2 * y + 1] = __ldg(rp + y * pw + 1); }
+            }
+        }
 #pragma unroll
         for (int pos = 0; pos < 9; pos++) {
             if (pos < pos0) continue;
@@ -125,7 +140,9 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
                 const int sh = (int)(off & 3) * 8;
                 uint32_t w[4];
 #pragma unroll
-                for (int y = 0; y < 4; y++) w[y] = __funnelshift_r(__ldg(rp + y * pw), __ldg(rp + y * pw + 1), sh);
+                for (int y = 0; y < 4; y++)
+                    w[y] = LAT ? __funnelshift_r(raw[pos][2 * y], raw[pos][2 * y + 1], sh)
+                               : __funnelshift_r(__ldg(rp + y * pw), __ldg(rp + y * pw + 1), sh);
                 if (P.use_hadamard) {
                     // 4x4 Hadamard on 16-bit lane pairs held as plain integers (hi*65536 + lo, |lane| <= 2040):
                     // ordinary 32-bit add/sub act on both lanes.  The last butterfly stage pairs the two
@@ -282,7 +299,8 @@ cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_ds
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
 {
     int n_items = d_n_units(P) * P.num_refs;
-    me_subpel_kernel<<<n_items, 128, 0, st>>>(P);
+    if (P.mb_list) me_subpel_kernel<true><<<n_items, 128, 0, st>>>(P);
+    else me_subpel_kernel<false><<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
 }
 
