@@ -40,6 +40,8 @@ struct jmme_ctx {
     jmme_params p;
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
     int device, num_sms, K;
+    int tune_group, tune_cluster;         // launch knobs of me_int_tb.cu (JMME_GROUP, JMME_CLUSTER)
+    bool force_wave_step;                 // JMME_WAVE_STEP: predictors always by wave_step_kernel
     cudaStream_t stream;
     cudaStream_t copy_stream;             // host->device copy of the current picture, overlaps the plane kernel
     cudaEvent_t ev_copy;
@@ -172,6 +174,12 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
     c->ncols = 2 * p->search_range + 1; c->ncand = c->ncols * c->ncols;
     const char *ek = getenv("JMME_VARIANT");      // tuning knob: 10*K + launch shape, see me_int.cu
     c->K = ek ? atoi(ek) : 0;                      // 0 = choose by search range
+    {
+        const char *eg = getenv("JMME_GROUP"), *ec = getenv("JMME_CLUSTER");
+        c->tune_group = eg ? atoi(eg) : 2;         // MBs per work item of the zero-predictor kernel
+        c->tune_cluster = ec ? atoi(ec) : 4;       // largest cluster of a wavefront step (1 = none)
+        c->force_wave_step = getenv("JMME_WAVE_STEP") != nullptr;
+    }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -273,6 +281,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
     P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy;
     P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
+    P.tune_group = c->tune_group; P.tune_cluster = c->tune_cluster;
 }
 
 // enqueue the whole search on `st`; nothing is synchronised here
@@ -308,7 +317,7 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         // the default integer kernel of a wavefront step (me_int_tb.cu, 12 warps, clusters) predicts in its own
         // prologue; the other kernels read the predictors wave_step_kernel writes
         const bool in_kernel = c->K == 0 && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
-                               c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !getenv("JMME_WAVE_STEP");
+                               c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !c->force_wave_step;
         P.wave_tab = in_kernel ? c->d_wave_tab : nullptr;
         for (int t = 0; t < c->n_steps; t++) {
             P.mb_list = c->d_wave + c->wave_off[t]; P.n_list = c->wave_off[t + 1] - c->wave_off[t];

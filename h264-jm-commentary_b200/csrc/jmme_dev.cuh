@@ -50,6 +50,7 @@ struct SearchParams {
     int8_t *field_ref;                   //           MB to the 4x4-granular field [4 mb_h][4 mb_w]([2])
     const WaveTab *wave_tab;             // non-null: the search kernel predicts its MB's 41 vectors itself from the
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
+    int tune_group, tune_cluster;        // host-side launch knobs (JMME_GROUP, JMME_CLUSTER), read once per context
 };
 
 // the MBs one launch works on: a stripe of MB rows, or an explicit list

@@ -563,8 +563,7 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
     const bool pb = P.pred_policy == JMME_PRED_PER_BLOCK;
     if (pb && P.mb_list && K == 6 && shape == 4) {       // a wavefront step: spread each MB over a cluster
         const int n_items = P.n_list * P.num_refs;
-        const char *ec = getenv("JMME_CLUSTER");             // tuning knob: 1 = no clusters
-        const int cmax = ec ? atoi(ec) : 4;
+        const int cmax = P.tune_cluster;                     // 1 = no clusters
         if (P.wave_tab) {                                    // predictors computed in the kernel
             if (cmax >= 4 && 4 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4, true>(P, num_sms, st);
             if (cmax >= 2 && 2 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2, true>(P, num_sms, st);
@@ -578,8 +577,7 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
     if (K == KK && shape == SH) {                                                          \
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
         if (P.R == 32 && !P.pred && !KG) {                                                                     \
-            const char *g_ = getenv("JMME_GROUP");                  /* MBs per item: tuning knob, default 2 */ \
-            const int grp = g_ ? atoi(g_) : 2;                                                                  \
+            const int grp = P.tune_group;                           /* MBs per item, default 2 */             \
             if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4>(P, num_sms, st);            \
             if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2>(P, num_sms, st);             \
             return launch_tb<KK, NWW, MB, false, 78, false, true, 1>(P, num_sms, st);                           \

@@ -502,3 +502,24 @@ def test_yuv_sequence_pass_matches_oracle(cuda, oracle, tmp_path):
         assert len(a) == len(b) == 3
         for (n, ga, _), (_, gb, _) in zip(a, b):
             assert_same(ga, gb, f"policy {policy} frame {n}")
+
+
+def test_get_predictors_states_mirror_the_oracle(cuda, oracle):
+    w, h, R = 32, 32, 4
+    cur, refs = synth.frame_pair(w, h, seed=1, search_range=R)
+    for lib in (cuda, oracle):
+        with lib.context(width=w, height=h, search_range=R) as ctx:
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.get_predictors()
+            assert e.value.code == abi.ERR_STATE
+        with lib.context(width=w, height=h, search_range=R, pred_policy=abi.PRED_MEDIAN) as ctx:
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.get_predictors()
+            assert e.value.code == abi.ERR_STATE
+            ctx.set_reference(0, refs[0])
+            ctx.search_frame(cur)
+            assert ctx.get_predictors().shape == (1, 4, 41, 2)
+        for bad in (dict(pred_policy=abi.PRED_MEDIAN, slice_rows=-1), dict(pred_policy=4)):
+            with pytest.raises(abi.JmmeError) as e:
+                lib.context(width=w, height=h, search_range=R, **bad)
+            assert e.value.code == abi.ERR_PARAM

@@ -156,3 +156,24 @@ def test_in_frame_median_lowers_cost_against_zero_predictors(oracle):
         c1.set_reference(0, refs[0])
         res1 = c1.search_frame(cur)
     assert res1["cost"][:, 0].astype(np.int64).sum() < res0["cost"][:, 0].astype(np.int64).sum()
+
+
+def test_get_predictors_states(oracle):
+    w, h, R = 32, 32, 4
+    cur, refs = synth.frame_pair(w, h, seed=1, search_range=R)
+    with oracle.context(width=w, height=h, search_range=R) as ctx:          # not a median context
+        with pytest.raises(abi.JmmeError) as e:
+            ctx.get_predictors()
+        assert e.value.code == abi.ERR_STATE
+    with oracle.context(width=w, height=h, search_range=R, pred_policy=abi.PRED_MEDIAN) as ctx:
+        with pytest.raises(abi.JmmeError) as e:                              # nothing searched yet
+            ctx.get_predictors()
+        assert e.value.code == abi.ERR_STATE
+        ctx.set_reference(0, refs[0])
+        ctx.search_frame(cur, pred=np.zeros(3, np.int16))                    # `pred` is ignored by this policy
+        assert ctx.get_predictors().shape == (1, 4, 41, 2)
+    with pytest.raises(abi.JmmeError) as e:
+        oracle.context(width=w, height=h, search_range=R, pred_policy=abi.PRED_MEDIAN, slice_rows=-1)
+    assert e.value.code == abi.ERR_PARAM
+    with pytest.raises(abi.JmmeError):
+        oracle.context(width=w, height=h, search_range=R, pred_policy=4)
