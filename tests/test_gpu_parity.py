@@ -523,3 +523,24 @@ def test_get_predictors_states_mirror_the_oracle(cuda, oracle):
             with pytest.raises(abi.JmmeError) as e:
                 lib.context(width=w, height=h, search_range=R, **bad)
             assert e.value.code == abi.ERR_PARAM
+
+
+def test_randomised_in_frame_median(cuda, oracle):
+    """Seeded random sweep of the in-frame median policy: sizes, ranges, lambda, masks, slices, references,
+    search modes and sub-pel options; predictors and records against the oracle."""
+    rng = np.random.default_rng(77)
+    for case in range(20):
+        w, h = int(rng.integers(17, 150)), int(rng.integers(17, 120))
+        R = int(rng.choice([1, 2, 3, 5, 8, 13, 16, 21, 32, 40]))
+        refs_n = int(rng.integers(1, 4))
+        kw = dict(search_range=R, qp=int(rng.integers(0, 52)), rdopt=int(rng.integers(0, 2)), subpel=int(rng.integers(0, 2)),
+                  use_hadamard=int(rng.integers(0, 2)), satd_round=int(rng.integers(0, 2)),
+                  blocktype_mask=int(rng.choice([0xFE, 0x02, 0x92, 0x0E, 0xF0, 0x80, 0xFE])),
+                  search_mode=int(rng.integers(0, 2)), slice_rows=int(rng.choice([0, 0, 1, 2, 3])))
+        kind = str(rng.choice(["texture", "noise", "gradient"]))
+        cur, refs = synth.frame_pair(w, h, seed=100 + case, search_range=R, kind=kind, num_refs=refs_n)
+        g, gp, gpred = run_median(cuda, cur, refs, **kw)
+        o, op, opred = run_median(oracle, cur, refs, **kw)
+        assert np.array_equal(gpred, opred), f"case {case} predictors {w}x{h} {kw}"
+        assert_same(gp, op, f"case {case} per-ref {w}x{h} {kw}")
+        assert_same(g, o, f"case {case} best {w}x{h} {kw}")
