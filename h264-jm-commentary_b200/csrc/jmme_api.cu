@@ -42,6 +42,7 @@ struct jmme_ctx {
     int device, num_sms, K;
     int tune_group, tune_cluster;         // launch knobs of me_int_tb.cu (JMME_GROUP, JMME_CLUSTER)
     bool force_wave_step;                 // JMME_WAVE_STEP: predictors always by wave_step_kernel
+    bool use_pdl;                         // JMME_PDL=0: no programmatic dependent launch in the wavefront
     cudaStream_t stream;
     cudaStream_t copy_stream;             // host->device copy of the current picture, overlaps the plane kernel
     cudaEvent_t ev_copy;
@@ -179,6 +180,8 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         c->tune_group = eg ? atoi(eg) : 2;         // MBs per work item of the zero-predictor kernel
         c->tune_cluster = ec ? atoi(ec) : 4;       // largest cluster of a wavefront step (1 = none)
         c->force_wave_step = getenv("JMME_WAVE_STEP") != nullptr;
+        const char *epd = getenv("JMME_PDL");
+        c->use_pdl = !epd || atoi(epd) != 0;
     }
 
     int ndev = 0;
@@ -319,6 +322,9 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         const bool in_kernel = c->K == 0 && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
                                c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !c->force_wave_step;
         P.wave_tab = in_kernel ? c->d_wave_tab : nullptr;
+        // search and sub-pel kernels of consecutive steps overlap their launch latency and constant-only
+        // prologues (programmatic dependent launch); JMME_PDL=0 turns it off
+        P.pdl = in_kernel && c->use_pdl;
         for (int t = 0; t < c->n_steps; t++) {
             P.mb_list = c->d_wave + c->wave_off[t]; P.n_list = c->wave_off[t + 1] - c->wave_off[t];
             if (!in_kernel) {

@@ -51,7 +51,14 @@ struct SearchParams {
     const WaveTab *wave_tab;             // non-null: the search kernel predicts its MB's 41 vectors itself from the
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
     int tune_group, tune_cluster;        // host-side launch knobs (JMME_GROUP, JMME_CLUSTER), read once per context
+    int pdl;                             // wavefront steps: launch with programmatic stream serialization
 };
+
+// Programmatic dependent launch (sm_90+).  pdl_trigger: the next kernel of the stream may start its prologue;
+// pdl_wait: results of the previous kernel are complete and visible from here on.  Both are no-ops for a
+// kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // the MBs one launch works on: a stripe of MB rows, or an explicit list
 __host__ __device__ inline int d_n_units(const SearchParams &P)

@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     if constexpr (WP) {                                  // (first used after the barriers inside decode_item)
         if (tid < JMME_NBLK * 4) s_wsrc[tid >> 2][tid & 3] = P.wave_tab->src[tid >> 2][tid & 3];
         if (tid < JMME_NBLK) s_wtp[tid] = P.wave_tab->tp[tid];
+        // Everything above reads launch constants only and may overlap the tail of the previous step's
+        // sub-pel kernel; the committed field is read below.  (No early trigger here: sub-pel CTAs launched
+        // while this kernel holds most SMs would crowd onto the few free ones — measured slower.)
+        pdl_wait();
     }
     auto decode_item = [&](int item, Item &it) {           // called by all threads of the CTA together
         it.ref = item / n_it_stripe;
@@ -536,14 +540,23 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
         c_dev = dev; c_bytes = bytes; c_occ = occ;
     }
     int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
-    if constexpr (CL > 1) {
+    if (CL > 1 || P.pdl) {
         cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        if (CL > 1) {
+            at[na].id = cudaLaunchAttributeClusterDimension;
+            at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            na++;
+        }
+        if (P.pdl) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            na++;
+        }
         cfg.gridDim = dim3((unsigned)(CL * min(n_items, max(num_sms * c_occ / CL, 1))));
         cfg.blockDim = dim3(NW * 32);
-        cfg.dynamicSmemBytes = bytes; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        cfg.dynamicSmemBytes = bytes; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = na;
         return cudaLaunchKernelEx(&cfg, kern, P);
     }
     int grid = min(n_items, num_sms * c_occ);

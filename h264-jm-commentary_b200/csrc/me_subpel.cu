@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
             cb[y] = __byte_perm(cw[y], 0, 0x4341);
         }
     }
+    if constexpr (LAT) {                                 // (the loads above read the current picture only)
+        pdl_trigger();
+        pdl_wait();
+    }
     int mvx, mvy, mn, px = 0, py = 0;
     {
         const BlkRes r = res[b];
@@ -299,6 +303,15 @@ cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_ds
 cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
 {
     int n_items = d_n_units(P) * P.num_refs;
+    if (P.mb_list && P.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3((unsigned)n_items); cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, me_subpel_kernel<true>, P);
+    }
     if (P.mb_list) me_subpel_kernel<true><<<n_items, 128, 0, st>>>(P);
     else me_subpel_kernel<false><<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
