@@ -58,10 +58,14 @@ __device__ __forceinline__ int need_of_type(int t) { return (0x0415D7F0u >> (4 *
 // runs the same strict-< scan over the positions — no shared memory, no barriers, no atomics.
 // LAT (the MB lists of the in-frame median wavefront: a few dozen CTAs on the whole GPU, nothing to hide the
 // L2 latency behind): the plane words of all nine positions of a step are requested before the first is used.
-template <bool LAT>
-__global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
+// NG = 3 (with LAT): three groups of 128 threads share the positions of a step (3 + 3 + 3, then 2 + 3 + 3),
+// each runs the strict-< scan over its own and the groups' (cost, position) minima meet in shared memory:
+// the lowest position among equal costs wins, as in the sequential scan.  A third of the dependent chain.
+template <bool LAT, int NG>
+__global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams P)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ long long s_pk[NG > 1 ? 2 : 1][NG > 1 ? NG : 1][NG > 1 ? JMME_NBLK : 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & 3, grp = tid >> 7;
     const int t = 2 * warp + (lane >> 4) + 1;            // blocktype 1..7 (8 = idle)
     const int cell = lane & 15, cx4 = cell & 3, cy4 = cell >> 2;
     const int n_mb_stripe = d_n_units(P);
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
         if constexpr (LAT) {
 #pragma unroll
             for (int pos = 0; pos < 9; pos++) {
-                if (pos < pos0 || !active) continue;
+                if (pos < pos0 || !active || (NG > 1 && pos / 3 != grp)) continue;
                 const int qx = ox + step * c_sp9h[pos][0], qy = oy + step * c_sp9h[pos][1];
                 const size_t off = psz * ((qy & 3) * 4 + (qx & 3)) + (size_t)(ry0 + (qy >> 2)) * P.pstride + (rx0 + (qx >> 2));
                 const uint32_t *rp = (const uint32_t *)(planes + (off & ~(size_t)3));
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
         }
 #pragma unroll
         for (int pos = 0; pos < 9; pos++) {
-            if (pos < pos0) continue;
+            if (pos < pos0 || (NG > 1 && pos / 3 != grp)) continue;  // (uniform per warp)
             const int sx = c_sp9h[pos][0], sy = c_sp9h[pos][1];     // compile-time after unrolling
             const int qx = ox + step * sx, qy = oy + step * sy;
             int v = 0;
@@ -190,11 +194,24 @@ __global__ void __launch_bounds__(128) me_subpel_kernel(const SearchParams P)
             if (qx == 0 && qy == 0) cst -= bonus;
             if (cst < mn) { mn = cst; best = pos; }
         }
+        if constexpr (NG > 1) {                          // (cost, position) minimum over the groups
+            const bool own = t <= 7 && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2);
+            if (active && own) s_pk[step - 1][grp][b] = ((long long)mn << 4) | best;
+            __syncthreads();
+            if (active) {
+                long long pk = s_pk[step - 1][0][b];
+#pragma unroll
+                for (int g = 1; g < NG; g++) pk = min(pk, s_pk[step - 1][g][b]);
+                mn = (int)(pk >> 4); best = (int)(pk & 15);
+            } else {
+                best = 0;
+            }
+        }
         mvx = ox + step * c_sp9[best][0];
         mvy = oy + step * c_sp9[best][1];
     }
     // the lane that owns the block's top-left cell publishes the result
-    const bool owner = t <= 7 && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2);
+    const bool owner = grp == 0 && t <= 7 && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2);
     if (active && owner) {
         BlkRes r;
         r.mvx = (int16_t)mvx; r.mvy = (int16_t)mvy; r.cost = mn;
@@ -310,10 +327,11 @@ cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.gridDim = dim3((unsigned)n_items); cfg.blockDim = dim3(128);
         cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, me_subpel_kernel<true>, P);
+        cfg.blockDim = dim3(384);
+        return cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3>, P);
     }
-    if (P.mb_list) me_subpel_kernel<true><<<n_items, 128, 0, st>>>(P);
-    else me_subpel_kernel<false><<<n_items, 128, 0, st>>>(P);
+    if (P.mb_list) me_subpel_kernel<true, 3><<<n_items, 384, 0, st>>>(P);
+    else me_subpel_kernel<false, 1><<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
 }
 
