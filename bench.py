@@ -46,6 +46,16 @@ OPS_PER_CAND_16 = 66
 QP = 28
 
 
+def policy_kw(args):
+    """Context parameters of --pred-policy (3 = JMME_PRED_MEDIAN)."""
+    return dict(pred_policy=3, slice_rows=args.slice_rows) if args.pred_policy == "median" else {}
+
+
+def slice_unit(args, mb_h):
+    """Stripes and CPU samples are whole slices under the median policy."""
+    return (args.slice_rows or mb_h) if args.pred_policy == "median" else 1
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -139,16 +149,18 @@ def run_reference(args, rank, world):
     rows = 1
     times = []
     with orc.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
-                     mb_row_begin=mb_h // 2, mb_row_end=mb_h // 2 + 1) as c:
+                     mb_row_begin=mb_h // 2, mb_row_end=mb_h // 2 + 1) as c:      # calibration: zero predictors
         t0 = time.perf_counter()
         for i, r in enumerate(ref_l):
             c.set_reference(i, r)
         c.search_frame(cur)
         t_row = time.perf_counter() - t0
+    unit = slice_unit(args, mb_h)
     rows = int(max(1, min(mb_h, args.ref_seconds / max(t_row, 1e-6))))
-    b = max(0, (mb_h - rows) // 2)
+    rows = min(mb_h, -(-rows // unit) * unit)
+    b = max(0, (mb_h - rows) // 2) // unit * unit
     with orc.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
-                     mb_row_begin=b, mb_row_end=b + rows) as c:
+                     mb_row_begin=b, mb_row_end=min(mb_h, b + rows), **policy_kw(args)) as c:
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             for i, r in enumerate(ref_l):
@@ -165,7 +177,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "ME macroblocks/sec", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "qp": QP, "note": "CPU restatement (oracle/) of the JM path; the mounted "
+        "config": {"workload": args.workload, "qp": QP, "pred_policy": args.pred_policy, "note": "CPU restatement (oracle/) of the JM path; the mounted "
                    "reference holds no sources, so this is a port, not JM itself"},
         "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,17 +196,21 @@ def cpu_baseline(args):
     cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
     mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
 
+    unit = slice_unit(args, mb_h)
+
     def go(rows):
-        b = max(0, (mb_h - rows) // 2)
+        rows = min(mb_h, -(-rows // unit) * unit)
+        b = max(0, (mb_h - rows) // 2) // unit * unit
         with orc.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
-                         mb_row_begin=b, mb_row_end=b + rows) as c:
+                         mb_row_begin=b, mb_row_end=min(mb_h, b + rows), **policy_kw(args)) as c:
             t0 = time.perf_counter()
             for i, r in enumerate(ref_l):
                 c.set_reference(i, r)
             c.search_frame(cur)
             return time.perf_counter() - t0
-    t1 = go(1)
+    t1 = go(1) / min(mb_h, unit)
     rows = int(max(1, min(mb_h, args.cpu_seconds / max(t1, 1e-6))))
+    rows = min(mb_h, -(-rows // unit) * unit)
     t = go(rows)
     n = rows * mb_w
     return {"value": n / t, "unit": "MB/s", "cores": 1, "kind": "port",
@@ -232,14 +248,14 @@ def run_ours(args, rank, world, local_rank):
     w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
     mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
     n_mb = mb_h * mb_w
-    rb, re = stripe_of(rank, world, mb_h)
+    rb, re = stripe_of(rank, world, mb_h, slice_unit(args, mb_h))
     cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
     d_cur = torch.from_numpy(cur).cuda()
     d_refs = [torch.from_numpy(r).cuda() for r in ref_l]
     if re <= rb:
         raise SystemExit(f"rank {rank}: empty stripe — {mb_h} MB rows cannot feed {world} ranks of {-(-mb_h // world)} rows")
     ds = DeviceSearch(lib, width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
-                      mb_row_begin=rb, mb_row_end=re)
+                      mb_row_begin=rb, mb_row_end=re, **policy_kw(args))
     ds.ctx.set_profiling(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     rec = abi.MBRESULT_DTYPE.itemsize
@@ -248,13 +264,13 @@ def run_ours(args, rank, world, local_rank):
     gather, gather_mode = None, "none (1 rank)"
     if world > 1 and args.gather == "p2p":
         try:
-            gather = PeerPushGather(mb_w, mb_h, "cuda")
+            gather = PeerPushGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
             gather_mode = "peer stores into symmetric memory (jmme_push_stripe_dev) + symm-mem barrier"
         except Exception as e:  # noqa: BLE001
             sys.stderr.write(f"rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL\n")
             gather = None
     if gather is None:
-        gather = StripeGather(mb_w, mb_h, "cuda")
+        gather = StripeGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
         if world > 1:
             gather_mode = "in-place NCCL all_gather_into_tensor"
     p2p = isinstance(gather, PeerPushGather)
@@ -276,6 +292,10 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
+    barrier()
+    l_a = ds.launch_count()
+    step_device()
+    launches_per_step = ds.launch_count() - l_a          # kernels of one step (a graph replay launches the same ones)
     barrier()
     # per-kernel device times (CUDA events around each kernel, eager launches) for the roofline
     ktimes = []
@@ -322,8 +342,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = ds.launch_count() - l0
     if graph is not None:                 # replays launch the captured kernels without passing the counter
-        launches = args.steps * (len(d_refs) + (1 if w % 16 else 0) + 1 + (1 if subpel else 0) +
-                                 (0 if (subpel and refs == 1) else 1) + (1 if p2p else 0))
+        launches = args.steps * launches_per_step
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_dev = float(np.mean(step_ms))
 
@@ -332,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
     h_refs = [torch.from_numpy(r).pin_memory() for r in ref_l]
     h_out = torch.zeros(n_mb * rec, dtype=torch.uint8).pin_memory()
     hctx = lib.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
-                       mb_row_begin=rb, mb_row_end=re, device_ids=[local_rank], async_reference=1)
+                       mb_row_begin=rb, mb_row_end=re, device_ids=[local_rank], async_reference=1, **policy_kw(args))
     pu8 = C.POINTER(C.c_uint8)
 
     def step_host():
@@ -365,7 +384,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         step_device()
         torch.cuda.synchronize()
-        chk = StripeGather(mb_w, mb_h, "cuda")
+        chk = StripeGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
         chk.field[rb * mb_w:re * mb_w].copy_(gather.field[rb * mb_w:re * mb_w])
         ref_field = chk.gather()
         torch.cuda.synchronize()
@@ -387,6 +406,9 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src, _ = int_peak_live()
         hbm, hbm_src = measured_peaks()
         alg_ops = (re - rb) * mb_w * refs * ncand * ops_cand          # this rank's launch
+        wave = args.pred_policy == "median"
+        if wave:            # no per-kernel brackets inside the wavefront: the whole search (all steps) is the "launch"
+            k_int = max(ms_dev - k_itp * refs, 1e-9)
         achieved = alg_ops / (k_int * 1e-3) * 1e-12
         pad = hctx.pad
         rows_itp = ((16 * mb_h + 2 * pad) if re == mb_h else min(16 * mb_h + 2 * pad, pad + 16 * re + 2 * R + 4)) - \
@@ -407,7 +429,10 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "frame": f"{w}x{h}", "mbs": n_mb, "search_range": R, "refs": refs,
                        "blocks": 41 if mask != 0x02 else 1, "subpel": "half+quarter SATD" if subpel else "none",
-                       "qp": QP, "pred_policy": "zero", "partition": f"{world} MB-row stripes",
+                       "qp": QP, "pred_policy": ("zero" if not wave else
+                                                 f"in-frame median (JMME_PRED_MEDIAN), slice_rows={args.slice_rows}: "
+                                                 f"a 2:1 wavefront of {mb_w + 2 * (min(args.slice_rows or mb_h, re - rb) - 1)} steps"),
+                       "partition": f"{world} MB-row stripes",
                        "l2": "256 MB buffer written between timed steps (outside the event pair)",
                        "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
                        "launch": launch_mode, "gather": gather_mode},
@@ -419,8 +444,9 @@ def run_ours(args, rank, world, local_rank):
                           "share_me_int": k_int / max(k_itp + k_int + k_sub + k_sel, 1e-9)},
             "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
                          "frac": achieved / peak,
-                         "traffic": ncu_traffic("me_int_tb_kernel") if (world == 1 and args.workload.startswith("1080p_r32")) else None,
-                         "kernel": "me_int_tb_kernel" if (R <= 32 and mask != 0x02) else "me_int_kernel",
+                         "traffic": ncu_traffic("me_int_tb_kernel") if (world == 1 and not wave and args.workload.startswith("1080p_r32")) else None,
+                         "kernel": ("wavefront step chain (me_int_tb_kernel clusters + me_subpel_kernel), whole search" if wave
+                                    else "me_int_tb_kernel" if (R <= 32 and mask != 0x02) else "me_int_kernel"),
                          "algorithmic_ops_per_candidate": ops_cand, "peak_source": peak_src},
             "roofline_interp": {"bound": "hbm", "achieved": itp_gbs, "peak": hbm, "unit": "GB/s",
                                 "frac": (itp_gbs / hbm) if itp_gbs else None,
@@ -455,6 +481,9 @@ def main():
     ap.add_argument("--workload", default="1080p_r32_41blk_qpel_1ref", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=4.0, help="CPU work per step of --impl reference")
+    ap.add_argument("--pred-policy", default="zero", choices=["zero", "median"],
+                    help="median: JMME_PRED_MEDIAN, the predictor loop closed inside the frame (a wavefront)")
+    ap.add_argument("--slice-rows", type=int, default=1, help="MB rows per slice of --pred-policy median (0 = whole frame)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the MV field is gathered")

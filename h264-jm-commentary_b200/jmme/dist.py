@@ -31,11 +31,12 @@ class StripeGather:
     indexing puts its stripe into its own chunk), then `gather()` runs ONE in-place all-gather — the
     only collective of the path."""
 
-    def __init__(self, mb_w: int, mb_h: int, device, group=None):
+    def __init__(self, mb_w: int, mb_h: int, device, group=None, unit: int = 1):
+        """unit: stripes are whole groups of `unit` MB rows (see stripe_of)."""
         self.mb_w, self.mb_h, self.group = mb_w, mb_h, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.rows = -(-mb_h // self.world)
+        self.rows = -(-(-(-mb_h // unit)) // self.world) * unit
         self.chunk = self.rows * mb_w
         self.field = torch.zeros((self.world * self.chunk, REC), dtype=torch.uint8, device=device)
 
@@ -55,11 +56,11 @@ class PeerPushGather:
     pushes its stripe into all peers' fields with one kernel of NVLink peer stores
     (jmme_push_stripe_dev) and a symmetric-memory barrier orders the reads."""
 
-    def __init__(self, mb_w: int, mb_h: int, device, group=None):
+    def __init__(self, mb_w: int, mb_h: int, device, group=None, unit: int = 1):
         import torch.distributed._symmetric_memory as symm_mem
         self.mb_w, self.mb_h = mb_w, mb_h
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.rows = -(-mb_h // self.world)
+        self.rows = -(-(-(-mb_h // unit)) // self.world) * unit
         n = self.world * self.rows * mb_w
         self.field = symm_mem.empty((n, REC), dtype=torch.uint8, device=device)
         self.field.zero_()
