@@ -11,7 +11,7 @@ GOLD = sorted((pathlib.Path(__file__).parent / "golden").glob("*.npz"))
 def replay(lib, g):
     w, h, R, refs, pol = (int(v) for v in g["params"])
     kw = {str(k): int(v) for k, v in zip(g["kw_keys"], g["kw_vals"])}
-    pred = g["pred"] if pol else None
+    pred = g["pred"] if pol in (1, 2) else None            # 0: zero predictors, 3: in-frame median
     with lib.context(width=w, height=h, search_range=R, num_refs=refs, pred_policy=pol, **kw) as ctx:
         for i in range(refs):
             ctx.set_reference(i, g["refs"][i])
@@ -34,7 +34,7 @@ def check(lib, path):
 
 
 def test_golden_files_exist():
-    assert len(GOLD) >= 5
+    assert len(GOLD) >= 7
 
 
 @pytest.mark.parametrize("path", GOLD, ids=lambda p: p.stem)

@@ -23,6 +23,9 @@ CASES = {
     "all41_rdopt_r12_2refs_qpel_perblock": (64, 64, 12, 2, dict(qp=33, rdopt=1, subpel=1, satd_round=1), 2),
     "all41_r32_int_permb": (64, 48, 32, 1, dict(qp=24), 1),
     "odd_size_sad_subpel": (52, 38, 6, 1, dict(qp=30, subpel=1, use_hadamard=0), 0),
+    # in-frame median (JMME_PRED_MEDIAN): slices of two MB rows with two references; one slice = the frame
+    "median_slices2_2refs_qpel": (80, 96, 8, 2, dict(qp=30, subpel=1, slice_rows=2), 3),
+    "median_wholeframe_rdopt_r6": (96, 64, 6, 1, dict(qp=34, rdopt=1, subpel=1, slice_rows=0), 3),
 }
 
 
@@ -31,11 +34,13 @@ def main():
     out = ROOT / "tests" / "golden"
     out.mkdir(parents=True, exist_ok=True)
     for name, (w, h, R, refs, kw, pol) in CASES.items():
+        if (out / f"{name}.npz").exists() and "--all" not in sys.argv:
+            continue                                      # frozen: existing fixtures are only rewritten with --all
         cur, ref_l = synth.frame_pair(w, h, seed=11, search_range=R, num_refs=refs)
         with orc.context(width=w, height=h, search_range=R, num_refs=refs, pred_policy=pol, **kw) as ctx:
             n_mb = ctx.mb_w * ctx.mb_h
             pred = None
-            if pol:
+            if pol in (1, 2):
                 pred = synth.random_pred(refs, n_mb, 1 if pol == 1 else 41, seed=5, max_qpel=4 * R + 20)
             for i, r in enumerate(ref_l):
                 ctx.set_reference(i, r)
