@@ -40,7 +40,7 @@ struct jmme_ctx {
     jmme_params p;
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
     int device, num_sms, K;
-    int tune_group, tune_cluster;         // launch knobs of me_int_tb.cu (JMME_GROUP, JMME_CLUSTER)
+    int tune_group, tune_cluster, tune_lin;   // launch knobs of me_int_tb.cu (JMME_GROUP, JMME_CLUSTER, JMME_LIN)
     bool force_wave_step;                 // JMME_WAVE_STEP: predictors always by wave_step_kernel
     bool use_pdl;                         // JMME_PDL=0: no programmatic dependent launch in the wavefront
     cudaStream_t stream;
@@ -179,6 +179,8 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         const char *eg = getenv("JMME_GROUP"), *ec = getenv("JMME_CLUSTER");
         c->tune_group = eg ? atoi(eg) : 2;         // MBs per work item of the zero-predictor kernel
         c->tune_cluster = ec ? atoi(ec) : 4;       // largest cluster of a wavefront step (1 = none)
+        const char *el = getenv("JMME_LIN");
+        c->tune_lin = el ? atoi(el) : 1;           // integer lambda: linear per-block rate instead of the table
         c->force_wave_step = getenv("JMME_WAVE_STEP") != nullptr;
         const char *epd = getenv("JMME_PDL");
         c->use_pdl = !epd || atoi(epd) != 0;
@@ -284,7 +286,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
     P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy;
     P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
-    P.tune_group = c->tune_group; P.tune_cluster = c->tune_cluster;
+    P.tune_group = c->tune_group; P.tune_cluster = c->tune_cluster; P.tune_lin = c->tune_lin;
 }
 
 // enqueue the whole search on `st`; nothing is synchronised here

@@ -51,6 +51,7 @@ struct SearchParams {
     const WaveTab *wave_tab;             // non-null: the search kernel predicts its MB's 41 vectors itself from the
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
     int tune_group, tune_cluster;        // host-side launch knobs (JMME_GROUP, JMME_CLUSTER), read once per context
+    int tune_lin;                        // JMME_LIN=0: per-block rate always from the table
     int pdl;                             // wavefront steps: launch with programmatic stream serialization
 };
 

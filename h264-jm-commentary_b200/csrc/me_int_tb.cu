@@ -82,7 +82,9 @@ struct Item {
 // tasks, and the partial minima meet in CTA 0's shared memory (distributed shared memory atomicMin).
 // WP (with PER_BLOCK and an MB list): the kernel computes the 41 median predictors of its MB from the committed
 // field itself (wave.cuh) instead of reading P.pred, which it fills for the sub-pel kernel.
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL, bool WP>
+// LIN (with PER_BLOCK): lambda is an integer (every !rdopt lambda is), so the rate is linear in the bits and
+// one IMAD replaces the table look-up: rate << 15 = (4 bits) * (lambda * 8192).
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL, bool WP, bool LIN>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     __shared__ WaveNb s_wnb[WP ? 10 : 1];
@@ -421,10 +423,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                     uint32_t sw[6];
 #pragma unroll
                     for (int i = 0; i < 3; i++) { const uint2 v = q[i]; sw[2 * i] = v.x + bxw[2 * i]; sw[2 * i + 1] = v.y + bxw[2 * i + 1]; }
+                    if constexpr (LIN) {
+                        const unsigned lam8k = (unsigned)(P.lambda_factor >> 16) << 13;
+                        const unsigned keyb = key + (bias << JMME_KEY_BITS);
 #pragma unroll
-                    for (int b = 0; b < NL; b++) {
-                        const unsigned off = __byte_perm(sw[b >> 2], 0, 0x4440 | (b & 3));
-                        pk[b] = (o[b] << JMME_KEY_BITS) + *(const uint32_t *)((const char *)s_T + off) + key;
+                        for (int b = 0; b < NL; b++) {
+                            const unsigned b4 = __byte_perm(sw[b >> 2], 0, 0x4440 | (b & 3));
+                            pk[b] = (o[b] << JMME_KEY_BITS) + (b4 * lam8k + keyb);
+                        }
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < NL; b++) {
+                            const unsigned off = __byte_perm(sw[b >> 2], 0, 0x4440 | (b & 3));
+                            pk[b] = (o[b] << JMME_KEY_BITS) + *(const uint32_t *)((const char *)s_T + off) + key;
+                        }
                     }
                 }
             };
@@ -518,12 +530,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 }
 
 template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1, int CL = 1,
-          bool WP = false>
+          bool WP = false, bool LIN = false>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL, WP>;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL, WP, LIN>;
     // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
     static thread_local int c_dev = -1, c_occ = 0;
     static thread_local size_t c_bytes = 0;
@@ -574,12 +586,21 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st)
 {
     const bool pb = P.pred_policy == JMME_PRED_PER_BLOCK;
+    const bool lin = (P.lambda_factor & 0xFFFF) == 0 && P.tune_lin;       // integer lambda: linear rate (LIN)
+    if (pb && lin && !P.mb_list && K == 6 && shape == 8)                  // the default per-block kernel
+        return launch_tb<6, 4, 3, true, 0, false, false, 1, 1, false, true>(P, num_sms, st);
     if (pb && P.mb_list && K == 6 && shape == 4) {       // a wavefront step: spread each MB over a cluster
         const int n_items = P.n_list * P.num_refs;
         const int cmax = P.tune_cluster;                     // 1 = no clusters
         if (P.wave_tab) {                                    // predictors computed in the kernel
-            if (cmax >= 4 && 4 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4, true>(P, num_sms, st);
-            if (cmax >= 2 && 2 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2, true>(P, num_sms, st);
+            const int cl = (cmax >= 4 && 4 * n_items <= num_sms) ? 4 : ((cmax >= 2 && 2 * n_items <= num_sms) ? 2 : 1);
+            if (lin) {
+                if (cl == 4) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4, true, true>(P, num_sms, st);
+                if (cl == 2) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2, true, true>(P, num_sms, st);
+                return launch_tb<6, 12, 1, true, 0, false, false, 1, 1, true, true>(P, num_sms, st);
+            }
+            if (cl == 4) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4, true>(P, num_sms, st);
+            if (cl == 2) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2, true>(P, num_sms, st);
             return launch_tb<6, 12, 1, true, 0, false, false, 1, 1, true>(P, num_sms, st);
         }
         if (cmax >= 4 && 4 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 4>(P, num_sms, st);
