@@ -544,3 +544,28 @@ def test_randomised_in_frame_median(cuda, oracle):
         assert np.array_equal(gpred, opred), f"case {case} predictors {w}x{h} {kw}"
         assert_same(gp, op, f"case {case} per-ref {w}x{h} {kw}")
         assert_same(g, o, f"case {case} best {w}x{h} {kw}")
+
+
+@pytest.mark.parametrize("force_wave_step", [0, 1])
+def test_in_frame_median_tall_frame(cuda, oracle, force_wave_step):
+    """135 MB rows (4K height): more MBs per wavefront step than one chunk of wave_step_kernel (128) and more
+    (MB, ref) items than SMs; both predictor paths (search-kernel prologue / wave_step_kernel)."""
+    import ctypes
+    w, h, R = 256, 2160, 6
+    cur, refs = synth.frame_pair(w, h, seed=8, search_range=R, num_refs=2)
+    kw = dict(search_range=R, slice_rows=1, qp=30, subpel=1)
+    if force_wave_step:
+        os.environ["JMME_WAVE_STEP"] = "1"
+    try:
+        g, gp, gpred = run_median(cuda, cur, refs, **kw)
+    finally:
+        os.environ.pop("JMME_WAVE_STEP", None)
+    oracle.dll.jmme_oracle_set_threads.restype = ctypes.c_int
+    oracle.dll.jmme_oracle_set_threads(0)
+    try:
+        o, op, opred = run_median(oracle, cur, refs, **kw)
+    finally:
+        oracle.dll.jmme_oracle_set_threads(1)
+    assert np.array_equal(gpred, opred)
+    assert_same(gp, op, "per-ref")
+    assert_same(g, o, "best")
