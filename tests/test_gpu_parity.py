@@ -569,3 +569,36 @@ def test_in_frame_median_tall_frame(cuda, oracle, force_wave_step):
     assert np.array_equal(gpred, opred)
     assert_same(gp, op, "per-ref")
     assert_same(g, o, "best")
+
+
+@pytest.mark.parametrize("h,stripe", [(208, None), (400, (4, 21)), (1080, None)])
+def test_async_reference_with_the_pipelined_host_path(cuda, oracle, h, stripe):
+    """async_reference = 1 (jmme_set_reference returns before its copy and plane kernel have run) together with
+    the host path that searches the stripe in parts on separate streams."""
+    w, R = (1920, 32) if h == 1080 else (128, 8)
+    cur, refs = synth.frame_pair(w, h, seed=h, search_range=R, num_refs=1 if h == 1080 else 2)
+    kw = dict(search_range=R, qp=28, subpel=1)
+    if stripe:
+        kw.update(mb_row_begin=stripe[0], mb_row_end=stripe[1])
+    g, gp = run(cuda, cur, refs, None, True, async_reference=1, **kw)
+    if h == 1080:                                            # oracle on a few rows around the part boundaries
+        for rb in (21, 44, 66):
+            o, op = run(oracle, cur, refs, None, True, **dict(kw, mb_row_begin=rb, mb_row_end=rb + 2))
+            sl = slice(rb * 120, (rb + 2) * 120)
+            assert_same(g[sl], o[sl], f"rows {rb}..")
+        g0 = run(cuda, cur, refs, **kw)
+        assert g0.tobytes() == g.tobytes()
+        return
+    o, op = run(oracle, cur, refs, None, True, **kw)
+    mb_w = w // 16
+    sl = slice((stripe[0] if stripe else 0) * mb_w, (stripe[1] if stripe else (h + 15) // 16) * mb_w)
+    assert_same(gp[:, sl], op[:, sl], "per-ref")
+    assert_same(g[sl], o[sl], "best")
+    # planes of an asynchronous build are the planes of a synchronous one
+    with cuda.context(width=w, height=h, num_refs=2, async_reference=1, **kw) as a, \
+            cuda.context(width=w, height=h, num_refs=2, **kw) as b:
+        a.set_reference(1, refs[1]); b.set_reference(1, refs[1])
+        for fx, fy in ((0, 0), (2, 1), (3, 3)):
+            pa, pb = a.get_subimage(1, fx, fy), b.get_subimage(1, fx, fy)
+            if stripe is None:
+                assert np.array_equal(pa, pb)
