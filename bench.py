@@ -262,13 +262,20 @@ def run_ours(args, rank, world, local_rank):
     # the search writes its stripe straight into the field; N > 1: gathered either by peer stores over
     # NVLink into symmetric memory (default) or by one in-place NCCL all-gather (--gather nccl)
     gather, gather_mode = None, "none (1 rank)"
-    if world > 1 and args.gather == "p2p":
+    fused = False
+    if world > 1 and args.gather in ("p2p", "p2p-push"):
         try:
             gather = PeerPushGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
-            gather_mode = "peer stores into symmetric memory (jmme_push_stripe_dev) + symm-mem barrier"
+            fused = args.gather == "p2p"
+            if fused:
+                gather.attach(ds)
+                gather_mode = ("peer stores into symmetric memory from the kernels that write the records "
+                               "(jmme_set_peer_fields_dev) + symm-mem barriers")
+            else:
+                gather_mode = "peer stores into symmetric memory (jmme_push_stripe_dev) + symm-mem barrier"
         except Exception as e:  # noqa: BLE001
             sys.stderr.write(f"rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL\n")
-            gather = None
+            gather, fused = None, False
     if gather is None:
         gather = StripeGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
         if world > 1:
@@ -278,6 +285,10 @@ def run_ours(args, rank, world, local_rank):
     def step_device():
         for i, r in enumerate(d_refs):
             ds.set_reference(i, r)
+        if fused:
+            gather.pre()
+            ds.search(d_cur, out=gather.field)
+            return gather.post()
         ds.search(d_cur, out=gather.field)
         return gather.gather(ds) if p2p else gather.gather()
 
@@ -486,7 +497,9 @@ def main():
     ap.add_argument("--slice-rows", type=int, default=1, help="MB rows per slice of --pred-policy median (0 = whole frame)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: how the MV field is gathered")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-push", "nccl"],
+                    help="N > 1: how the MV field is gathered: peer stores from the search kernels (p2p), from a "
+                         "separate push kernel (p2p-push), or one NCCL all-gather")
     ap.add_argument("--watchdog", type=float, default=300.0, help="hard exit after this many seconds")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

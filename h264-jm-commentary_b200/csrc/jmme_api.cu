@@ -75,6 +75,8 @@ struct jmme_ctx {
     int *wave_off;                        // [n_steps + 1] offsets into d_wave (host)
     int n_steps;
     bool searched;                        // d_pred holds the predictors of a finished median search
+    void *peer_fields[JMME_MAX_GPUS];     // jmme_set_peer_fields_dev
+    int n_peer_fields;
 };
 
 namespace {
@@ -311,6 +313,8 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
     P.cur_h = cur_h;
     P.fused_select = c->p.num_refs == 1 && c->p.subpel;
+    for (int i = 0; i < c->n_peer_fields; i++)           // fused gather (jmme_set_peer_fields_dev)
+        if (c->peer_fields[i] && c->peer_fields[i] != (void *)d_out) P.peer_out[P.n_peer_out++] = (jmme_mbresult *)c->peer_fields[i];
     if (rb >= 0) { P.mb_row_begin = rb; P.mb_row_end = re; }
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
     if (c->p.pred_policy == JMME_PRED_MEDIAN) {
@@ -643,6 +647,15 @@ int jmme_predict_frame(jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int1
     }
     cudaFree(d_mv); cudaFree(d_ref);
     return rc;
+}
+
+int jmme_set_peer_fields_dev(jmme_ctx *c, void *const *d_peers, int n_peers)
+{
+    if (!c || n_peers < 0 || n_peers > JMME_MAX_GPUS || (n_peers && !d_peers)) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    for (int i = 0; i < n_peers; i++) c->peer_fields[i] = d_peers[i];
+    c->n_peer_fields = n_peers;
+    return JMME_OK;
 }
 
 int jmme_push_stripe_dev(jmme_ctx *c, const void *d_local, void *const *d_peers, int n_peers, void *stream)

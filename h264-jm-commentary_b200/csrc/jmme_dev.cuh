@@ -53,7 +53,22 @@ struct SearchParams {
     int tune_group, tune_cluster;        // host-side launch knobs (JMME_GROUP, JMME_CLUSTER), read once per context
     int tune_lin;                        // JMME_LIN=0: per-block rate always from the table
     int pdl;                             // wavefront steps: launch with programmatic stream serialization
+    jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
+    int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
 };
+
+// copy the records of n_rec MBs (mb_of(i) = frame MB index of record i) from P.out to every peer buffer; the
+// calling threads wrote those records themselves and have passed a barrier since
+template <class F>
+__device__ __forceinline__ void push_records(const SearchParams &P, int n_rec, F mb_of, int tid, int nthreads)
+{
+    constexpr int RW = sizeof(jmme_mbresult) / 4;
+    for (int i = tid; i < n_rec * RW * P.n_peer_out; i += nthreads) {
+        const int p = i / (n_rec * RW), j = i - p * (n_rec * RW), rec = j / RW, w = j - rec * RW;
+        const int mb = mb_of(rec);
+        if (mb >= 0) ((uint32_t *)(P.peer_out[p] + mb))[w] = __ldcg((const uint32_t *)(P.out + mb) + w);
+    }
+}
 
 // Programmatic dependent launch (sm_90+).  pdl_trigger: the next kernel of the stream may start its prologue;
 // pdl_wait: results of the previous kernel are complete and visible from here on.  Both are no-ops for a

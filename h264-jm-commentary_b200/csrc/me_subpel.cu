@@ -235,6 +235,10 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
             o->reserved[tid] = 0;
             if (q) q->reserved[tid] = 0;
         }
+        if (P.n_peer_out) {                                // fused gather: this MB's record to the peers (uniform branch)
+            __syncthreads();
+            push_records(P, 1, [&](int) { return mb; }, tid, 128 * NG);
+        }
         if (P.field_mv) {                                  // in-frame median: commit this MB (uniform branch)
             __shared__ int32_t s_cost[JMME_NBLK];
             __shared__ uint32_t s_mv[JMME_NBLK];
@@ -283,6 +287,11 @@ __global__ void select_ref_kernel(const SearchParams P)
         if (on && tot < bc) { bc = tot; br = r; bx = v.mvx; by = v.mvy; }
     }
     if (work) { o->mv[b][0] = (int16_t)bx; o->mv[b][1] = (int16_t)by; o->cost[b] = bc; o->ref_idx[b] = (int8_t)br; }
+    if (P.n_peer_out) {                                    // fused gather: the records of this CTA's MBs to the peers
+        __syncthreads();
+        push_records(P, 4, [&](int k) { const int m = 4 * (int)blockIdx.x + k; return m < n_mb_stripe ? d_unit_mb(P, m) : -1; },
+                     (int)threadIdx.x, 192);
+    }
     if (P.field_mv) {                                      // in-frame median: commit the MBs of this CTA (uniform branch)
         if (work) {
             s_cost[g][b] = bc; s_ref[g][b] = (int8_t)br;

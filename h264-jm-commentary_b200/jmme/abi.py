@@ -53,7 +53,8 @@ EXPORTS = [
     "jmme_default_params", "jmme_create", "jmme_destroy", "jmme_strerror", "jmme_last_error", "jmme_backend",
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
     "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
-    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_push_stripe_dev", "jmme_launch_count",
+    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev",
+    "jmme_launch_count",
     "jmme_set_profiling",
     "jmme_get_kernel_times", "jmme_InitMotionSearchModule", "jmme_SetMotionVectorPredictor",
     "jmme_commit_field", "jmme_predict_frame",
@@ -100,6 +101,7 @@ class Lib:
             "jmme_set_reference_dev": (i32, [vp, i32, vp, i32, vp]),
             "jmme_search_frame_dev": (i32, [vp, vp, i32, vp, vp, vp, vp]),
             "jmme_push_stripe_dev": (i32, [vp, vp, C.POINTER(vp), i32, vp]),
+            "jmme_set_peer_fields_dev": (i32, [vp, C.POINTER(vp), i32]),
             "jmme_launch_count": (C.c_longlong, [vp]),
             "jmme_set_profiling": (i32, [vp, i32]),
             "jmme_get_kernel_times": (i32, [vp, C.POINTER(C.c_float)]),

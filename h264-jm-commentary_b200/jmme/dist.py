@@ -76,3 +76,16 @@ class PeerPushGather:
         search.push_stripe(self.field, self.peer_ptrs)
         self.hdl.barrier(channel=1)            # every stripe has landed everywhere
         return self.frame()
+
+    # ---- fused variant: the search kernels store their records into the peers' fields themselves ----------
+    def attach(self, search):
+        """Every later search of `search` (with out=self.field) also writes its records into all peers' fields
+        (jmme_set_peer_fields_dev): no push kernel; bracket the search with pre() and post()."""
+        search.set_peer_fields(self.peer_ptrs)
+
+    def pre(self):
+        self.hdl.barrier(channel=0)            # peers are done reading the previous field
+
+    def post(self) -> torch.Tensor:
+        self.hdl.barrier(channel=1)            # every stripe has landed everywhere
+        return self.frame()

@@ -55,6 +55,11 @@ class DeviceSearch:
         self.lib.check(self.lib.dll.jmme_push_stripe_dev(self.ctx.handle, C.c_void_p(field.data_ptr()), arr, len(peer_ptrs),
                                                          self._stream()), self.ctx.handle)
 
+    def set_peer_fields(self, peer_ptrs):
+        """Every later search also stores its records into the peer buffers (fused gather); [] turns it off."""
+        arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        self.lib.check(self.lib.dll.jmme_set_peer_fields_dev(self.ctx.handle, arr, len(peer_ptrs)), self.ctx.handle)
+
     def stripe_rows(self):
         return self.ctx.params.mb_row_begin, (self.ctx.params.mb_row_end or self.ctx.mb_h)
 

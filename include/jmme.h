@@ -161,6 +161,13 @@ int jmme_search_frame_dev(jmme_ctx *ctx, const void *d_cur_luma, int stride, con
  * caller provides the cross-rank barrier before the field is read. */
 int jmme_push_stripe_dev(jmme_ctx *ctx, const void *d_field_local, void *const *d_field_peers, int n_peers,
                          void *stream);
+/* The same gather fused into the search: after this call every record jmme_search_frame_dev writes into its
+ * output buffer is also stored, by the kernel that produces it, into the same offsets of the peer buffers
+ * (d_field_peers as in jmme_push_stripe_dev; entries that are NULL or equal to the output buffer of the search
+ * are skipped; n_peers = 0 turns the fusion off).  No push kernel is needed then.  The caller provides the
+ * cross-rank barriers: before the search (the peers have finished reading the previous field) and after it
+ * (every stripe has landed everywhere). */
+int jmme_set_peer_fields_dev(jmme_ctx *ctx, void *const *d_field_peers, int n_peers);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 long long jmme_launch_count(const jmme_ctx *ctx);
 /* Per-kernel device times.  jmme_set_profiling(ctx,1) makes every later set_reference / search

@@ -337,6 +337,11 @@ int jmme_mb_width(const jmme_ctx *c) { return c ? c->mb_w : 0; }
 int jmme_mb_height(const jmme_ctx *c) { return c ? c->mb_h : 0; }
 int jmme_pad(const jmme_ctx *c) { return c ? c->pad : 0; }
 int jmme_lambda_factor_of(const jmme_ctx *c) { return c ? c->lambda_factor : 0; }
+int jmme_set_peer_fields_dev(jmme_ctx *c, void *const *p, int n)
+{
+    (void)p; (void)n;
+    return set_err(c, JMME_ERR_UNSUPPORTED, "device pointers: CUDA library only");
+}
 int jmme_push_stripe_dev(jmme_ctx *c, const void *l, void *const *p, int n, void *st)
 { (void)l; (void)p; (void)n; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
 long long jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }

@@ -602,3 +602,36 @@ def test_async_reference_with_the_pipelined_host_path(cuda, oracle, h, stripe):
             pa, pb = a.get_subimage(1, fx, fy), b.get_subimage(1, fx, fy)
             if stripe is None:
                 assert np.array_equal(pa, pb)
+
+
+@pytest.mark.parametrize("nref,subpel,median", [(1, 1, False), (2, 1, False), (1, 0, False), (1, 1, True), (2, 1, True)])
+def test_fused_peer_stores(cuda, nref, subpel, median):
+    """jmme_set_peer_fields_dev: the kernel that writes a record also stores it into the peer buffers (here two more
+    buffers on the same device stand in for the peers; NULL and the output buffer itself are skipped)."""
+    import torch
+    from jmme.torch_api import DeviceSearch
+    w, h, R = 96, 112, 8
+    cur, refs = synth.frame_pair(w, h, seed=2, search_range=R, num_refs=nref)
+    kw = dict(width=w, height=h, search_range=R, num_refs=nref, subpel=subpel, qp=30, mb_row_begin=2, mb_row_end=6)
+    if median:
+        kw.update(pred_policy=abi.PRED_MEDIAN, slice_rows=2)
+    ds = DeviceSearch(cuda, **kw)
+    for i, r in enumerate(refs):
+        ds.set_reference(i, torch.from_numpy(r).cuda())
+    peers = [torch.full_like(ds.out, 0xAB) for _ in range(2)]
+    ds.set_peer_fields([peers[0].data_ptr(), 0, ds.out.data_ptr(), peers[1].data_ptr()])
+    out = ds.search(torch.from_numpy(cur).cuda())
+    torch.cuda.synchronize()
+    mb_w = w // 16
+    lo, hi = 2 * mb_w, 6 * mb_w
+    for p in peers:
+        assert torch.equal(p[lo:hi], out[lo:hi])                       # the stripe landed in every peer
+        assert bool((p[:lo] == 0xAB).all()) and bool((p[hi:] == 0xAB).all())   # and nothing else was touched
+    n0 = ds.launch_count()
+    ds.set_peer_fields([])                                             # off again: peers keep their contents
+    for p in peers:
+        p.fill_(0xCD)
+    ds.search(torch.from_numpy(cur).cuda())
+    torch.cuda.synchronize()
+    assert all(bool((p == 0xCD).all()) for p in peers) and ds.launch_count() > n0
+    ds.close()
