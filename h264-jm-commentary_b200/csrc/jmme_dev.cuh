@@ -63,10 +63,11 @@ template <class F>
 __device__ __forceinline__ void push_records(const SearchParams &P, int n_rec, F mb_of, int tid, int nthreads)
 {
     constexpr int RW = sizeof(jmme_mbresult) / 4;
-    for (int i = tid; i < n_rec * RW * P.n_peer_out; i += nthreads) {
-        const int p = i / (n_rec * RW), j = i - p * (n_rec * RW), rec = j / RW, w = j - rec * RW;
-        const int mb = mb_of(rec);
-        if (mb >= 0) ((uint32_t *)(P.peer_out[p] + mb))[w] = __ldcg((const uint32_t *)(P.out + mb) + w);
+    for (int j = tid; j < n_rec * RW; j += nthreads) {     // one word per thread: read once, store to every peer
+        const int rec = j / RW, w = j - rec * RW, mb = mb_of(rec);
+        if (mb < 0) continue;
+        const uint32_t v = __ldcg((const uint32_t *)(P.out + mb) + w);
+        for (int p = 0; p < P.n_peer_out; p++) ((uint32_t *)(P.peer_out[p] + mb))[w] = v;
     }
 }
 
