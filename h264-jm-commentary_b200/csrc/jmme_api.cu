@@ -319,8 +319,8 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
     if (c->p.pred_policy == JMME_PRED_MEDIAN) {
         // predict -> search -> commit, one wavefront step after the other; the kernels of a step work on
-        // that step's list of MBs with the per-block predictors wave_step_kernel has just written
-        // (the kernel that writes the records of a step — sub-pel or reference selection — commits its MBs)
+        // that step's list of MBs; the kernel that writes the records of a step — sub-pel or
+        // reference selection — commits its MBs to the field
         P.pred = c->d_pred; P.pred_policy = JMME_PRED_PER_BLOCK;
         P.field_mv = c->d_fmv; P.field_ref = c->d_fref; P.slice_rows = c->p.slice_rows;
         // the default integer kernel of a wavefront step (me_int_tb.cu, 12 warps, clusters) predicts in its own
