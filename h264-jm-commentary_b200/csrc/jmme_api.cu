@@ -77,6 +77,7 @@ struct jmme_ctx {
     bool searched;                        // d_pred holds the predictors of a finished median search
     void *peer_fields[JMME_MAX_GPUS];     // jmme_set_peer_fields_dev
     int n_peer_fields;
+    bool dev_call;                        // inside jmme_search_frame_dev (the fused gather applies to that call only)
 };
 
 namespace {
@@ -313,7 +314,7 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
     P.cur_h = cur_h;
     P.fused_select = c->p.num_refs == 1 && c->p.subpel;
-    for (int i = 0; i < c->n_peer_fields; i++)           // fused gather (jmme_set_peer_fields_dev)
+    for (int i = 0; c->dev_call && i < c->n_peer_fields; i++)          // fused gather (jmme_set_peer_fields_dev)
         if (c->peer_fields[i] && c->peer_fields[i] != (void *)d_out) P.peer_out[P.n_peer_out++] = (jmme_mbresult *)c->peer_fields[i];
     if (rb >= 0) { P.mb_row_begin = rb; P.mb_row_end = re; }
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
@@ -591,8 +592,11 @@ int jmme_search_frame_dev(jmme_ctx *c, const void *d_cur, int stride, const void
     if (c->p.pred_policy != JMME_PRED_ZERO && c->p.pred_policy != JMME_PRED_MEDIAN && !d_pred)
         return fail(c, JMME_ERR_PARAM, "pred required");
     CU(c, cudaSetDevice(c->device));
-    return enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
-                          (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
+    c->dev_call = true;
+    const int rc = enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
+                                  (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
+    c->dev_call = false;
+    return rc;
 }
 
 int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_t *ref4, uint8_t *mode)
