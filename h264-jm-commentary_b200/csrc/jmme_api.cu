@@ -465,7 +465,7 @@ int jmme_mb_width(const jmme_ctx *c) { return c ? c->mb_w : 0; }
 int jmme_mb_height(const jmme_ctx *c) { return c ? c->mb_h : 0; }
 int jmme_pad(const jmme_ctx *c) { return c ? c->pad : 0; }
 int jmme_lambda_factor_of(const jmme_ctx *c) { return c ? c->lambda_factor : 0; }
-long long jmme_launch_count(const jmme_ctx *c)
+int64_t jmme_launch_count(const jmme_ctx *c)
 {
     if (!c) return 0;
     long long n = c->launches;

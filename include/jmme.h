@@ -169,7 +169,7 @@ int jmme_push_stripe_dev(jmme_ctx *ctx, const void *d_field_local, void *const *
  * (every stripe has landed everywhere). */
 int jmme_set_peer_fields_dev(jmme_ctx *ctx, void *const *d_field_peers, int n_peers);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
-long long jmme_launch_count(const jmme_ctx *ctx);
+int64_t jmme_launch_count(const jmme_ctx *ctx);
 /* Per-kernel device times.  jmme_set_profiling(ctx,1) makes every later set_reference / search
  * bracket its kernels with CUDA events on the launching stream; jmme_get_kernel_times waits for
  * the last bracket and returns milliseconds of the most recent

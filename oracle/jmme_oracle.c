@@ -344,7 +344,7 @@ int jmme_set_peer_fields_dev(jmme_ctx *c, void *const *p, int n)
 }
 int jmme_push_stripe_dev(jmme_ctx *c, const void *l, void *const *p, int n, void *st)
 { (void)l; (void)p; (void)n; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
-long long jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }
+int64_t jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }
 int jmme_set_profiling(jmme_ctx *c, int e) { (void)e; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no kernels"); }
 int jmme_get_kernel_times(jmme_ctx *c, float ms[4]) { (void)ms; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no kernels"); }
 
