@@ -44,6 +44,21 @@ WORKLOADS = {
 OPS_PER_CAND_41 = 171      # 64 VABSDIFF4.ACC + 25 partition adds + 41 x (pack + min), SURVEY §8(d)
 OPS_PER_CAND_16 = 66
 QP = 28
+SEEDS = (1, 2, 3)          # synthetic frame pairs; timed step s uses seed SEEDS[s % 3]
+
+
+def config_of(args, rows=None):
+    """The `config` object of the JSON line — identical in both arms (`--impl ours` / `--impl reference`); how
+    an arm ran it (partition, launch mode, gather) goes into its own `run` object."""
+    w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
+    mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
+    wave = args.pred_policy == "median"
+    k = args.slice_rows or mb_h
+    return {"workload": args.workload, "frame": f"{w}x{h}", "mbs": mb_h * mb_w, "search_range": R, "refs": refs,
+            "blocks": 41 if mask != 0x02 else 1, "subpel": "half+quarter SATD" if subpel else "none", "qp": QP,
+            "seeds": SEEDS,
+            "pred_policy": ("zero" if not wave else f"in-frame median (JMME_PRED_MEDIAN), slice_rows={args.slice_rows}: "
+                            f"slices of {k} MB rows, each a 2:1 wavefront")}
 
 
 def policy_kw(args):
@@ -93,8 +108,14 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        pw = []
+        for r in self.rows:
+            try:
+                pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                pass
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
 def measured_peaks():
@@ -105,28 +126,72 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_table():
+    """Per-kernel counters of the committed `ncu --set full` capture of this command (profiles/r02_ncu.json, made
+    by tools/ncu_key.py from the .ncu-rep; keys me_int / me_subpel / interp), else the round-1 file."""
+    for name in ("r02_ncu.json", "r01_traffic.json"):
+        f = ROOT / "profiles" / name
+        if f.exists():
+            d = json.loads(f.read_text())
+            if name.startswith("r01"):
+                d = {"me_int": d.get("me_int_tb_kernel"), "interp": d.get("interp_kernel"), "me_subpel": d.get("me_subpel_kernel")}
+            return d
+    return {}
+
+
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    """DRAM bytes per launch (read + write) of `kernel` from the committed ncu capture, or None."""
     try:
-        d = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())[kernel]
+        d = _ncu_table()[kernel]
         return d["dram_bytes_read"] + d["dram_bytes_write"]
     except Exception:  # noqa: BLE001
         return None
 
 
-def int_peak_live():
-    """Integer issue peak measured on this GPU right now by csrc/microbench (same instruction mix as the
-    search kernel: 64 VABSDIFF4 + 66 IMAD + 41 VIMNMX per candidate)."""
+def ncu_metric(kernel, key):
+    try:
+        return _ncu_table()[kernel][key]
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def int_peaks(dev):
+    """The two ceilings of the integer search:
+    mix_peak       the search kernel's own per-candidate instruction mix (64 VABSDIFF4 + 66 IMAD + 41 min) issued
+                   from registers by every SM, measured on this GPU right now by csrc/microbench as a SUSTAINED rate
+                   (back-to-back launches until the clock has settled under the power cap, like bf16_tflops_sustained)
+    issue_ceiling  SMs x 4 schedulers x 32 lanes x clocks.max.sm: what no kernel can exceed"""
+    import torch
+    prop = torch.cuda.get_device_properties(dev)
+    max_mhz = 1965.0
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits", "-i", str(dev)],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        max_mhz = float(out.splitlines()[0])
+    except Exception:  # noqa: BLE001
+        pass
+    res = {"issue_ceiling": prop.multi_processor_count * 128 * max_mhz * 1e6 * 1e-12}
     exe = ROOT / "h264-jm-commentary_b200" / "csrc" / "microbench"
     try:
-        d = json.loads(subprocess.run([str(exe)], capture_output=True, text=True, timeout=120, check=True).stdout)
-        return d["mix_64sad_66imad_41min"]["tera_lane_ops_per_s"], "measured live (csrc/microbench, kernel-mix issue rate)", d
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[dev]
+                   if os.environ.get("CUDA_VISIBLE_DEVICES") else str(dev))
+        d = json.loads(subprocess.run([str(exe), "120", "mix-only"], capture_output=True, text=True, timeout=120,
+                                      check=True, env=env).stdout)
+        m = d["mix_64sad_66imad_41min"]
+        res.update(mix_peak=m["tera_lane_ops_per_s"], sm_mhz=m.get("mhz_nvml") or m.get("mhz_clock64"),
+                   source="measured live, sustained (csrc/microbench: kernel-mix issue rate from registers, "
+                          f"{m.get('launches')} back-to-back launches, SM clock {m.get('mhz_nvml')} MHz by NVML / "
+                          f"{m.get('mhz_clock64')} MHz by clock64, {m.get('power_w_max')} W)")
     except Exception as e:  # noqa: BLE001
-        p = ROOT / "profiles" / "INT_PEAKS_r01.json"
-        if p.exists():
-            d = json.loads(p.read_text())
-            return d["mix_64sad_66imad_41min"]["tera_lane_ops_per_s"], f"profiles/INT_PEAKS_r01.json ({type(e).__name__})", d
-        return 25.9, "fallback constant", {}
+        for name in ("INT_PEAKS_r02.json", "INT_PEAKS_r01.json"):
+            f = ROOT / "profiles" / name
+            if f.exists():
+                m = json.loads(f.read_text())["mix_64sad_66imad_41min"]
+                res.update(mix_peak=m["tera_lane_ops_per_s"], sm_mhz=m.get("mhz_nvml"), source=f"profiles/{name} ({type(e).__name__})")
+                break
+        else:
+            res.update(mix_peak=25.9, sm_mhz=None, source="fallback constant (round-1 measurement)")
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -165,20 +230,25 @@ def run_reference(args, rank, world):
             t0 = time.perf_counter()
             for i, r in enumerate(ref_l):
                 c.set_reference(i, r)
+            t1 = time.perf_counter()
             c.search_frame(cur)
-            dt = time.perf_counter() - t0
+            t2 = time.perf_counter()
+            # the oracle always interpolates the whole reference: a sample of `rows` MB rows is charged its share
+            dt = (t2 - t1) + (t1 - t0) * rows / mb_h
             if s >= args.warmup:
                 times.append(dt)
     ms = 1e3 * float(np.mean(times))
     n_mb = rows * mb_w
     v = n_mb / (ms * 1e-3)
-    sample = f"{rows} of {mb_h} MB rows ({n_mb} MBs) of {args.workload} per step, interpolation of the whole reference included"
+    sample = (f"{rows} of {mb_h} MB rows ({n_mb} MBs) of {args.workload} per step: search of those rows + {rows}/{mb_h} of the "
+              f"time of interpolating the whole reference")
     print(json.dumps({
         "impl": "reference", "metric": "ME macroblocks/sec", "value": v, "unit": "MB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "qp": QP, "pred_policy": args.pred_policy, "note": "CPU restatement (oracle/) of the JM path; the mounted "
-                   "reference holds no sources, so this is a port, not JM itself"},
+        "config": config_of(args),
+        "note": "CPU restatement (oracle/) of the JM path on all host cores; the mounted reference holds no sources, "
+                "so this is a port, not JM itself; each step is a bounded sample of the workload (cpu_baseline.sample)",
         "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -206,8 +276,10 @@ def cpu_baseline(args):
             t0 = time.perf_counter()
             for i, r in enumerate(ref_l):
                 c.set_reference(i, r)
+            t1 = time.perf_counter()
             c.search_frame(cur)
-            return time.perf_counter() - t0
+            # (the oracle interpolates the whole reference: the sample is charged its share of that)
+            return (time.perf_counter() - t1) + (t1 - t0) * rows / mb_h
     t1 = go(1) / min(mb_h, unit)
     rows = int(max(1, min(mb_h, args.cpu_seconds / max(t1, 1e-6))))
     rows = min(mb_h, -(-rows // unit) * unit)
@@ -230,6 +302,64 @@ def _watchdog(seconds):
     t.start()
 
 
+def oracle_parity(args, fields):
+    """Parity guard of the bench line: the field the GPU produced for every seed against the CPU oracle (all host
+    threads, not timed).  Whole frame when the oracle needs about `--parity-seconds` or less for it, else MB rows
+    spread over the frame (first, last and evenly in between, whole slices under the median policy).
+    fields: {seed: numpy MBRESULT array of the whole frame}.  Returns the `parity` object; raises on a mismatch."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as oracle_mod
+    from jmme import synth
+    orc = oracle_mod.load()
+    orc.dll.jmme_oracle_set_threads.restype = C.c_int
+    cores = orc.dll.jmme_oracle_set_threads(0)
+    w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
+    mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
+    unit = slice_unit(args, mb_h)
+    kw = dict(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP, **policy_kw(args))
+
+    def rows_of(seed, groups):
+        cur, ref_l = synth.frame_pair(w, h, seed=seed, search_range=R, num_refs=refs)
+        out = {}
+        for g in groups:
+            rb, re = g * unit, min(mb_h, (g + 1) * unit)
+            with orc.context(mb_row_begin=rb, mb_row_end=re, **kw) as c:
+                for i, r in enumerate(ref_l):
+                    c.set_reference(i, r)
+                out[(rb, re)] = c.search_frame(cur)[rb * mb_w:re * mb_w]
+        return out
+
+    try:
+        n_groups = -(-mb_h // unit)
+        t0 = time.perf_counter()
+        first = rows_of(SEEDS[0], [n_groups // 2])              # calibration: one group of rows
+        t_group = time.perf_counter() - t0
+        budget = max(1, int(args.parity_seconds / max(t_group, 1e-6) / len(fields)))
+        if budget >= n_groups:
+            groups = list(range(n_groups))
+        else:
+            groups = sorted({round(i * (n_groups - 1) / max(budget - 1, 1)) for i in range(budget)})
+        checked = mism = 0
+        for seed, field in fields.items():
+            exp = rows_of(seed, groups)
+            if seed == SEEDS[0]:
+                exp.update(first)
+            for (rb, re), o in exp.items():
+                g = field[rb * mb_w:re * mb_w]
+                checked += len(o)
+                if g.tobytes() != o.tobytes():
+                    mism += int(np.count_nonzero(np.any(g["mv"] != o["mv"], axis=(1, 2)) | np.any(g["cost"] != o["cost"], axis=1) |
+                                                 np.any(g["ref_idx"] != o["ref_idx"], axis=1))) or 1
+    finally:
+        orc.dll.jmme_oracle_set_threads(1)
+    par = {"mbs": checked, "mismatches": mism, "blocks_per_mb": 41, "seeds": list(fields),
+           "rows": "whole frame" if len(groups) == n_groups else f"{len(groups)} of {n_groups} row groups of {unit}, spread",
+           "checker": f"oracle/libjmme_oracle.so, {cores} threads, every MV / ref_idx / cost byte of the records"}
+    if mism:
+        raise SystemExit(f"bench.py: GPU field differs from the oracle: {json.dumps(par)}")
+    return par
+
+
 def run_ours(args, rank, world, local_rank):
     _watchdog(args.watchdog)
     import torch
@@ -249,9 +379,17 @@ def run_ours(args, rank, world, local_rank):
     mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
     n_mb = mb_h * mb_w
     rb, re = stripe_of(rank, world, mb_h, slice_unit(args, mb_h))
-    cur, ref_l = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=refs)
-    d_cur = torch.from_numpy(cur).cuda()
-    d_refs = [torch.from_numpy(r).cuda() for r in ref_l]
+    pairs = [synth.frame_pair(w, h, seed=sd, search_range=R, num_refs=refs) for sd in SEEDS]
+    # the step's inputs live in these device buffers; the frame pair of step s (seed SEEDS[s % 3]) is copied
+    # into them before the timed region of the step starts
+    d_pairs = [(torch.from_numpy(c).cuda(), [torch.from_numpy(r).cuda() for r in rl]) for c, rl in pairs]
+    d_cur = d_pairs[0][0].clone()
+    d_refs = [r.clone() for r in d_pairs[0][1]]
+
+    def load_pair(i):
+        d_cur.copy_(d_pairs[i][0])
+        for a, b_ in zip(d_refs, d_pairs[i][1]):
+            a.copy_(b_)
     if re <= rb:
         raise SystemExit(f"rank {rank}: empty stripe — {mb_h} MB rows cannot feed {world} ranks of {-(-mb_h // world)} rows")
     ds = DeviceSearch(lib, width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
@@ -307,10 +445,12 @@ def run_ours(args, rank, world, local_rank):
     l_a = ds.launch_count()
     step_device()
     launches_per_step = ds.launch_count() - l_a          # kernels of one step (a graph replay launches the same ones)
+    kernel_instance = ds.ctx.last_kernel()
     barrier()
     # per-kernel device times (CUDA events around each kernel, eager launches) for the roofline
     ktimes = []
     for s in range(min(args.steps, 10)):
+        load_pair(s % len(SEEDS))
         flush.fill_(s & 255)
         step_device()
         torch.cuda.synchronize()
@@ -343,13 +483,17 @@ def run_ours(args, rank, world, local_rank):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = ds.launch_count()
     barrier()
+    fields = {}
     for s in range(args.steps):
+        load_pair(s % len(SEEDS))         # this step's frame pair, resident in HBM before the timed region
         flush.fill_(s & 255)              # L2 flush between timed iterations (outside the event pair)
         barrier()
         ev[s][0].record()
         run_step()
         ev[s][1].record()
         torch.cuda.synchronize()
+        if rank == 0 and SEEDS[s % len(SEEDS)] not in fields and not args.no_parity:
+            fields[SEEDS[s % len(SEEDS)]] = ds.to_numpy(gather.frame()).copy()      # the timed step's own output
     barrier()
     launches = ds.launch_count() - l0
     if graph is not None:                 # replays launch the captured kernels without passing the counter
@@ -358,48 +502,52 @@ def run_ours(args, rank, world, local_rank):
     ms_dev = float(np.mean(step_ms))
 
     # ---- end to end through the C-ABI host calls (pinned host buffers) -------------------------
-    h_cur = torch.from_numpy(cur).pin_memory()
-    h_refs = [torch.from_numpy(r).pin_memory() for r in ref_l]
+    h_pairs = [(torch.from_numpy(c).pin_memory(), [torch.from_numpy(r).pin_memory() for r in rl]) for c, rl in pairs]
     h_out = torch.zeros(n_mb * rec, dtype=torch.uint8).pin_memory()
     hctx = lib.context(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
                        mb_row_begin=rb, mb_row_end=re, device_ids=[local_rank], async_reference=1, **policy_kw(args))
     pu8 = C.POINTER(C.c_uint8)
 
-    def step_host():
-        for i, r in enumerate(h_refs):
-            lib.check(lib.dll.jmme_set_reference(hctx.handle, i, C.cast(r.data_ptr(), pu8), w), hctx.handle)
+    def step_host(i):
+        h_cur, h_refs = h_pairs[i]
+        for k, r in enumerate(h_refs):
+            lib.check(lib.dll.jmme_set_reference(hctx.handle, k, C.cast(r.data_ptr(), pu8), w), hctx.handle)
         lib.check(lib.dll.jmme_search_frame(hctx.handle, C.cast(h_cur.data_ptr(), pu8), w, None,
                                             C.c_void_p(h_out.data_ptr()), None), hctx.handle)
 
     for _ in range(max(args.warmup, 3)):
-        step_host()
+        step_host(0)
     e2e_t = []
     barrier()
+    last_seed_i = 0
     for s in range(args.steps):
         flush.fill_(s & 255)
         barrier()
+        last_seed_i = s % len(SEEDS)
         t0 = time.perf_counter()
-        step_host()
+        step_host(last_seed_i)
         e2e_t.append(time.perf_counter() - t0)
     barrier()
     ms_e2e = 1e3 * float(np.mean(e2e_t))
     launches_e2e = hctx.launch_count()
     clocks = sampler.stop() if rank == 0 else None
 
-    # parity guard: the host path and the device path must agree byte for byte on this rank's stripe
+    # the host path and the device path must agree byte for byte on this rank's stripe (same frame pair)
+    load_pair(last_seed_i)
+    step_device()
+    torch.cuda.synchronize()
     got = ds.to_numpy(gather.frame())[rb * mb_w:re * mb_w]
     exp = h_out.numpy().view(abi.MBRESULT_DTYPE)[rb * mb_w:re * mb_w]
     assert got.tobytes() == exp.tobytes(), "device-resident and host-buffer paths disagree"
 
     # the gathered field must be the same on every rank and equal to an independent NCCL gather
     if world > 1:
-        step_device()
-        torch.cuda.synchronize()
         chk = StripeGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
         chk.field[rb * mb_w:re * mb_w].copy_(gather.field[rb * mb_w:re * mb_w])
         ref_field = chk.gather()
         torch.cuda.synchronize()
         assert torch.equal(ref_field, gather.frame()), f"rank {rank}: gathered MV field differs from the NCCL gather"
+        chk = None
 
     # ---- max over ranks -------------------------------------------------------------------------
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
@@ -414,7 +562,7 @@ def run_ours(args, rank, world, local_rank):
         k_sub = float(np.mean([k["me_subpel"] for k in ktimes]))
         k_itp = float(np.mean([k["interp"] for k in ktimes]))
         k_sel = float(np.mean([k["select"] for k in ktimes]))
-        peak, peak_src, _ = int_peak_live()
+        peaks = int_peaks(local_rank)
         hbm, hbm_src = measured_peaks()
         alg_ops = (re - rb) * mb_w * refs * ncand * ops_cand          # this rank's launch
         wave = args.pred_policy == "median"
@@ -434,53 +582,62 @@ def run_ours(args, rank, world, local_rank):
         h2d_bytes = (refs * ref_rows + cur_rows) * w
         pad_ = (2 * R + 16 + 15) & ~15
         plane_mb = (16 if subpel else 1) * (((w + 15) & ~15) + 2 * pad_) * (((h + 15) & ~15) + 2 * pad_) / 1e6
+        headline = world == 1 and not wave and args.workload.startswith("1080p_r32")
         line = {
             "metric": "ME macroblocks/sec", "value": n_mb / (ms_dev * 1e-3), "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "frame": f"{w}x{h}", "mbs": n_mb, "search_range": R, "refs": refs,
-                       "blocks": 41 if mask != 0x02 else 1, "subpel": "half+quarter SATD" if subpel else "none",
-                       "qp": QP, "pred_policy": ("zero" if not wave else
-                                                 f"in-frame median (JMME_PRED_MEDIAN), slice_rows={args.slice_rows}: "
-                                                 f"a 2:1 wavefront of {mb_w + 2 * (min(args.slice_rows or mb_h, re - rb) - 1)} steps"),
-                       "partition": f"{world} MB-row stripes",
-                       "l2": "256 MB buffer written between timed steps (outside the event pair)",
-                       "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
-                       "launch": launch_mode, "gather": gather_mode},
+            "config": config_of(args, re - rb),
+            "run": {"partition": f"{world} MB-row stripes",
+                    "l2": "256 MB buffer written between timed steps (outside the event pair)",
+                    "timing": "CUDA events per step on the launching stream, mean over steps, max over ranks",
+                    "launch": launch_mode, "gather": gather_mode},
             "e2e": {"value": n_mb / (ms_e2e * 1e-3), "unit": "MB/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": (re - rb) * mb_w * rec,
                     "api": "jmme_set_reference + jmme_search_frame (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches + launches_e2e),
             "kernel_ms": {"interp": k_itp, "me_int": k_int, "me_subpel": k_sub, "select_ref": k_sel,
                           "share_me_int": k_int / max(k_itp + k_int + k_sub + k_sel, 1e-9)},
-            "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
-                         "frac": achieved / peak,
-                         "traffic": ncu_traffic("me_int_tb_kernel") if (world == 1 and not wave and args.workload.startswith("1080p_r32")) else None,
+            "roofline": {"bound": "int_alu", "achieved": achieved, "peak": peaks["mix_peak"], "unit": "Tlane-op/s",
+                         "frac": achieved / peaks["mix_peak"],
+                         # the same achieved rate against the two other ceilings the review asked for
+                         "frac_of_issue_ceiling": achieved / peaks["issue_ceiling"],
+                         "issue_ceiling": peaks["issue_ceiling"],
+                         "alu_pipe_pct_ncu": ncu_metric("me_int", "alu_pipe_pct") if headline else None,
+                         "traffic": ncu_traffic("me_int") if headline else None,
                          "kernel": ("wavefront step chain (me_int_tb_kernel clusters + me_subpel_kernel), whole search" if wave
-                                    else "me_int_tb_kernel" if (R <= 32 and mask != 0x02) else "me_int_kernel"),
-                         "algorithmic_ops_per_candidate": ops_cand, "peak_source": peak_src},
-            "roofline_interp": {"bound": "hbm", "achieved": itp_gbs, "peak": hbm, "unit": "GB/s",
-                                "frac": (itp_gbs / hbm) if itp_gbs else None,
-                                "traffic": ncu_traffic("interp_kernel") if (world == 1 and args.workload.startswith("1080p_r32")) else None,
+                                    else kernel_instance.split("<")[0]),
+                         "kernel_instance": kernel_instance,
+                         "algorithmic_ops_per_candidate": ops_cand, "peak_source": peaks["source"],
+                         "sm_mhz_microbench": peaks.get("sm_mhz")},
+            "roofline_interp": {"bound": "alu (the planes stay in the 126 MB L2; HBM figure for reference)", "achieved": itp_gbs,
+                                "peak": hbm, "unit": "GB/s", "frac": (itp_gbs / hbm) if itp_gbs else None,
+                                "traffic": ncu_traffic("interp") if (world == 1 and args.workload.startswith("1080p_r32")) else None,
                                 "note": (f"{plane_mb:.1f} MB of planes per reference are written; they stay in the 126 MB L2 for the "
                                          "sub-pel kernel when they fit" if subpel else "integer plane only"),
                                 "kernel": "interp_kernel", "algorithmic_bytes_per_pixel": 17, "peak_source": hbm_src},
             "clocks": clocks,
         }
+        if fields:
+            line["parity"] = oracle_parity(args, fields)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
-    # Orderly exit.  A captured graph holds NCCL work; destroying the process group with it alive was seen
-    # to hang, so the graph goes first, every rank meets at a barrier, and the process leaves without
-    # running the communicator's destructor (a watchdog bounds everything above in case a rank is stuck).
+    # Orderly exit through the interpreter (the driver records the loaded .so files at exit).  A captured graph
+    # holds the step's kernels (and NCCL / symmetric-memory work): it goes first, then the contexts, every rank
+    # meets at a barrier and the process group is destroyed; the watchdog bounds all of it.
     sys.stdout.flush()
-    graph = None
+    graph = run_step = None
     torch.cuda.synchronize()
+    hctx.close()
+    ds.close()
     if world > 1:
         dist.barrier()
+        gather = None
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 def main():
@@ -496,6 +653,9 @@ def main():
                     help="median: JMME_PRED_MEDIAN, the predictor loop closed inside the frame (a wavefront)")
     ap.add_argument("--slice-rows", type=int, default=1, help="MB rows per slice of --pred-policy median (0 = whole frame)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed steps' output")
+    ap.add_argument("--parity-seconds", type=float, default=20.0,
+                    help="CPU time budget of the oracle comparison (whole frame if it fits, else spread rows)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-push", "nccl"],
                     help="N > 1: how the MV field is gathered: peer stores from the search kernels (p2p), from a "

@@ -19,6 +19,11 @@
 #include "wave.cuh"
 
 const WaveTab &jmme_wave_tab();
+char *jmme_kernel_name_buf()
+{
+    static thread_local char buf[JMME_KNAME_LEN];
+    return buf;
+}
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st);
 cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st);
@@ -39,16 +44,15 @@ cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_ds
 struct jmme_ctx {
     jmme_params p;
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
-    int device, num_sms, K;
-    int tune_group, tune_cluster, tune_lin;   // launch knobs of me_int_tb.cu (JMME_GROUP, JMME_CLUSTER, JMME_LIN)
-    bool force_wave_step;                 // JMME_WAVE_STEP: predictors always by wave_step_kernel
-    bool use_pdl;                         // JMME_PDL=0: no programmatic dependent launch in the wavefront
+    int device, num_sms;
+    jmme_tuning tune;                     // launch knobs with the defaults resolved (jmme_set_tuning)
+    char last_kernel[JMME_KNAME_LEN];     // integer-search kernel instantiation of the last search
     cudaStream_t stream;
     cudaStream_t copy_stream;             // host->device copy of the current picture, overlaps the plane kernel
     cudaEvent_t ev_copy;
     cudaStream_t part_stream[4];          // the pipelined host path searches the stripe in up to 4 parts
     cudaEvent_t ev_ref;
-    int pipe_parts;
+    cudaEvent_t ev_search;                // end of the last in-frame median search (orders jmme_get_predictors)
     uint8_t *d_raw;                       // staging for the raw current picture (width x height)
     uint8_t *d_raw_ref[JMME_MAX_REFS];    // staging for the raw reference pictures
     uint8_t *d_planes[JMME_MAX_REFS];
@@ -100,6 +104,18 @@ int fail(jmme_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
 
 int pad_for(int R) { return (2 * R + 16 + 15) & ~15; }
 
+// jmme_tuning with every 0 replaced by the measured default
+void resolve_tuning(const jmme_tuning *in, jmme_tuning *out)
+{
+    jmme_tuning t;
+    memset(&t, 0, sizeof t);
+    if (in) t = *in;
+    if (t.group <= 0) t.group = 2;                // MBs per work item of the zero-predictor kernel
+    if (t.cluster <= 0) t.cluster = 4;            // largest cluster of a wavefront step (1 = none)
+    t.pipe_parts = t.pipe_parts <= 0 ? 3 : std::min(t.pipe_parts, 4);
+    *out = t;
+}
+
 // rows of `width` bytes host -> device; one linear copy when the source rows are contiguous
 cudaError_t upload_rows(uint8_t *dst, const uint8_t *src, int stride, int width, int rows, cudaStream_t st)
 {
@@ -135,6 +151,7 @@ void free_device(jmme_ctx *c)
             if (c->ev_prof[i][j]) cudaEventDestroy(c->ev_prof[i][j]);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_ref) cudaEventDestroy(c->ev_ref);
+    if (c->ev_search) cudaEventDestroy(c->ev_search);
     for (int i = 0; i < 4; i++)
         if (c->part_stream[i]) cudaStreamDestroy(c->part_stream[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -176,18 +193,7 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
     if (c->lambda_factor > (96 << 16)) { delete c; return JMME_ERR_PARAM; }
     c->n_planes = p->subpel ? 16 : 1;
     c->ncols = 2 * p->search_range + 1; c->ncand = c->ncols * c->ncols;
-    const char *ek = getenv("JMME_VARIANT");      // tuning knob: 10*K + launch shape, see me_int.cu
-    c->K = ek ? atoi(ek) : 0;                      // 0 = choose by search range
-    {
-        const char *eg = getenv("JMME_GROUP"), *ec = getenv("JMME_CLUSTER");
-        c->tune_group = eg ? atoi(eg) : 2;         // MBs per work item of the zero-predictor kernel
-        c->tune_cluster = ec ? atoi(ec) : 4;       // largest cluster of a wavefront step (1 = none)
-        const char *el = getenv("JMME_LIN");
-        c->tune_lin = el ? atoi(el) : 1;           // integer lambda: linear per-block rate instead of the table
-        c->force_wave_step = getenv("JMME_WAVE_STEP") != nullptr;
-        const char *epd = getenv("JMME_PDL");
-        c->use_pdl = !epd || atoi(epd) != 0;
-    }
+    resolve_tuning(nullptr, &c->tune);
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -211,10 +217,7 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         CUC(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
         for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&c->part_stream[i], cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&c->ev_ref, cudaEventDisableTiming));
-        {
-            const char *ep = getenv("JMME_PIPE_PARTS");   // tuning knob: 1 = no pipelining
-            c->pipe_parts = ep ? std::min(std::max(atoi(ep), 1), 4) : 3;
-        }
+        CUC(cudaEventCreateWithFlags(&c->ev_search, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         CUC(cudaMalloc(&c->d_raw, (size_t)p->width * p->height));
         for (int r = 0; r < p->num_refs; r++) {
@@ -289,7 +292,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
     P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy;
     P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
-    P.tune_group = c->tune_group; P.tune_cluster = c->tune_cluster; P.tune_lin = c->tune_lin;
+    P.tune_group = c->tune.group; P.tune_cluster = c->tune.cluster; P.tune_lin = !c->tune.table_rate;
 }
 
 // enqueue the whole search on `st`; nothing is synchronised here
@@ -326,12 +329,12 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         P.field_mv = c->d_fmv; P.field_ref = c->d_fref; P.slice_rows = c->p.slice_rows;
         // the default integer kernel of a wavefront step (me_int_tb.cu, 12 warps, clusters) predicts in its own
         // prologue; the other kernels read the predictors wave_step_kernel writes
-        const bool in_kernel = c->K == 0 && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
-                               c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !c->force_wave_step;
+        const bool in_kernel = c->tune.variant == 0 && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
+                               c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !c->tune.wave_step;
         P.wave_tab = in_kernel ? c->d_wave_tab : nullptr;
         // search and sub-pel kernels of consecutive steps overlap their launch latency and constant-only
-        // prologues (programmatic dependent launch); JMME_PDL=0 turns it off
-        P.pdl = in_kernel && c->use_pdl;
+        // prologues (programmatic dependent launch); jmme_tuning.no_pdl turns it off
+        P.pdl = in_kernel && !c->tune.no_pdl;
         for (int t = 0; t < c->n_steps; t++) {
             P.mb_list = c->d_wave + c->wave_off[t]; P.n_list = c->wave_off[t + 1] - c->wave_off[t];
             if (!in_kernel) {
@@ -340,11 +343,13 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
                 c->launches++;
             }
             if (c->p.search_mode == JMME_SEARCH_FULL) CU(c, jmme_launch_me_full(P, st));
-            else CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
+            else CU(c, jmme_launch_me_int(P, c->num_sms, c->tune.variant, st));
             c->launches++;
             if (c->p.subpel) { CU(c, jmme_launch_subpel(P, st)); c->launches++; }
             if (!P.fused_select) { CU(c, jmme_launch_select(P, st)); c->launches++; }
         }
+        memcpy(c->last_kernel, jmme_kernel_name_buf(), JMME_KNAME_LEN);
+        CU(c, cudaEventRecord(c->ev_search, st));    // jmme_get_predictors copies d_pred on another stream
         c->searched = true;
         return JMME_OK;
     }
@@ -352,7 +357,8 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     if (c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK)
         CU(c, jmme_launch_me_full(P, st));           // a window per block: nothing to share (me_full.cu)
     else
-        CU(c, jmme_launch_me_int(P, c->num_sms, c->K, st));
+        CU(c, jmme_launch_me_int(P, c->num_sms, c->tune.variant, st));
+    memcpy(c->last_kernel, jmme_kernel_name_buf(), JMME_KNAME_LEN);
     if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[1][1], st)); c->prof_valid[1] = true; }
     c->launches++;
     if (c->p.subpel) {
@@ -473,6 +479,23 @@ int64_t jmme_launch_count(const jmme_ctx *c)
     return n;
 }
 
+int jmme_set_tuning(jmme_ctx *c, const jmme_tuning *t)
+{
+    if (!c || !t) return JMME_ERR_PARAM;
+    if (t->variant < 0 || t->group < 0 || t->group > 4 || t->cluster < 0 || t->cluster > 4 || t->pipe_parts < 0)
+        return fail(c, JMME_ERR_PARAM, "tuning out of range");
+    resolve_tuning(t, &c->tune);
+    for (int g = 0; g < c->n_sub; g++) resolve_tuning(t, &c->sub[g]->tune);
+    return JMME_OK;
+}
+int jmme_get_tuning(const jmme_ctx *c, jmme_tuning *t)
+{
+    if (!c || !t) return JMME_ERR_PARAM;
+    *t = c->n_sub ? c->sub[0]->tune : c->tune;
+    return JMME_OK;
+}
+const char *jmme_last_kernel(const jmme_ctx *c) { return !c ? "" : (c->n_sub ? c->sub[0]->last_kernel : c->last_kernel); }
+
 int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d_luma, int stride, void *stream)
 {
     if (!c || !d_luma || r < 0 || r >= c->p.num_refs || stride < c->p.width) return JMME_ERR_PARAM;
@@ -560,6 +583,7 @@ int jmme_get_predictors(jmme_ctx *c, int16_t *pred)
         jmme_ctx *s = subs[g];
         if (!s->searched) return fail(c, JMME_ERR_STATE, "no median search yet");
         CU(c, cudaSetDevice(s->device));
+        CU(c, cudaStreamWaitEvent(s->stream, s->ev_search, 0));     // the search may have run on the caller's stream
         const size_t off = (size_t)s->p.mb_row_begin * s->mb_w, cnt = (size_t)(s->p.mb_row_end - s->p.mb_row_begin) * s->mb_w;
         for (int r = 0; r < c->p.num_refs; r++)
             CU(c, cudaMemcpyAsync(pred + (r * n_mb + off) * per_mb, s->d_pred + (r * n_mb + off) * per_mb,
@@ -633,23 +657,25 @@ int jmme_predict_frame(jmme_ctx *c, const int16_t *mv4, const int8_t *ref4, int1
     const size_t n_mb = (size_t)s->mb_w * s->mb_h, cells = 16 * n_mb;
     const size_t n_pred = (size_t)s->p.num_refs * n_mb * JMME_NBLK * 2;
     CU(c, cudaSetDevice(s->device));
-    int16_t *d_mv = nullptr; int8_t *d_ref = nullptr;
+    int16_t *d_mv = nullptr, *d_p = nullptr; int8_t *d_ref = nullptr;
     int rc = JMME_OK;
     cudaError_t e;
-    if ((e = cudaMalloc(&d_mv, cells * 4)) != cudaSuccess || (e = cudaMalloc(&d_ref, cells)) != cudaSuccess)
+    // (a scratch buffer of its own: d_pred keeps the predictors of the last in-frame median search)
+    if ((e = cudaMalloc(&d_mv, cells * 4)) != cudaSuccess || (e = cudaMalloc(&d_ref, cells)) != cudaSuccess ||
+        (e = cudaMalloc(&d_p, n_pred * sizeof(int16_t))) != cudaSuccess)
         rc = fail(c, JMME_ERR_CUDA, "cudaMalloc(field)", e);
     if (rc == JMME_OK) {
         cudaMemcpyAsync(d_mv, mv4, cells * 4, cudaMemcpyHostToDevice, s->stream);
         cudaMemcpyAsync(d_ref, ref4, cells, cudaMemcpyHostToDevice, s->stream);
-        if ((e = jmme_launch_predict(d_mv, d_ref, s->mb_w, s->mb_h, s->p.num_refs, s->d_pred, s->stream)) != cudaSuccess)
+        if ((e = jmme_launch_predict(d_mv, d_ref, s->mb_w, s->mb_h, s->p.num_refs, d_p, s->stream)) != cudaSuccess)
             rc = fail(c, JMME_ERR_CUDA, "predict_kernel", e);
     }
     if (rc == JMME_OK) {
         s->launches++;
-        cudaMemcpyAsync(pred, s->d_pred, n_pred * sizeof(int16_t), cudaMemcpyDeviceToHost, s->stream);
+        cudaMemcpyAsync(pred, d_p, n_pred * sizeof(int16_t), cudaMemcpyDeviceToHost, s->stream);
         if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess) rc = fail(c, JMME_ERR_CUDA, "predict_frame", e);
     }
-    cudaFree(d_mv); cudaFree(d_ref);
+    cudaFree(d_mv); cudaFree(d_ref); cudaFree(d_p);
     return rc;
 }
 
@@ -690,43 +716,70 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
     const int ns = c->n_sub ? c->n_sub : 1;
     const size_t n_mb = (size_t)c->mb_w * c->mb_h;
     const int npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
-    const size_t pred_elems = !pred ? 0 : (size_t)c->p.num_refs * n_mb * npb * 2;
     for (int r = 0; r < c->p.num_refs; r++)
         if (!subs[0]->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
-    for (size_t i = 0; i < pred_elems; i++)
-        if (pred[i] > JMME_MAX_PRED_QPEL || pred[i] < -JMME_MAX_PRED_QPEL)
-            return fail(c, JMME_ERR_PARAM, "pred out of range");
+    // predictors: only the MB rows of this context's stripe are read (checked here, uploaded below) — rows
+    // outside it may be left uninitialised by the caller
+    const size_t per_mb = (size_t)npb * 2;
+    if (pred)
+        for (int r = 0; r < c->p.num_refs; r++) {
+            const int16_t *q = pred + ((size_t)r * n_mb + (size_t)c->p.mb_row_begin * c->mb_w) * per_mb;
+            const size_t n = (size_t)(c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w * per_mb;
+            for (size_t i = 0; i < n; i++)
+                if (q[i] > JMME_MAX_PRED_QPEL || q[i] < -JMME_MAX_PRED_QPEL) return fail(c, JMME_ERR_PARAM, "pred out of range");
+        }
+    auto upload_pred = [&](jmme_ctx *s, cudaStream_t st) -> cudaError_t {      // the stripe rows of every reference
+        for (int r = 0; pred && r < c->p.num_refs; r++) {
+            const size_t off = ((size_t)r * n_mb + (size_t)s->p.mb_row_begin * s->mb_w) * per_mb;
+            const size_t n = (size_t)(s->p.mb_row_end - s->p.mb_row_begin) * s->mb_w * per_mb;
+            cudaError_t e = cudaMemcpyAsync(s->d_pred + off, pred + off, n * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
 
     // Single device, host buffers: the stripe is searched in parts on separate streams, so that the upload of
     // the later parts of the current picture and the download of the earlier parts of the MV field overlap
     // the kernels of the other parts (the reference planes are shared).
-    if (ns == 1 && !c->profiling && c->pipe_parts > 1 && c->p.pred_policy != JMME_PRED_MEDIAN && c->w16 == c->p.width && !(stride & 15) && !((uintptr_t)cur & 15) &&
-        c->p.mb_row_end - c->p.mb_row_begin >= 4 * c->pipe_parts) {
+    if (ns == 1 && !c->profiling && c->tune.pipe_parts > 1 && c->p.pred_policy != JMME_PRED_MEDIAN && c->w16 == c->p.width && !(stride & 15) && !((uintptr_t)cur & 15) &&
+        c->p.mb_row_end - c->p.mb_row_begin >= 4 * c->tune.pipe_parts) {
         jmme_ctx *s = c;
         CU(c, cudaSetDevice(s->device));
-        if (pred_elems)
-            CU(c, cudaMemcpyAsync(s->d_pred, pred, pred_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, upload_pred(s, s->stream));
         CU(c, cudaEventRecord(s->ev_ref, s->stream));          // planes (and predictors) are ready after this
-        const int np = s->pipe_parts, rows = s->p.mb_row_end - s->p.mb_row_begin;
+        const int np = s->tune.pipe_parts, rows = s->p.mb_row_end - s->p.mb_row_begin;
+        int rc = JMME_OK, used = 0;
+        // a failure in part k must not return while parts 0..k-1 still write into the caller's buffers
+#define CUP(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) { rc = fail(c, JMME_ERR_CUDA, #call, e_); goto parts_done; }    \
+    } while (0)
         for (int pt = 0; pt < np; pt++) {
             const int rb = s->p.mb_row_begin + rows * pt / np, re = s->p.mb_row_begin + rows * (pt + 1) / np;
             cudaStream_t st = s->part_stream[pt];
             const int y0 = std::min(16 * rb, s->p.height - 1), y1 = std::min(16 * re, s->p.height);
-            CU(c, upload_rows(s->d_raw + (size_t)y0 * s->p.width, cur + (size_t)y0 * stride, stride, s->p.width,
-                              std::max(y1 - y0, 1), st));
-            CU(c, cudaStreamWaitEvent(st, s->ev_ref, 0));
-            int rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,
-                                    st, rb, re);
-            if (rc != JMME_OK) return rc;
+            used = pt + 1;
+            CUP(upload_rows(s->d_raw + (size_t)y0 * s->p.width, cur + (size_t)y0 * stride, stride, s->p.width,
+                            std::max(y1 - y0, 1), st));
+            CUP(cudaStreamWaitEvent(st, s->ev_ref, 0));
+            rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,
+                                st, rb, re);
+            if (rc != JMME_OK) goto parts_done;
             const size_t off = (size_t)rb * s->mb_w, cnt = (size_t)(re - rb) * s->mb_w;
-            CU(c, cudaMemcpyAsync(out + off, s->d_out + off, cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, st));
+            CUP(cudaMemcpyAsync(out + off, s->d_out + off, cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, st));
             if (out_per_ref)
                 for (int r = 0; r < c->p.num_refs; r++)
-                    CU(c, cudaMemcpyAsync(out_per_ref + r * n_mb + off, s->d_out_per_ref + r * n_mb + off,
-                                          cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, st));
+                    CUP(cudaMemcpyAsync(out_per_ref + r * n_mb + off, s->d_out_per_ref + r * n_mb + off,
+                                        cnt * sizeof(jmme_mbresult), cudaMemcpyDeviceToHost, st));
         }
-        for (int pt = 0; pt < np; pt++) CU(c, cudaStreamSynchronize(s->part_stream[pt]));
-        return JMME_OK;
+#undef CUP
+    parts_done:
+        for (int pt = 0; pt < used; pt++) {
+            cudaError_t e = cudaStreamSynchronize(s->part_stream[pt]);
+            if (e != cudaSuccess && rc == JMME_OK) rc = fail(c, JMME_ERR_CUDA, "cudaStreamSynchronize(part)", e);
+        }
+        return rc;
     }
 
     // enqueue on every device, then gather
@@ -743,8 +796,7 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
             CU(c, cudaEventRecord(s->ev_copy, s->copy_stream));
             CU(c, cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
         }
-        if (pred_elems)
-            CU(c, cudaMemcpyAsync(s->d_pred, pred, pred_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s->stream));
+        CU(c, upload_pred(s, s->stream));
         int rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,
                                 s->stream);
         if (rc != JMME_OK) return fail(c, rc, s->err);

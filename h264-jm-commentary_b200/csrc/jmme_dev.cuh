@@ -7,7 +7,6 @@
 #include "jmme.h"
 
 #define JMME_NBLK 41
-#define JMME_MAX_PRED_QPEL 2048          // |pred| limit enforced by the host API
 #define JMME_KEY_BITS 15                 // packed cost = (cost + bias) << 15 | key
 #define JMME_KEY_MASK 0x7FFFu
 #define JMME_NT 64                       // entries of the rate table T[bits]
@@ -50,8 +49,8 @@ struct SearchParams {
     int8_t *field_ref;                   //           MB to the 4x4-granular field [4 mb_h][4 mb_w]([2])
     const WaveTab *wave_tab;             // non-null: the search kernel predicts its MB's 41 vectors itself from the
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
-    int tune_group, tune_cluster;        // host-side launch knobs (JMME_GROUP, JMME_CLUSTER), read once per context
-    int tune_lin;                        // JMME_LIN=0: per-block rate always from the table
+    int tune_group, tune_cluster;        // host-side launch knobs (jmme_tuning.group / .cluster, defaults resolved)
+    int tune_lin;                        // 0 (jmme_tuning.table_rate): per-block rate always from the table
     int pdl;                             // wavefront steps: launch with programmatic stream serialization
     jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
     int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
@@ -70,6 +69,52 @@ __device__ __forceinline__ void push_records(const SearchParams &P, int n_rec, F
         for (int p = 0; p < P.n_peer_out; p++) ((uint32_t *)(P.peer_out[p] + mb))[w] = v;
     }
 }
+
+// ---- host side: per-(kernel instantiation, device) launch state -------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is process-wide per (kernel, device): it is raised once to the
+// device's opt-in maximum (never lowered, so host threads with different search ranges cannot undo each
+// other), and the occupancy of the last (bytes) is cached per device.  One static KernelState per template
+// instantiation of a launch function.
+#include <mutex>
+#define JMME_MAX_DEVICES 64
+struct KernelState {
+    std::mutex mu;
+    bool attr_set[JMME_MAX_DEVICES] = {};
+    size_t bytes[JMME_MAX_DEVICES] = {};
+    int occ[JMME_MAX_DEVICES] = {};
+};
+template <class Kern>
+cudaError_t jmme_kernel_occupancy(Kern kern, KernelState &ks, int threads, size_t bytes, int *occ_out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= JMME_MAX_DEVICES) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(ks.mu);
+    if (!ks.attr_set[dev]) {
+        int optin = 0;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) return e;
+        ks.attr_set[dev] = true;
+    }
+    if (ks.bytes[dev] != bytes || ks.occ[dev] == 0) {
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, bytes);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        ks.bytes[dev] = bytes; ks.occ[dev] = occ;
+    }
+    *occ_out = ks.occ[dev];
+    return cudaSuccess;
+}
+// name of the integer-search kernel instantiation a launch function picked (jmme_last_kernel); per host thread
+char *jmme_kernel_name_buf();
+#define JMME_KNAME_LEN 192
 
 // Programmatic dependent launch (sm_90+).  pdl_trigger: the next kernel of the stream may start its prologue;
 // pdl_wait: results of the previous kernel are complete and visible from here on.  Both are no-ops for a
@@ -101,6 +146,9 @@ __device__ __forceinline__ int d_ref_cost(int f, int rdopt, int ref)
     return ref ? (int)((2ll * f) >> 16) : 0;
 }
 __device__ __forceinline__ int d_clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// Predictor components as the kernels use them: the host entry points refuse |pred| > JMME_MAX_PRED_QPEL, the
+// device-pointer entry points cannot look, so every load clamps (keeps se_bits sums inside the rate tables).
+__device__ __forceinline__ int d_pred(int v) { return d_clamp(v, -JMME_MAX_PRED_QPEL, JMME_MAX_PRED_QPEL); }
 
 // 4 absolute byte differences summed and accumulated: one VABSDIFF4.U8.ACC
 __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c)

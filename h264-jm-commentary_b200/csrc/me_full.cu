@@ -7,6 +7,8 @@
 // kernel is the plain, correct form (thread = candidate, VABSDIFF4 on unaligned words fetched through
 // L1), kept off the headline path.  Conventions: DESIGN.md §2 (spiral order, strict <, 16x16 bonus;
 // no (0,0) pre-test in FULL mode).
+#include <cstdio>
+
 #include "jmme_dev.cuh"
 
 namespace {
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
     for (int b = 0; b < JMME_NBLK; b++) {
         if (!((P.blocktype_mask >> c_blk_type[b]) & 1)) continue;
         const int bx = c_blk_x[b], by = c_blk_y[b], bw4 = c_blk_w[b] >> 2, bh = c_blk_h[b];
-        const int px = pr ? pr[2 * (npb == 1 ? 0 : b)] : 0, py = pr ? pr[2 * (npb == 1 ? 0 : b) + 1] : 0;
+        const int px = pr ? d_pred(pr[2 * (npb == 1 ? 0 : b)]) : 0, py = pr ? d_pred(pr[2 * (npb == 1 ? 0 : b) + 1]) : 0;
         const int cx = d_clamp(px / 4, -R, R), cy = d_clamp(py / 4, -R, R);
         const int bonus = b == 0 ? bonus16 : 0;
         unsigned long long best = ~0ull;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
     if (tid < JMME_NBLK && ((P.blocktype_mask >> c_blk_type[tid]) & 1)) {
         const unsigned long long v = s_best[tid];
         const unsigned key = (unsigned)v;
-        const int px = pr ? pr[2 * (npb == 1 ? 0 : tid)] : 0, py = pr ? pr[2 * (npb == 1 ? 0 : tid) + 1] : 0;
+        const int px = pr ? d_pred(pr[2 * (npb == 1 ? 0 : tid)]) : 0, py = pr ? d_pred(pr[2 * (npb == 1 ? 0 : tid) + 1]) : 0;
         const int cx = d_clamp(px / 4, -R, R), cy = d_clamp(py / 4, -R, R);
         BlkRes r;
         r.mvx = (int16_t)(4 * (cx + P.spiral_xy[2 * (key - 1)]));
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
 cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st)
 {
     const int n_items = d_n_units(P) * P.num_refs;
+    snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN, "me_full_kernel");
     me_full_kernel<<<n_items, 128, 0, st>>>(P);
     return cudaGetLastError();
 }

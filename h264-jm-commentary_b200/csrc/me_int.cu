@@ -26,6 +26,8 @@
 //              41 running minima per thread, then CREDUX.MIN per warp and shared atomicMin per CTA
 //   MV (0,0)   JM's "(0,0) first" pre-test (!rdopt) is the key table entry of that candidate set
 //              to 0 for the item; the 16x16 (0,0) bonus is one extra 16x16 evaluation by warp 0
+#include <cstdio>
+
 #include "jmme_dev.cuh"
 
 namespace {
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
         it.mby = it.mb / P.mb_w;
         it.mbx = it.mb - it.mby * P.mb_w;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
-        const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
+        const int p16x = pr ? d_pred(pr[0]) : 0, p16y = pr ? d_pred(pr[1]) : 0;
         it.cx = d_clamp(p16x / 4, -R, R);
         it.cy = d_clamp(p16y / 4, -R, R);
     };
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         for (int i = tid; i < NPB * ncols; i += NW * 32) {
             const int b = i / ncols, o = i - b * ncols;
-            const int px = pr ? pr[2 * b] : 0, py = pr ? pr[2 * b + 1] : 0;
+            const int px = pr ? d_pred(pr[2 * b]) : 0, py = pr ? d_pred(pr[2 * b + 1]) : 0;
             s_bx[i] = (uint8_t)d_se_bits(4 * (it.cx + o - R) - px);
             s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + o - R) - py);
         }
@@ -363,21 +365,12 @@ cudaError_t launch_one(const SearchParams &P, int num_sms, cudaStream_t st)
     SmemLayout<PER_BLOCK> L(P.R);
     size_t bytes = (size_t)L.total_words * 4;
     auto kern = me_int_kernel<K, NW, MINB, PER_BLOCK, ONLY16, RS_CT>;
-    // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
-    static thread_local int c_dev = -1, c_occ = 0;
-    static thread_local size_t c_bytes = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    static KernelState ks;                               // shared-memory opt-in and occupancy, per device
+    int c_occ = 0;
+    cudaError_t e = jmme_kernel_occupancy(kern, ks, NW * 32, bytes, &c_occ);
     if (e != cudaSuccess) return e;
-    if (dev != c_dev || bytes != c_bytes) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) return cudaErrorLaunchOutOfResources;
-        c_dev = dev; c_bytes = bytes; c_occ = occ;
-    }
+    snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN, "me_int_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,ONLY16=%d,RS_CT=%d>", K, NW,
+             MINB, (int)PER_BLOCK, (int)ONLY16, RS_CT);
     int n_items = d_n_units(P) * P.num_refs;
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);

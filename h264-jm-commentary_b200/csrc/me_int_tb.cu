@@ -14,6 +14,7 @@
 //   banks        the window row stride is == 2 (mod 4) words, so the B lanes (8 rows further down)
 //                sit 16 banks away from the T lanes: 16 + 16 consecutive banks, conflict-free
 //   K            up to 8 candidates per run: 4*(7+K)/K row words per thread and candidate
+#include <cstdio>
 #include <cstdlib>
 
 #include <cooperative_groups.h>
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
                     (uint32_t)(uint16_t)s_wpred[2 * tid] | ((uint32_t)(uint16_t)s_wpred[2 * tid + 1] << 16);
             pr = s_wpred;
         }
-        const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
+        const int p16x = pr ? d_pred(pr[0]) : 0, p16y = pr ? d_pred(pr[1]) : 0;
         it.cx = d_clamp(p16x / 4, -R, R);
         it.cy = d_clamp(p16y / 4, -R, R);
     };
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         const int16_t *pr = WP ? s_wpred : (P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr);
         if constexpr (!PER_BLOCK) {
             for (int i = tid; i < ncols; i += NW * 32) {
-                const int px = pr ? pr[0] : 0, py = pr ? pr[1] : 0;
+                const int px = pr ? d_pred(pr[0]) : 0, py = pr ? d_pred(pr[1]) : 0;
                 s_bx[i] = (uint8_t)d_se_bits(4 * (it.cx + i - R) - px);
                 s_by[i] = (uint8_t)d_se_bits(4 * (it.cy + i - R) - py);
             }
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int b = 4 * q + j, gb = b < NL ? kGT[b] + hf * kDL[b] : 0;
-                        px[hf][j] = pr[2 * gb]; py[hf][j] = pr[2 * gb + 1];
+                        px[hf][j] = d_pred(pr[2 * gb]); py[hf][j] = d_pred(pr[2 * gb + 1]);
                     }
                 for (int row = r0; row < 2 * ncols; row += TPR) {
                     const int hf = row >= ncols, o = row - (hf ? ncols : 0);
@@ -536,21 +537,13 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
     TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     size_t bytes = (size_t)L.total_words * 4;
     auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL, WP, LIN>;
-    // shared-memory opt-in and occupancy are queried once per (device, size) and instantiation
-    static thread_local int c_dev = -1, c_occ = 0;
-    static thread_local size_t c_bytes = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    static KernelState ks;                               // shared-memory opt-in and occupancy, per device
+    int c_occ = 0;
+    cudaError_t e = jmme_kernel_occupancy(kern, ks, NW * 32, bytes, &c_occ);
     if (e != cudaSuccess) return e;
-    if (dev != c_dev || bytes != c_bytes) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, bytes);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) return cudaErrorLaunchOutOfResources;
-        c_dev = dev; c_bytes = bytes; c_occ = occ;
-    }
+    snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN,
+             "me_int_tb_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,RS_CT=%d,KEYG=%d,KRTAB=%d,NMB=%d,CL=%d,WP=%d,LIN=%d>", K, NW, MINB,
+             (int)PER_BLOCK, RS_CT, (int)KEYG, (int)KRTAB, NMB, CL, (int)WP, (int)LIN);
     int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
     if (CL > 1 || P.pdl) {
         cudaLaunchConfig_t cfg = {};

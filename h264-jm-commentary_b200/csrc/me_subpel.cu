@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
         if (P.pred) {
             const int npb = P.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
             const int16_t *pr = P.pred + ((size_t)ref * n_mb + mb) * npb * 2 + (npb == 1 ? 0 : 2 * b);
-            px = pr[0]; py = pr[1];
+            px = d_pred(pr[0]); py = d_pred(pr[1]);
         }
     }
     // reference position of this cell at MV (0,0), in padded-plane coordinates

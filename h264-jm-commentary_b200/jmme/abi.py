@@ -11,6 +11,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+ABI_VERSION = 3          # JMME_ABI_VERSION of include/jmme.h
 BLOCKS_PER_MB = 41
 MAX_REFS = 4
 MAX_GPUS = 8
@@ -45,6 +46,12 @@ class Params(C.Structure):
                                                      ("async_reference", C.c_int32), ("slice_rows", C.c_int32)]
 
 
+class Tuning(C.Structure):
+    """jmme_tuning: launch knobs of the product library, 0 = default."""
+    _fields_ = [(n, C.c_int32) for n in ("variant", "group", "cluster", "table_rate", "wave_step", "no_pdl",
+                                         "pipe_parts")] + [("reserved", C.c_int32 * 9)]
+
+
 MBRESULT_DTYPE = np.dtype([("mv", np.int16, (BLOCKS_PER_MB, 2)), ("cost", np.int32, (BLOCKS_PER_MB,)),
                            ("ref_idx", np.int8, (BLOCKS_PER_MB,)), ("reserved", np.int8, (3,))], align=True)
 assert MBRESULT_DTYPE.itemsize == 372, MBRESULT_DTYPE.itemsize
@@ -54,7 +61,7 @@ EXPORTS = [
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
     "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
     "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev",
-    "jmme_launch_count",
+    "jmme_launch_count", "jmme_set_tuning", "jmme_get_tuning", "jmme_last_kernel",
     "jmme_set_profiling",
     "jmme_get_kernel_times", "jmme_InitMotionSearchModule", "jmme_SetMotionVectorPredictor",
     "jmme_commit_field", "jmme_predict_frame",
@@ -103,6 +110,9 @@ class Lib:
             "jmme_push_stripe_dev": (i32, [vp, vp, C.POINTER(vp), i32, vp]),
             "jmme_set_peer_fields_dev": (i32, [vp, C.POINTER(vp), i32]),
             "jmme_launch_count": (C.c_longlong, [vp]),
+            "jmme_set_tuning": (i32, [vp, C.POINTER(Tuning)]),
+            "jmme_get_tuning": (i32, [vp, C.POINTER(Tuning)]),
+            "jmme_last_kernel": (C.c_char_p, [vp]),
             "jmme_set_profiling": (i32, [vp, i32]),
             "jmme_get_kernel_times": (i32, [vp, C.POINTER(C.c_float)]),
             "jmme_InitMotionSearchModule": (i32, [i32, i32, pi32, i32, pi32, pi16, pi16]),
@@ -152,8 +162,12 @@ class Lib:
     def lambda_factor(self, qp, rdopt):
         return self.dll.jmme_lambda_factor(qp, rdopt)
 
-    def context(self, **kw):
-        return Context(self, self.default_params(**kw))
+    def context(self, tuning=None, **kw):
+        """tuning: dict of jmme_tuning fields applied right after jmme_create (product library only)."""
+        ctx = Context(self, self.default_params(**kw))
+        if tuning:
+            ctx.set_tuning(**tuning)
+        return ctx
 
     # ---- leaf entry points ---------------------------------------------------------------
     def init_motion_search_module(self, R, max_mvd=64, n_refbits=16):
@@ -323,6 +337,23 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.dll.jmme_launch_count(self.handle))
+
+    def set_tuning(self, **kw):
+        t = Tuning()
+        for k, v in kw.items():
+            if not hasattr(t, k):
+                raise AttributeError(k)
+            setattr(t, k, int(v))
+        self.lib.check(self.lib.dll.jmme_set_tuning(self.handle, C.byref(t)), self.handle)
+
+    def get_tuning(self):
+        t = Tuning()
+        self.lib.check(self.lib.dll.jmme_get_tuning(self.handle, C.byref(t)), self.handle)
+        return {n: getattr(t, n) for n, _ in Tuning._fields_ if n != "reserved"}
+
+    def last_kernel(self):
+        """Integer-search kernel instantiation the last search launched (jmme_last_kernel)."""
+        return self.lib.dll.jmme_last_kernel(self.handle).decode()
 
     def set_profiling(self, enable=True):
         self.lib.check(self.lib.dll.jmme_set_profiling(self.handle, int(enable)), self.handle)

@@ -40,11 +40,13 @@
 extern "C" {
 #endif
 
-#define JMME_ABI_VERSION     2
+#define JMME_ABI_VERSION     3
 #define JMME_BLOCKS_PER_MB   41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 */
 #define JMME_MAX_REFS        4
 #define JMME_MAX_SEARCH_RANGE 64
 #define JMME_MAX_GPUS        8
+#define JMME_MAX_PRED_QPEL   2048 /* |predictor component| limit, quarter-pel: host entry points refuse larger */
+                                  /* values (JMME_ERR_PARAM); the device-pointer entry points clamp to it       */
 
 /* error codes: 0 = OK, negative otherwise; the library never exits or aborts */
 #define JMME_OK               0
@@ -170,6 +172,28 @@ int jmme_push_stripe_dev(jmme_ctx *ctx, const void *d_field_local, void *const *
 int jmme_set_peer_fields_dev(jmme_ctx *ctx, void *const *d_field_peers, int n_peers);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 int64_t jmme_launch_count(const jmme_ctx *ctx);
+
+/* Launch tuning of the product library.  Explicit per-context state (no environment variables): every field
+ * 0 = the library's measured default.  Results never depend on it — only which instantiation
+ * of the kernels runs and how the work is cut; the parity tests sweep it.  jmme_set_tuning applies to later
+ * searches of the context (and to every sub-context of an n_gpus parent). */
+typedef struct jmme_tuning {
+    int32_t variant;         /* integer-search kernel: 10*K + launch shape (me_int.cu / me_int_tb.cu); 0 = by range */
+    int32_t group;           /* zero-predictor items of 1, 2 or 4 adjacent MBs sharing one window; 0 = default       */
+    int32_t cluster;         /* largest thread-block cluster of a wavefront step: 1, 2, 4; 0 = default (4)           */
+    int32_t table_rate;      /* 1: per-block rate always from the table (no linear-rate form for integer lambda)    */
+    int32_t wave_step;       /* 1: in-frame median predictors always by the separate wave_step kernel                */
+    int32_t no_pdl;          /* 1: no programmatic dependent launch between the kernels of a wavefront step         */
+    int32_t pipe_parts;      /* host path: the stripe is searched in this many parts on separate streams (1..4)      */
+    int32_t reserved[9];
+} jmme_tuning;
+int jmme_set_tuning(jmme_ctx *ctx, const jmme_tuning *t);
+int jmme_get_tuning(const jmme_ctx *ctx, jmme_tuning *t);      /* the values in effect (defaults resolved)         */
+/* Name and template arguments of the integer-search kernel the last search of this context launched, e.g.
+ * "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0>" ("" before the
+ * first search; the oracle returns "cpu-oracle").  The parity tests assert it so that a test of a BASELINE
+ * config provably ran the kernel the bench times. */
+const char *jmme_last_kernel(const jmme_ctx *ctx);
 /* Per-kernel device times.  jmme_set_profiling(ctx,1) makes every later set_reference / search
  * bracket its kernels with CUDA events on the launching stream; jmme_get_kernel_times waits for
  * the last bracket and returns milliseconds of the most recent

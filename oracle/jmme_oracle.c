@@ -29,7 +29,7 @@
 #endif
 
 #define MAX_MVD 4096                 /* |cand - pred| in quarter-pel units stays below this */
-#define MAX_PRED 2048                /* |pred| limit, quarter-pel                            */
+#define MAX_PRED JMME_MAX_PRED_QPEL   /* |pred| limit, quarter-pel                            */
 
 static int g_threads = 1;            /* worker threads, see jmme_oracle_set_threads */
 
@@ -345,6 +345,9 @@ int jmme_set_peer_fields_dev(jmme_ctx *c, void *const *p, int n)
 int jmme_push_stripe_dev(jmme_ctx *c, const void *l, void *const *p, int n, void *st)
 { (void)l; (void)p; (void)n; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
 int64_t jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }
+int jmme_set_tuning(jmme_ctx *c, const jmme_tuning *t) { (void)t; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no launch tuning"); }
+int jmme_get_tuning(const jmme_ctx *c, jmme_tuning *t) { (void)c; if (t) memset(t, 0, sizeof *t); return JMME_ERR_UNSUPPORTED; }
+const char *jmme_last_kernel(const jmme_ctx *c) { (void)c; return "cpu-oracle"; }
 int jmme_set_profiling(jmme_ctx *c, int e) { (void)e; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no kernels"); }
 int jmme_get_kernel_times(jmme_ctx *c, float ms[4]) { (void)ms; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no kernels"); }
 
@@ -837,10 +840,14 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
         c->fref = (int8_t *)malloc((size_t)nmb * 16);
         if (!c->med_pred || !c->fmv || !c->fref) return JMME_ERR_NOMEM;
     }
-    if (pred && c->p.pred_policy != JMME_PRED_ZERO) {
-        size_t i, n = (size_t)c->p.num_refs * nmb * npb * 2;
-        for (i = 0; i < n; i++)
-            if (pred[i] > MAX_PRED || pred[i] < -MAX_PRED) return set_err(c, JMME_ERR_PARAM, "pred out of range");
+    if (pred && c->p.pred_policy != JMME_PRED_ZERO) {       /* only the stripe's MB rows are read */
+        const size_t per_mb = (size_t)npb * 2, n = (size_t)(c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w * per_mb;
+        size_t i;
+        for (r = 0; r < c->p.num_refs; r++) {
+            const int16_t *q = pred + ((size_t)r * nmb + (size_t)c->p.mb_row_begin * c->mb_w) * per_mb;
+            for (i = 0; i < n; i++)
+                if (q[i] > MAX_PRED || q[i] < -MAX_PRED) return set_err(c, JMME_ERR_PARAM, "pred out of range");
+        }
     }
     if (c->p.pred_policy == JMME_PRED_ZERO) pred = NULL;
     cur = (uint8_t *)malloc((size_t)c->w16 * c->h16);

@@ -6,6 +6,8 @@ import subprocess
 
 import pytest
 
+from jmme import abi
+
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 
 
@@ -21,7 +23,7 @@ def build_and_run(tmp_path, libdir, libname):
 
 def test_c89_demo_against_the_oracle(oracle, tmp_path):
     out = build_and_run(tmp_path, ROOT / "oracle", "jmme_oracle")
-    assert out[0].startswith("backend cpu-oracle, ABI 2")
+    assert out[0].startswith(f"backend cpu-oracle, ABI {abi.ABI_VERSION}")
     assert "policy 0: 24 MBs" in out[1] and "policy 3: 24 MBs" in out[2]
     # the planted integer displacement is found by the inner macroblocks
     assert int(out[1].split("found in ")[1].split(",")[0]) >= 8
@@ -31,5 +33,5 @@ def test_c89_demo_against_the_oracle(oracle, tmp_path):
 def test_c89_demo_against_the_cuda_library(cuda, oracle, tmp_path):
     ref = build_and_run(tmp_path, ROOT / "oracle", "jmme_oracle")
     got = build_and_run(tmp_path, ROOT / "h264-jm-commentary_b200" / "csrc", "jmme_cuda")
-    assert got[0].startswith("backend cuda-sm_100a, ABI 2")
+    assert got[0].startswith(f"backend cuda-sm_100a, ABI {abi.ABI_VERSION}")
     assert got[1:] == ref[1:]

@@ -1,6 +1,6 @@
 """GPU parity: libjmme_cuda.so (through the C ABI) against the CPU oracle on the same seeded inputs.
 Bit-exact: MV, ref_idx and cost of all 41 blocks of every macroblock; every byte of the 16 planes."""
-import os
+import ctypes
 
 import numpy as np
 import pytest
@@ -12,12 +12,40 @@ pytestmark = pytest.mark.gpu
 BLOCKS = abi.block_table()
 
 
-def run(lib, cur, refs, pred=None, per_ref=False, **kw):
+LAST = {}          # what the last CUDA run() launched: kernel name (jmme_last_kernel) and tuning in effect
+
+
+def run(lib, cur, refs, pred=None, per_ref=False, tuning=None, **kw):
+    """tuning: jmme_tuning fields for the product library (explicit per-context state; the oracle has none)."""
     h, w = cur.shape
-    with lib.context(width=w, height=h, num_refs=len(refs), **kw) as ctx:
+    is_cuda = lib.backend().startswith("cuda")
+    with lib.context(width=w, height=h, num_refs=len(refs), tuning=tuning if is_cuda else None, **kw) as ctx:
         for i, r in enumerate(refs):
             ctx.set_reference(i, r)
-        return ctx.search_frame(cur, pred, per_ref)
+        out = ctx.search_frame(cur, pred, per_ref)
+        if is_cuda:
+            LAST["kernel"], LAST["tuning"] = ctx.last_kernel(), ctx.get_tuning()
+        return out
+
+
+def oracle_threads(oracle, n):
+    """All host threads for the big oracle runs (0 = every core), 1 = back to the JM-like single thread."""
+    oracle.dll.jmme_oracle_set_threads.restype = ctypes.c_int
+    return oracle.dll.jmme_oracle_set_threads(n)
+
+
+DEFAULT_KERNELS = {
+    "config1": "me_int_kernel<K=3,NW=4,MINB=3,PER_BLOCK=0,ONLY16=1,RS_CT=0>",
+    "config2": "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0>",
+    "config3": "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0>",
+    "config4": "me_int_kernel<K=5,NW=8,MINB=1,PER_BLOCK=0,ONLY16=0,RS_CT=144>",
+}
+
+
+def assert_default_kernel(prefix):
+    """The run used the library's default launch (no forced variant) and the kernel family the bench times."""
+    assert LAST["tuning"]["variant"] == 0, LAST
+    assert LAST["kernel"].startswith(prefix), LAST
 
 
 def assert_same(got, exp, what=""):
@@ -37,7 +65,7 @@ def assert_same(got, exp, what=""):
 
 def test_library_is_the_cuda_backend(cuda):
     assert cuda.backend() == "cuda-sm_100a"
-    assert cuda.dll.jmme_abi_version() == 2
+    assert cuda.dll.jmme_abi_version() == abi.ABI_VERSION
 
 
 def test_tables_leaf(cuda, oracle):
@@ -145,10 +173,9 @@ CASES = [
 @pytest.mark.parametrize("variant", [0, 32, 47, 69, 51])
 @pytest.mark.parametrize("w,h,R,kw", CASES)
 def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
-    os.environ["JMME_VARIANT"] = str(variant)
     for kind, seed in (("texture", 1), ("noise", 2)):
         cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R, kind=kind)
-        got = run(cuda, cur, refs, search_range=R, **kw)
+        got = run(cuda, cur, refs, search_range=R, tuning=dict(variant=variant), **kw)
         exp = run(oracle, cur, refs, search_range=R, **kw)
         assert_same(got, exp, f"{w}x{h} R={R} {kw} {kind}")
 
@@ -157,12 +184,11 @@ def test_search_frame_matches_oracle(cuda, oracle, w, h, R, kw, variant):
 @pytest.mark.parametrize("policy,nb", [(abi.PRED_PER_MB, 1), (abi.PRED_PER_BLOCK, 41)])
 @pytest.mark.parametrize("rdopt", [0, 1])
 def test_predictor_policies(cuda, oracle, policy, nb, rdopt, variant):
-    os.environ["JMME_VARIANT"] = str(variant)
     w, h, R = 64, 48, 8
     cur, refs = synth.frame_pair(w, h, seed=4, search_range=R, num_refs=2)
     pred = synth.random_pred(2, 12, nb, seed=7 + rdopt, max_qpel=4 * R + 30)   # some centres get clamped
     kw = dict(search_range=R, qp=31, rdopt=rdopt, pred_policy=policy, subpel=1)
-    g, gp = run(cuda, cur, refs, pred, True, **kw)
+    g, gp = run(cuda, cur, refs, pred, True, tuning=dict(variant=variant), **kw)
     o, op = run(oracle, cur, refs, pred, True, **kw)
     assert_same(gp, op, "per-ref")
     assert_same(g, o, "best-ref")
@@ -236,16 +262,24 @@ def test_config1_cif_16x16_full_search(cuda, oracle):
     cur, refs = synth.frame_pair(352, 288, seed=1, search_range=16)
     kw = dict(search_range=16, blocktype_mask=abi.MASK_16x16, search_mode=abi.SEARCH_FULL, qp=28)
     assert_same(run(cuda, cur, refs, **kw), run(oracle, cur, refs, **kw), "config 1")
+    assert_default_kernel("me_int_kernel<")
 
 
-def test_config2_720p_stripe_against_oracle_and_planted_motion(cuda, oracle):
-    """BASELINE config 2 at full size on the GPU; oracle on a 4-row stripe; planted motion everywhere."""
+def test_config2_720p_whole_frame_against_oracle_and_planted_motion(cuda, oracle):
+    """BASELINE config 2 at full size: every MB of the frame against the oracle (all host threads), under the
+    default kernel; planted motion everywhere."""
     w, h, R = 1280, 720, 32
     cur, refs = synth.frame_pair(w, h, seed=1, search_range=R)
     kw = dict(search_range=R, qp=28)
     g = run(cuda, cur, refs, **kw)
-    o = run(oracle, cur, refs, mb_row_begin=20, mb_row_end=24, **kw)
-    assert_same(g[20 * 80:24 * 80], o[20 * 80:24 * 80], "720p rows 20..23")
+    assert_default_kernel("me_int_tb_kernel<")
+    oracle_threads(oracle, 0)
+    try:
+        o = run(oracle, cur, refs, **kw)
+    finally:
+        oracle_threads(oracle, 1)
+    assert len(g) == 80 * 45
+    assert_same(g, o, "720p whole frame")
     ref = synth.gen_luma(w, h, 5, "noise")
     dx, dy = -19, 27
     cur2 = np.roll(ref, (-dy, -dx), axis=(0, 1))
@@ -257,45 +291,74 @@ def test_config2_720p_stripe_against_oracle_and_planted_motion(cuda, oracle):
     assert np.all(inner["cost"] == exp)
 
 
-def test_config3_1080p_subpel_properties(cuda, oracle):
-    """BASELINE config 3 at full size: a stripe matches the oracle (including the rows replicated from
-    1080 to 1088) and stripes reproduce the whole-frame result."""
+@pytest.mark.parametrize("seed", [1, 2])
+def test_config3_1080p_whole_frame_against_oracle(cuda, oracle, seed):
+    """BASELINE config 3 (the headline) at full size: all 8160 MBs x 41 blocks against the oracle (all host
+    threads; includes the rows replicated from 1080 to 1088), under the default kernels; seed 1 is the frame
+    pair bench.py times.  Stripes reproduce the whole-frame result."""
     w, h, R = 1920, 1080, 32
-    cur, refs = synth.frame_pair(w, h, seed=2, search_range=R)
+    cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R)
     kw = dict(search_range=R, qp=28, subpel=1)
     g = run(cuda, cur, refs, **kw)
+    assert_default_kernel("me_int_tb_kernel<")
     assert len(g) == 120 * 68
-    o = run(oracle, cur, refs, mb_row_begin=66, mb_row_end=68, **kw)
-    assert_same(g[66 * 120:], o[66 * 120:], "1080p rows 66..67")
+    oracle_threads(oracle, 0)
+    try:
+        o = run(oracle, cur, refs, **kw)
+    finally:
+        oracle_threads(oracle, 1)
+    assert_same(g, o, f"1080p whole frame, seed {seed}")
     s = run(cuda, cur, refs, mb_row_begin=30, mb_row_end=41, **kw)
     assert s[30 * 120:41 * 120].tobytes() == g[30 * 120:41 * 120].tobytes()
 
 
-@pytest.mark.parametrize("w,h,subpel,row", [(1920, 1080, 0, 33), (3840, 2160, 1, 134)])
-def test_config4_and_config5_r64_four_refs(cuda, oracle, w, h, subpel, row):
+@pytest.mark.parametrize("w,h,subpel", [(1920, 1080, 0), (3840, 2160, 1)])
+def test_config4_and_config5_r64_four_refs(cuda, oracle, w, h, subpel):
     """BASELINE configs 4 (1080p, integer) and 5 (4K, quarter-pel): R = 64, 4 references, at full size on the
-    GPU; the oracle (all host threads) on one MB row; two stripes reproduce the whole-frame field."""
-    import ctypes
+    GPU under the default R = 64 kernel; the oracle (all host threads) on ten MB rows spread over the frame
+    — top, bottom, the seams of the 2/4/8-rank stripe partitions and rows in between; two stripes reproduce the
+    whole-frame field."""
     R, nref = 64, 4
     cur, refs = synth.frame_pair(w, h, seed=4, search_range=R, num_refs=nref)
     kw = dict(search_range=R, qp=28, subpel=subpel)
     mb_w, mb_h = (w + 15) // 16, (h + 15) // 16
     g, gp = run(cuda, cur, refs, None, True, **kw)
-    oracle.dll.jmme_oracle_set_threads.restype = ctypes.c_int
-    oracle.dll.jmme_oracle_set_threads(0)
+    assert LAST["tuning"]["variant"] == 0 and "R64" not in LAST["kernel"], LAST
+    default_kernel = LAST["kernel"]
+    per8 = -(-mb_h // 8)
+    rows = sorted({0, 1, per8 - 1, per8, 2 * per8, 4 * per8 - 1, 4 * per8, 6 * per8, mb_h - 2, mb_h - 1})
+    oracle_threads(oracle, 0)
     try:
-        o, op = run(oracle, cur, refs, None, True, mb_row_begin=row, mb_row_end=row + 1, **kw)
+        for row in rows:
+            o, op = run(oracle, cur, refs, None, True, mb_row_begin=row, mb_row_end=row + 1, **kw)
+            sl = slice(row * mb_w, (row + 1) * mb_w)
+            assert_same(gp[:, sl], op[:, sl], f"per-ref row {row}")
+            assert_same(g[sl], o[sl], f"best row {row}")
     finally:
-        oracle.dll.jmme_oracle_set_threads(1)
-    sl = slice(row * mb_w, (row + 1) * mb_w)
-    assert_same(gp[:, sl], op[:, sl], f"per-ref row {row}")
-    assert_same(g[sl], o[sl], f"best row {row}")
+        oracle_threads(oracle, 1)
     assert len(np.unique(g["ref_idx"])) > 1                           # more than one reference wins somewhere
     half = mb_h // 2
     s0 = run(cuda, cur, refs, mb_row_begin=0, mb_row_end=half, **kw)
     s1 = run(cuda, cur, refs, mb_row_begin=half, mb_row_end=mb_h, **kw)
+    assert LAST["kernel"] == default_kernel
     assert s0[:half * mb_w].tobytes() == g[:half * mb_w].tobytes()
     assert s1[half * mb_w:].tobytes() == g[half * mb_w:].tobytes()
+
+
+def test_default_kernels_of_the_baseline_configs(cuda):
+    """Which integer-search instantiation each BASELINE config launches by default (jmme_last_kernel) — the
+    names bench.py prints in its JSON line (`roofline.kernel_instance`).  Updated whenever a default changes."""
+    expect = {
+        (352, 288, 16, 1, abi.MASK_16x16, abi.SEARCH_FULL): DEFAULT_KERNELS["config1"],
+        (1280, 720, 32, 1, abi.MASK_ALL, abi.SEARCH_FASTFULL): DEFAULT_KERNELS["config2"],
+        (1920, 1080, 32, 1, abi.MASK_ALL, abi.SEARCH_FASTFULL): DEFAULT_KERNELS["config3"],
+        (1920, 1080, 64, 4, abi.MASK_ALL, abi.SEARCH_FASTFULL): DEFAULT_KERNELS["config4"],
+    }
+    for (w, h, R, nref, mask, mode), name in expect.items():
+        cur, refs = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=nref)
+        # a two-row stripe is enough to see which kernel is picked
+        run(cuda, cur, refs, search_range=R, blocktype_mask=mask, search_mode=mode, mb_row_begin=2, mb_row_end=4)
+        assert LAST["kernel"] == name, (w, h, R, LAST)
 
 
 def test_launch_counter_counts_kernels(cuda):
@@ -396,12 +459,16 @@ def test_randomised_configurations(cuda, oracle):
 
 
 # ---- JMME_PRED_MEDIAN: predictor loop closed inside the frame (wavefront on the GPU, raster order in the oracle) ----
-def run_median(lib, cur, refs, **kw):
+def run_median(lib, cur, refs, tuning=None, **kw):
     h, w = cur.shape
-    with lib.context(width=w, height=h, num_refs=len(refs), pred_policy=abi.PRED_MEDIAN, **kw) as ctx:
+    is_cuda = lib.backend().startswith("cuda")
+    with lib.context(width=w, height=h, num_refs=len(refs), pred_policy=abi.PRED_MEDIAN,
+                     tuning=tuning if is_cuda else None, **kw) as ctx:
         for i, r in enumerate(refs):
             ctx.set_reference(i, r)
         out, opr = ctx.search_frame(cur, None, True)
+        if is_cuda:
+            LAST["kernel"], LAST["tuning"] = ctx.last_kernel(), ctx.get_tuning()
         return out, opr, ctx.get_predictors()
 
 
@@ -434,11 +501,8 @@ def test_in_frame_median_kernel_variants(cuda, oracle, variant):
     w, h, R = 96, 64, 8
     cur, refs = synth.frame_pair(w, h, seed=3, search_range=R)
     kw = dict(search_range=R, slice_rows=2, qp=30, subpel=1)
-    os.environ["JMME_VARIANT"] = str(variant)
-    try:
-        g, _, gpred = run_median(cuda, cur, refs, **kw)
-    finally:
-        del os.environ["JMME_VARIANT"]
+    g, _, gpred = run_median(cuda, cur, refs, tuning=dict(variant=variant), **kw)
+    assert LAST["tuning"]["variant"] == variant
     o, _, opred = run_median(oracle, cur, refs, **kw)
     assert np.array_equal(gpred, opred)
     assert_same(g, o, f"variant {variant}")
@@ -550,22 +614,16 @@ def test_randomised_in_frame_median(cuda, oracle):
 def test_in_frame_median_tall_frame(cuda, oracle, force_wave_step):
     """135 MB rows (4K height): more MBs per wavefront step than one chunk of wave_step_kernel (128) and more
     (MB, ref) items than SMs; both predictor paths (search-kernel prologue / wave_step_kernel)."""
-    import ctypes
     w, h, R = 256, 2160, 6
     cur, refs = synth.frame_pair(w, h, seed=8, search_range=R, num_refs=2)
     kw = dict(search_range=R, slice_rows=1, qp=30, subpel=1)
-    if force_wave_step:
-        os.environ["JMME_WAVE_STEP"] = "1"
-    try:
-        g, gp, gpred = run_median(cuda, cur, refs, **kw)
-    finally:
-        os.environ.pop("JMME_WAVE_STEP", None)
-    oracle.dll.jmme_oracle_set_threads.restype = ctypes.c_int
-    oracle.dll.jmme_oracle_set_threads(0)
+    g, gp, gpred = run_median(cuda, cur, refs, tuning=dict(wave_step=force_wave_step), **kw)
+    assert LAST["kernel"].startswith("me_int_tb_kernel<") and ("WP=0" if force_wave_step else "WP=1") in LAST["kernel"], LAST
+    oracle_threads(oracle, 0)
     try:
         o, op, opred = run_median(oracle, cur, refs, **kw)
     finally:
-        oracle.dll.jmme_oracle_set_threads(1)
+        oracle_threads(oracle, 1)
     assert np.array_equal(gpred, opred)
     assert_same(gp, op, "per-ref")
     assert_same(g, o, "best")

@@ -3,11 +3,12 @@ import numpy as np
 import pytest
 
 import refimpl
+from jmme import abi
 
 
 def test_backend_and_abi(oracle):
     assert oracle.backend() == "cpu-oracle"
-    assert oracle.dll.jmme_abi_version() == 2
+    assert oracle.dll.jmme_abi_version() == abi.ABI_VERSION
 
 
 def test_mvbits_known_answers(oracle):

@@ -1,7 +1,6 @@
 """Quick device-resident timing of the search at a BASELINE config for several K (tuning aid)."""
 import argparse
 import json
-import os
 import pathlib
 import sys
 
@@ -23,6 +22,7 @@ ap.add_argument("--mask", type=lambda s: int(s, 0), default=0xFE)
 ap.add_argument("--pred", type=int, default=0)
 ap.add_argument("--Ks", default="0,68,48,88,32,51")
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--group", type=int, default=0, help="jmme_tuning.group")
 ap.add_argument("--rows", type=int, default=0, help="search only the first N MB rows (stripe)")
 a = ap.parse_args()
 
@@ -31,10 +31,10 @@ cur, refs = synth.frame_pair(a.w, a.h, seed=1, search_range=a.R, num_refs=a.refs
 dcur = torch.from_numpy(cur).cuda()
 drefs = [torch.from_numpy(r).cuda() for r in refs]
 for K in [int(k) for k in a.Ks.split(",")]:
-    os.environ["JMME_VARIANT"] = str(K)
     for subpel in sorted({0, a.subpel}):
         s = DeviceSearch(lib, width=a.w, height=a.h, search_range=a.R, num_refs=a.refs, subpel=subpel,
-                         blocktype_mask=a.mask, pred_policy=a.pred, qp=28, mb_row_end=a.rows)
+                         blocktype_mask=a.mask, pred_policy=a.pred, qp=28, mb_row_end=a.rows,
+                         tuning=dict(variant=K, group=a.group))
         pred = None
         if a.pred:
             nb = 1 if a.pred == 1 else 41
@@ -58,6 +58,6 @@ for K in [int(k) for k in a.Ks.split(",")]:
         torch.cuda.synchronize()
         ms_ref = e0.elapsed_time(e1) / a.iters
         print(json.dumps(dict(K=K, subpel=subpel, w=a.w, h=a.h, R=a.R, refs=a.refs, mask=a.mask, pred=a.pred,
-                              ms_search=round(ms, 4), ms_set_reference=round(ms_ref, 4),
+                              ms_search=round(ms, 4), kernel=s.ctx.last_kernel(), ms_set_reference=round(ms_ref, 4),
                               rows=a.rows, mb_per_s=round((s.n_mb if not a.rows else a.rows * s.ctx.mb_w) / (ms * 1e-3)))), flush=True)
         s.close()
