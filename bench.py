@@ -318,30 +318,38 @@ def oracle_parity(args, fields):
     unit = slice_unit(args, mb_h)
     kw = dict(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP, **policy_kw(args))
 
-    def rows_of(seed, groups):
+    def rows_of(seed, spans, timing=None):
+        """oracle records of the MB-row spans [(rb, re)] of the frame pair of `seed` (one context per span: the stripe
+        of an oracle context is fixed at creation, and every context interpolates the whole reference)"""
         cur, ref_l = synth.frame_pair(w, h, seed=seed, search_range=R, num_refs=refs)
         out = {}
-        for g in groups:
-            rb, re = g * unit, min(mb_h, (g + 1) * unit)
+        for rb, re in spans:
             with orc.context(mb_row_begin=rb, mb_row_end=re, **kw) as c:
+                t0 = time.perf_counter()
                 for i, r in enumerate(ref_l):
                     c.set_reference(i, r)
+                t1 = time.perf_counter()
                 out[(rb, re)] = c.search_frame(cur)[rb * mb_w:re * mb_w]
+                if timing is not None:
+                    timing += [t1 - t0, time.perf_counter() - t1]
         return out
 
     try:
         n_groups = -(-mb_h // unit)
-        t0 = time.perf_counter()
-        first = rows_of(SEEDS[0], [n_groups // 2])              # calibration: one group of rows
-        t_group = time.perf_counter() - t0
-        budget = max(1, int(args.parity_seconds / max(t_group, 1e-6) / len(fields)))
-        if budget >= n_groups:
-            groups = list(range(n_groups))
+        g0 = n_groups // 2
+        tm = []
+        first = rows_of(SEEDS[0], [(g0 * unit, min(mb_h, (g0 + 1) * unit))], tm)       # calibration: one group of rows
+        t_ref, t_group = tm
+        budget = args.parity_seconds / len(fields)                                        # per seed
+        if t_ref + n_groups * t_group <= budget:
+            spans, first = [(0, mb_h)], {}                                                # the whole frame, one context
         else:
-            groups = sorted({round(i * (n_groups - 1) / max(budget - 1, 1)) for i in range(budget)})
+            n = max(1, int(budget / (t_ref + t_group)))
+            gs = sorted({round(i * (n_groups - 1) / max(n - 1, 1)) for i in range(n)})
+            spans = [(g * unit, min(mb_h, (g + 1) * unit)) for g in gs]
         checked = mism = 0
         for seed, field in fields.items():
-            exp = rows_of(seed, groups)
+            exp = rows_of(seed, spans)
             if seed == SEEDS[0]:
                 exp.update(first)
             for (rb, re), o in exp.items():
@@ -352,8 +360,9 @@ def oracle_parity(args, fields):
                                                  np.any(g["ref_idx"] != o["ref_idx"], axis=1))) or 1
     finally:
         orc.dll.jmme_oracle_set_threads(1)
+    whole = spans == [(0, mb_h)]
     par = {"mbs": checked, "mismatches": mism, "blocks_per_mb": 41, "seeds": list(fields),
-           "rows": "whole frame" if len(groups) == n_groups else f"{len(groups)} of {n_groups} row groups of {unit}, spread",
+           "rows": "whole frame" if whole else f"{len(spans)} of {n_groups} row groups of {unit} MB rows, spread over the frame",
            "checker": f"oracle/libjmme_oracle.so, {cores} threads, every MV / ref_idx / cost byte of the records"}
     if mism:
         raise SystemExit(f"bench.py: GPU field differs from the oracle: {json.dumps(par)}")

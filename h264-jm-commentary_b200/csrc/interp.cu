@@ -157,7 +157,24 @@ __global__ void pad_cur_kernel(const uint8_t *__restrict__ src, int w_in, int h_
     *(uint32_t *)(dst + (size_t)y * w16 + x) = v;
 }
 
+// chroma ME: a w x h picture replicated into a pw x ph plane with `pad` border samples on every side (pad = 0:
+// the current chroma padded to w16/2 x h16/2)
+__global__ void pad_plane_kernel(const uint8_t *__restrict__ src, int w, int h, int stride, int pad, int pw, int ph,
+                                 uint8_t *__restrict__ dst)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= pw || y >= ph) return;
+    dst[(size_t)y * pw + x] = src[(size_t)d_clamp(y - pad, 0, h - 1) * stride + d_clamp(x - pad, 0, w - 1)];
+}
+
 }  // namespace
+
+cudaError_t jmme_launch_pad_plane(const uint8_t *src, int w, int h, int stride, int pad, int pw, int ph, uint8_t *dst,
+                                  cudaStream_t st)
+{
+    pad_plane_kernel<<<dim3((pw + 127) / 128, ph), 128, 0, st>>>(src, w, h, stride, pad, pw, ph, dst);
+    return cudaGetLastError();
+}
 
 // rows [y_begin, y_end) of the padded planes are produced (y_begin a multiple of 4 is not required)
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,

@@ -39,12 +39,20 @@ cudaError_t jmme_launch_commit(const jmme_mbresult *res, int mb_w, int mb_h, int
                                uint8_t *mode, cudaStream_t st);
 cudaError_t jmme_launch_wave_step(const int *cur, int n_cur, int mb_w, int mb_h, int num_refs, int slice_rows,
                                   const int16_t *mv4, const int8_t *ref4, int16_t *pred, cudaStream_t st);
+cudaError_t jmme_launch_pad_plane(const uint8_t *src, int w, int h, int stride, int pad, int pw, int ph, uint8_t *dst,
+                                  cudaStream_t st);
 cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st);
 
 struct jmme_ctx {
     jmme_params p;
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
     int device, num_sms;
+    int metric[3], lf[3], ext;            // per-stage JMME_DIST_* / lambda factor in the context's cost domain; ext: general kernels
+    int cpad, cstride, cheight;           // chroma ME: padded integer chroma planes (w16/2 + 2 cpad) x (h16/2 + 2 cpad)
+    uint8_t *d_cplanes[JMME_MAX_REFS][2];
+    bool cref_set[JMME_MAX_REFS], cur_c_set;
+    uint8_t *d_cur_c[2];                  // current chroma, w16/2 x h16/2
+    uint8_t *d_craw;                      // staging for host chroma uploads (two components)
     jmme_tuning tune;                     // launch knobs with the defaults resolved (jmme_set_tuning)
     char last_kernel[JMME_KNAME_LEN];     // integer-search kernel instantiation of the last search
     cudaStream_t stream;
@@ -140,7 +148,10 @@ void free_device(jmme_ctx *c)
 {
     if (c->device >= 0) cudaSetDevice(c->device);
     cudaFree(c->d_raw);
-    for (int r = 0; r < JMME_MAX_REFS; r++) { cudaFree(c->d_planes[r]); cudaFree(c->d_raw_ref[r]); }
+    for (int r = 0; r < JMME_MAX_REFS; r++) {
+        cudaFree(c->d_planes[r]); cudaFree(c->d_raw_ref[r]); cudaFree(c->d_cplanes[r][0]); cudaFree(c->d_cplanes[r][1]);
+    }
+    cudaFree(c->d_cur_c[0]); cudaFree(c->d_cur_c[1]); cudaFree(c->d_craw);
     cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave); cudaFree(c->d_wave_tab);
@@ -164,9 +175,17 @@ int validate(const jmme_params *p)
         p->num_refs < 1 || p->num_refs > JMME_MAX_REFS || (p->blocktype_mask & ~JMME_MASK_ALL) ||
         !(p->blocktype_mask & JMME_MASK_ALL) || p->qp < 0 || p->qp > 51 || p->lambda_factor < 0 ||
         p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 3 || p->satd_round < 0 ||
-        p->satd_round > 1 || p->n_gpus < 0 || p->n_gpus > JMME_MAX_GPUS || p->slice_rows < 0)
+        p->satd_round > 1 || p->n_gpus < 0 || p->n_gpus > JMME_MAX_GPUS || p->slice_rows < 0 || p->cost_domain < 0 ||
+        p->cost_domain > 1 || p->me_distortion < 0 || p->me_distortion > 1 || p->transform8x8 < 0 || p->transform8x8 > 1 ||
+        p->chroma_me < 0 || p->chroma_me > 1)
         return JMME_ERR_PARAM;
-    if (p->cost_domain != 0) return JMME_ERR_UNSUPPORTED;
+    if (p->me_distortion &&
+        (p->me_distortion_fpel < 0 || p->me_distortion_fpel > 2 || p->me_distortion_hpel < 0 || p->me_distortion_hpel > 2 ||
+         p->me_distortion_qpel < 0 || p->me_distortion_qpel > 2))
+        return JMME_ERR_PARAM;
+    // the integer stage builds its surfaces from per-pixel sums (SAD or SSE): no Hadamard there (as in the oracle)
+    if (p->me_distortion && p->me_distortion_fpel == JMME_DIST_HADAMARD) return JMME_ERR_UNSUPPORTED;
+    if (p->chroma_me && !p->subpel) return JMME_ERR_PARAM;          // chroma enters at the sub-pel stages
     return JMME_OK;
 }
 
@@ -189,8 +208,27 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
     }
     c->pad = pad_for(p->search_range);
     c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
-    c->lambda_factor = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
-    if (c->lambda_factor > (96 << 16)) { delete c; return JMME_ERR_PARAM; }
+    {
+        // per-stage metric and lambda factor: an SSE stage works with lambda^2; cost domain 1 scales
+        // lambda by 32 instead of 65536 and leaves the rate untruncated
+        const int lf16 = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
+        if (lf16 > (96 << 16)) { delete c; return JMME_ERR_PARAM; }
+        const int q = std::min(std::max(p->qp - 12, 0), 39);
+        const double lambda = p->lambda_factor ? (double)p->lambda_factor / 65536.0
+                                               : (p->rdopt ? std::sqrt(0.85 * std::pow(2.0, q / 3.0)) : (double)kQp2Quant[q]);
+        c->metric[0] = p->me_distortion ? p->me_distortion_fpel : JMME_DIST_SAD;
+        c->metric[1] = p->me_distortion ? p->me_distortion_hpel : (p->use_hadamard ? JMME_DIST_HADAMARD : JMME_DIST_SAD);
+        c->metric[2] = p->me_distortion ? p->me_distortion_qpel : (p->use_hadamard ? JMME_DIST_HADAMARD : JMME_DIST_SAD);
+        for (int st = 0; st < 3; st++) {
+            const double l = c->metric[st] == JMME_DIST_SSE ? lambda * lambda : lambda;
+            c->lf[st] = (int)((p->cost_domain ? 32.0 : 65536.0) * l + 0.5);
+        }
+        c->lambda_factor = c->lf[0];
+        // the legacy kernels cover: domain 0, SAD integer stage, sub-pel stages both SAD or both Hadamard 4x4, luma only
+        c->ext = p->cost_domain || p->transform8x8 || p->chroma_me || c->metric[0] != JMME_DIST_SAD ||
+                 c->metric[1] == JMME_DIST_SSE || c->metric[2] == JMME_DIST_SSE || c->metric[1] != c->metric[2];
+    }
+    c->cpad = c->pad / 2; c->cstride = c->w16 / 2 + 2 * c->cpad; c->cheight = c->h16 / 2 + 2 * c->cpad;
     c->n_planes = p->subpel ? 16 : 1;
     c->ncols = 2 * p->search_range + 1; c->ncand = c->ncols * c->ncols;
     resolve_tuning(nullptr, &c->tune);
@@ -225,6 +263,12 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
             CUC(cudaMalloc(&c->d_raw_ref[r], (size_t)p->width * p->height));
         }
         CUC(cudaMalloc(&c->d_cur16, (size_t)c->w16 * c->h16));
+        if (p->chroma_me) {
+            for (int r = 0; r < p->num_refs; r++)
+                for (int k = 0; k < 2; k++) CUC(cudaMalloc(&c->d_cplanes[r][k], (size_t)c->cstride * c->cheight));
+            for (int k = 0; k < 2; k++) CUC(cudaMalloc(&c->d_cur_c[k], (size_t)(c->w16 / 2) * (c->h16 / 2)));
+            CUC(cudaMalloc(&c->d_craw, 2 * (size_t)((p->width + 1) / 2) * ((p->height + 1) / 2)));
+        }
         CUC(cudaMalloc(&c->d_pred, sizeof(int16_t) * 2 * JMME_NBLK * n_mb * p->num_refs));
         CUC(cudaMalloc(&c->d_res, sizeof(BlkRes) * JMME_NBLK * n_mb * p->num_refs));
         CUC(cudaMemset(c->d_res, 0, sizeof(BlkRes) * JMME_NBLK * n_mb * p->num_refs));
@@ -288,10 +332,15 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.R = c->p.search_range; P.ncols = c->ncols; P.num_refs = c->p.num_refs;
     P.lambda_factor = c->lambda_factor; P.rdopt = c->p.rdopt; P.search_mode = c->p.search_mode;
     P.pred_policy = c->p.pred_policy; P.blocktype_mask = c->p.blocktype_mask;
-    P.use_hadamard = c->p.use_hadamard; P.satd_round = c->p.satd_round; P.subpel = c->p.subpel;
+    P.use_hadamard = c->metric[1] == JMME_DIST_HADAMARD; P.satd_round = c->p.satd_round; P.subpel = c->p.subpel;
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
     P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy;
     P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
+    P.cost_domain = c->p.cost_domain; P.ext = c->ext; P.t8 = c->p.transform8x8; P.chroma_me = c->p.chroma_me;
+    for (int st = 0; st < 3; st++) { P.metric[st] = c->metric[st]; P.lf[st] = c->lf[st]; }
+    for (int r = 0; r < c->p.num_refs; r++)
+        for (int k = 0; k < 2; k++) P.cplanes[r][k] = c->d_cplanes[r][k];
+    P.cstride = c->cstride; P.cpad = c->cpad; P.cur_c[0] = c->d_cur_c[0]; P.cur_c[1] = c->d_cur_c[1]; P.cur_cs = c->w16 / 2;
     P.tune_group = c->tune.group; P.tune_cluster = c->tune.cluster; P.tune_lin = !c->tune.table_rate;
 }
 
@@ -302,6 +351,11 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
 {
     for (int r = 0; r < c->p.num_refs; r++)
         if (!c->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
+    if (c->p.chroma_me) {
+        if (!c->cur_c_set) return fail(c, JMME_ERR_STATE, "current chroma not set");
+        for (int r = 0; r < c->p.num_refs; r++)
+            if (!c->cref_set[r]) return fail(c, JMME_ERR_STATE, "reference chroma not set");
+    }
     const uint8_t *cur = d_cur;
     int cs = stride;
     // the search kernel fetches the current MB with 16-byte cp.async: rows must be 16-byte aligned
@@ -329,7 +383,8 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         P.field_mv = c->d_fmv; P.field_ref = c->d_fref; P.slice_rows = c->p.slice_rows;
         // the default integer kernel of a wavefront step (me_int_tb.cu, 12 warps, clusters) predicts in its own
         // prologue; the other kernels read the predictors wave_step_kernel writes
-        const bool in_kernel = c->tune.variant == 0 && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
+        const bool wide = c->p.cost_domain || c->metric[0] == JMME_DIST_SSE;      // me_int.cu's 64-bit kernels
+        const bool in_kernel = c->tune.variant == 0 && !wide && c->p.search_mode == JMME_SEARCH_FASTFULL && c->p.search_range <= 32 &&
                                c->ncols >= 6 && c->p.blocktype_mask != JMME_MASK_16x16 && !c->tune.wave_step;
         P.wave_tab = in_kernel ? c->d_wave_tab : nullptr;
         // search and sub-pel kernels of consecutive steps overlap their launch latency and constant-only
@@ -543,6 +598,77 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
     if (rc != JMME_OK) return rc;
     if (!c->p.async_reference) CU(c, cudaStreamSynchronize(c->stream));
     return JMME_OK;
+}
+
+// chroma ME: replicate a chroma pair (device pointers) into the padded planes of reference r (r >= 0) or into the
+// current-chroma buffers (r < 0), asynchronously on `st`
+static int chroma_to_planes(jmme_ctx *c, int r, const uint8_t *d_cb, const uint8_t *d_cr, int stride, cudaStream_t st)
+{
+    const int cw = (c->p.width + 1) / 2, ch = (c->p.height + 1) / 2;
+    const uint8_t *src[2] = {d_cb, d_cr};
+    for (int k = 0; k < 2; k++) {
+        if (r >= 0)
+            CU(c, jmme_launch_pad_plane(src[k], cw, ch, stride, c->cpad, c->cstride, c->cheight, c->d_cplanes[r][k], st));
+        else
+            CU(c, jmme_launch_pad_plane(src[k], cw, ch, stride, 0, c->w16 / 2, c->h16 / 2, c->d_cur_c[k], st));
+        c->launches++;
+    }
+    if (r >= 0) c->cref_set[r] = true;
+    else c->cur_c_set = true;
+    return JMME_OK;
+}
+
+int jmme_set_reference_chroma_dev(jmme_ctx *c, int r, const void *d_cb, const void *d_cr, int stride, void *stream)
+{
+    if (!c || !d_cb || !d_cr || r < 0 || r >= c->p.num_refs || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    if (!c->p.chroma_me) return fail(c, JMME_ERR_STATE, "chroma_me is off");
+    CU(c, cudaSetDevice(c->device));
+    return chroma_to_planes(c, r, (const uint8_t *)d_cb, (const uint8_t *)d_cr, stride, (cudaStream_t)stream);
+}
+
+int jmme_set_current_chroma_dev(jmme_ctx *c, const void *d_cb, const void *d_cr, int stride, void *stream)
+{
+    if (!c || !d_cb || !d_cr || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    if (!c->p.chroma_me) return fail(c, JMME_ERR_STATE, "chroma_me is off");
+    CU(c, cudaSetDevice(c->device));
+    return chroma_to_planes(c, -1, (const uint8_t *)d_cb, (const uint8_t *)d_cr, stride, (cudaStream_t)stream);
+}
+
+// host chroma: upload both components (whole pictures: a quarter of the luma each), then replicate
+static int chroma_from_host(jmme_ctx *c, int r, const uint8_t *cb, const uint8_t *cr, int stride)
+{
+    if (c->n_sub) {
+        for (int g = 0; g < c->n_sub; g++) {
+            int rc = chroma_from_host(c->sub[g], r, cb, cr, stride);
+            if (rc != JMME_OK) return fail(c, rc, c->sub[g]->err);
+        }
+        return JMME_OK;
+    }
+    if (!c->p.chroma_me) return fail(c, JMME_ERR_STATE, "chroma_me is off");
+    const int cw = (c->p.width + 1) / 2, ch = (c->p.height + 1) / 2;
+    CU(c, cudaSetDevice(c->device));
+    // the staging buffer is reused by the next call: the stream is drained first (chroma ME is not the pipelined path)
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, upload_rows(c->d_craw, cb, stride, cw, ch, c->stream));
+    CU(c, upload_rows(c->d_craw + (size_t)cw * ch, cr, stride, cw, ch, c->stream));
+    int rc = chroma_to_planes(c, r, c->d_craw, c->d_craw + (size_t)cw * ch, cw, c->stream);
+    if (rc != JMME_OK) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return JMME_OK;
+}
+
+int jmme_set_reference_chroma(jmme_ctx *c, int r, const uint8_t *cb, const uint8_t *cr, int stride)
+{
+    if (!c || !cb || !cr || r < 0 || r >= c->p.num_refs || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
+    return chroma_from_host(c, r, cb, cr, stride);
+}
+
+int jmme_set_current_chroma(jmme_ctx *c, const uint8_t *cb, const uint8_t *cr, int stride)
+{
+    if (!c || !cb || !cr || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
+    return chroma_from_host(c, -1, cb, cr, stride);
 }
 
 int jmme_set_profiling(jmme_ctx *c, int enable)

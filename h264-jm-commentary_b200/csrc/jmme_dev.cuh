@@ -54,6 +54,16 @@ struct SearchParams {
     int pdl;                             // wavefront steps: launch with programmatic stream serialization
     jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
     int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
+    // ---- ABI 4: cost domain, per-stage metrics, 8x8 Hadamard, chroma ME ----
+    int cost_domain;                     // 0: D + (lf*bits >> 16)   1: (D << 5) + lf*bits
+    int metric[3], lf[3];                // JMME_DIST_* and lambda factor of the integer / half-pel / quarter-pel stage
+    int ext;                             // 1: anything beyond the legacy path is on (domain 1, SSE, 8x8, chroma, or metrics
+                                         //    that restart the quarter-pel stage): kernels take their general form
+    int t8, chroma_me;
+    const uint8_t *cplanes[JMME_MAX_REFS][2];   // padded integer chroma planes (Cb, Cr) of every reference
+    int cstride, cpad;
+    const uint8_t *cur_c[2];             // current chroma, w16/2 x h16/2
+    int cur_cs;
 };
 
 // copy the records of n_rec MBs (mb_of(i) = frame MB index of record i) from P.out to every peer buffer; the
@@ -144,6 +154,17 @@ __device__ __forceinline__ int d_ref_cost(int f, int rdopt, int ref)
 {
     if (rdopt) return d_weighted_cost(f, d_ue_bits(ref));
     return ref ? (int)((2ll * f) >> 16) : 0;
+}
+// the same in either cost domain: domain 1 = JM >= 12 scaled-up costs, rate not truncated
+#define JMME_SCALEUP_BITS 5
+__device__ __forceinline__ int d_wcost(int domain, int f, int bits) { return domain ? f * bits : d_weighted_cost(f, bits); }
+__device__ __forceinline__ int d_dscale(int domain, int d) { return domain ? d << JMME_SCALEUP_BITS : d; }
+// reference rate with the lambda factor of the last stage that ran
+__device__ __forceinline__ int d_ref_cost_of(const SearchParams &P, int ref)
+{
+    const int f = P.lf[P.subpel ? 2 : 0];
+    if (P.rdopt) return d_wcost(P.cost_domain, f, d_ue_bits(ref));
+    return ref ? (P.cost_domain ? 2 * f : (int)((2ll * f) >> 16)) : 0;
 }
 __device__ __forceinline__ int d_clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
 // Predictor components as the kernels use them: the host entry points refuse |pred| > JMME_MAX_PRED_QPEL, the

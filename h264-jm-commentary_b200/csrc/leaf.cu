@@ -54,6 +54,45 @@ __global__ void satd_kernel(const int16_t *diff, int n, int satd_round, int32_t 
     out[i] = satd_of(d, satd_round);
 }
 
+// JM HadamardSAD8x8: one thread per 8x8 difference block, three butterfly stages per row then per column
+__global__ void satd8_kernel(const int16_t *diff, int n, int satd_round, int32_t *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int m[64];
+    for (int k = 0; k < 64; k++) m[k] = diff[64 * (size_t)i + k];
+    for (int pass = 0; pass < 2; pass++) {
+        const int sr = pass ? 1 : 8, se = pass ? 8 : 1;          // stride between lines / between elements of a line
+        for (int l = 0; l < 8; l++) {
+            int v[8];
+            for (int k = 0; k < 8; k++) v[k] = m[l * sr + k * se];
+            for (int h = 4; h; h >>= 1)
+                for (int k = 0; k < 8; k++)
+                    if (!(k & h)) { const int a = v[k], b = v[k + h]; v[k] = a + b; v[k + h] = a - b; }
+            for (int k = 0; k < 8; k++) m[l * sr + k * se] = v[k];
+        }
+    }
+    int s = 0;
+    for (int k = 0; k < 64; k++) s += abs(m[k]);
+    out[i] = satd_round ? (s + 2) >> 2 : s >> 2;
+}
+
+// the 64 eighth-pel planes of one chroma component [STD 8.4.2.2.2]; thread = padded sample, loops over the phases
+__global__ void chroma_planes_kernel(const uint8_t *src, int w, int h, int stride, int pad, int ps, int ph, uint8_t *out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= ps || y >= ph) return;
+    const int x0 = d_clamp(x - pad, 0, w - 1), x1 = d_clamp(x + 1 - pad, 0, w - 1);
+    const int y0 = d_clamp(y - pad, 0, h - 1), y1 = d_clamp(y + 1 - pad, 0, h - 1);
+    const int A = src[(size_t)y0 * stride + x0], B = src[(size_t)y0 * stride + x1];
+    const int C = src[(size_t)y1 * stride + x0], D = src[(size_t)y1 * stride + x1];
+    const size_t psz = (size_t)ps * ph;
+    for (int yf = 0; yf < 8; yf++)
+        for (int xf = 0; xf < 8; xf++)
+            out[psz * (yf * 8 + xf) + (size_t)y * ps + x] =
+                (uint8_t)(((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6);
+}
+
 // one thread per spiral position: 16 4x4 SADs with VABSDIFF4 on byte-gathered words, then the sums
 __global__ void blocksad_kernel(const uint8_t *cur, const uint8_t *ref, int rs, int ox, int oy, int cx, int cy,
                                 int ncand, const int16_t *sxy, int bonus, int32_t *out)
@@ -266,6 +305,35 @@ int jmme_getSubImagesLuma(const uint8_t *luma, int width, int height, int stride
     LCU(dst.alloc((size_t)ps * ph * 16));
     LCU(jmme_launch_interp(src.as<uint8_t>(), width, height, width, pad, ps, ph, 16, dst.as<uint8_t>(), 0, ph, 0));
     LCU(cudaMemcpy(out_planes, dst.p, (size_t)ps * ph * 16, cudaMemcpyDeviceToHost));
+    return JMME_OK;
+}
+
+int jmme_HadamardSAD8x8(const int16_t *diff, int n, int satd_round, int32_t *out)
+{
+    if (!diff || !out || n < 0) return JMME_ERR_PARAM;
+    if (n == 0) return JMME_OK;
+    DevBuf d_in, d_out;
+    LCU(d_in.alloc(sizeof(int16_t) * 64 * (size_t)n));
+    LCU(d_out.alloc(sizeof(int32_t) * (size_t)n));
+    LCU(cudaMemcpy(d_in.p, diff, sizeof(int16_t) * 64 * (size_t)n, cudaMemcpyHostToDevice));
+    satd8_kernel<<<(n + 63) / 64, 64>>>(d_in.as<int16_t>(), n, satd_round, d_out.as<int32_t>());
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpy(out, d_out.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    return JMME_OK;
+}
+
+int jmme_getSubImagesChroma(const uint8_t *chroma, int width, int height, int stride, int pad, uint8_t *out)
+{
+    if (!chroma || !out || width <= 0 || height <= 0 || pad < 0 || stride < width) return JMME_ERR_PARAM;
+    const int ps = width + 2 * pad, ph = height + 2 * pad;
+    DevBuf d_in, d_out;
+    LCU(d_in.alloc((size_t)stride * height));
+    LCU(d_out.alloc((size_t)ps * ph * 64));
+    LCU(cudaMemcpy(d_in.p, chroma, (size_t)stride * (height - 1) + width, cudaMemcpyHostToDevice));
+    chroma_planes_kernel<<<dim3((ps + 127) / 128, ph), 128>>>(d_in.as<uint8_t>(), width, height, stride, pad, ps, ph,
+                                                             d_out.as<uint8_t>());
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpy(out, d_out.p, (size_t)ps * ph * 64, cudaMemcpyDeviceToHost));
     return JMME_OK;
 }
 

@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
     const int mby = mb / P.mb_w, mbx = mb - mby * P.mb_w;
     const int npb = P.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
     const int16_t *pr = P.pred ? P.pred + ((size_t)ref * n_mb + mb) * npb * 2 : nullptr;
-    const int bonus16 = (!P.rdopt && ref == 0) ? d_weighted_cost(P.lambda_factor, 16) : 0;
+    const int dom = P.cost_domain, lf0 = P.lf[0];
+    const bool sse = P.metric[0] == JMME_DIST_SSE;
+    const int bonus16 = (!P.rdopt && ref == 0) ? d_wcost(dom, lf0, 16) : 0;
     const uint8_t *plane = P.planes[ref];
 
     if (tid < 64) {
@@ -56,11 +58,13 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
                 uint32_t a = __ldg(rp + y * pw);
                 for (int w = 0; w < bw4; w++) {
                     const uint32_t nx = __ldg(rp + y * pw + w + 1);
-                    s = sad4(s_cur[4 * (by + y) + (bx >> 2) + w], __funnelshift_r(a, nx, sh), s);
+                    const uint32_t cw = s_cur[4 * (by + y) + (bx >> 2) + w], rw = __funnelshift_r(a, nx, sh);
+                    if (sse) { const unsigned d = __vabsdiffu4(cw, rw); s = __dp4a(d, d, s); }
+                    else s = sad4(cw, rw, s);
                     a = nx;
                 }
             }
-            int c = (int)s + d_weighted_cost(P.lambda_factor, d_se_bits(4 * mx - px) + d_se_bits(4 * my - py));
+            int c = d_dscale(dom, (int)s) + d_wcost(dom, lf0, d_se_bits(4 * mx - px) + d_se_bits(4 * my - py));
             if (mx == 0 && my == 0) c -= bonus;
             const unsigned long long v = ((unsigned long long)(unsigned)(c + 0x40000000) << 32) | P.spiral_key[idx];
             best = v < best ? v : best;

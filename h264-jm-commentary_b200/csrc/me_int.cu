@@ -27,6 +27,7 @@
 //   MV (0,0)   JM's "(0,0) first" pre-test (!rdopt) is the key table entry of that candidate set
 //              to 0 for the item; the 16x16 (0,0) bonus is one extra 16x16 evaluation by warp 0
 #include <cstdio>
+#include <type_traits>
 
 #include "jmme_dev.cuh"
 
@@ -47,7 +48,7 @@ struct SmemLayout {
         off_cur = off_raw + rows * RAWW;
         off_T = off_cur + 2 * 64;
         off_best = off_T + JMME_NT;
-        off_key = off_best + 48;
+        off_key = off_best + 96;        // 48 minima; 64-bit ones in the wide kernels
         off_bx = off_key + (ncols * ncols + 1) / 2;
         const int nb = PER_BLOCK ? JMME_NBLK : 1;
         off_by = off_bx + (nb * ncols + 3) / 4;
@@ -91,20 +92,39 @@ struct Item {
     int ref, mbx, mby, mb, cx, cy;
 };
 
+// distortion of 4 pixels accumulated: SAD (one VABSDIFF4.ACC) or SSE (VABSDIFF4, then IDP.4A of the bytes with themselves)
+template <bool SSE>
+__device__ __forceinline__ unsigned dist4_t(unsigned a, unsigned b, unsigned c)
+{
+    if constexpr (SSE) { const unsigned d = __vabsdiffu4(a, b); return __dp4a(d, d, c); }
+    else return sad4(a, b, c);
+}
+
 // RS_CT: compile-time window row stride (0 = take it from the layout at run time)
-template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16, int RS_CT>
+// MODE 0: packed 32-bit (cost, key) minima — cost domain 0 with SAD, where cost + bias < 2^17.
+// MODE 1 / 2 ("wide"): 64-bit minima (cost << 15 | key) for what does not fit 17 bits: the scaled-up cost domain
+// (cost_domain = 1: (SAD << 5) + lambda_factor * bits, 22 bits) and SSE distortion (MODE 2: VABSDIFF4 then
+// IDP.4A of the difference bytes with themselves; 25 bits, 30 in domain 1).  A 64-bit unsigned minimum is two
+// ISETP and two SEL instead of one VIMNMX; the warp reduction splits it into two CREDUX (cost, then the key
+// among the lanes that hold that cost).
+template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16, int RS_CT, int MODE = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParams P)
 {
+    constexpr bool WIDE = MODE != 0, SSE = MODE == 2;
+    using best_t = typename std::conditional<WIDE, unsigned long long, uint32_t>::type;
     extern __shared__ __align__(16) uint32_t smem[];
     const SmemLayout<PER_BLOCK> L(P.R);
     uint32_t *s_win = smem + L.off_win;
     uint32_t *s_raw = smem + L.off_raw;
     uint32_t *s_cur2 = smem + L.off_cur;
     uint32_t *s_T = smem + L.off_T;
-    uint32_t *s_best = smem + L.off_best;
+    best_t *s_best = (best_t *)(smem + L.off_best);
     uint16_t *s_key = (uint16_t *)(smem + L.off_key);
     uint8_t *s_bx = (uint8_t *)(smem + L.off_bx);
     uint8_t *s_by = (uint8_t *)(smem + L.off_by);
+    constexpr best_t BEST_MAX = ~(best_t)0;
+    auto dist4 = [](unsigned a, unsigned b, unsigned c) { return dist4_t<SSE>(a, b, c); };
+    const int dom = WIDE ? P.cost_domain : 0, lf0 = WIDE ? P.lf[0] : P.lambda_factor;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = P.R, ncols = P.ncols, ncand = ncols * ncols;
@@ -119,10 +139,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
 
     // tables that do not depend on the work item
     for (int i = tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
-    const int bonus_base = P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16);
+    const int bonus_base = P.rdopt ? 0 : d_wcost(dom, lf0, 16);
     const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
-    for (int i = tid; i < JMME_NT; i += NW * 32)
-        s_T[i] = ((unsigned)d_weighted_cost(P.lambda_factor, i) + bias) << JMME_KEY_BITS;
+    for (int i = tid; i < JMME_NT; i += NW * 32)         // rate + bias, already shifted next to the key when packed in 32 bits
+        s_T[i] = ((unsigned)d_wcost(dom, lf0, i) + bias) << (WIDE ? 0 : JMME_KEY_BITS);
     const bool pretest = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
     int patched = -1;                                    // key-table entry currently forced to 0
 
@@ -174,7 +194,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
             v.w = __funnelshift_r(w0, w4, 24);
             *(uint4 *)(s_win + row * RS + 4 * q) = v;
         }
-        if (tid < 48) s_best[tid] = 0xFFFFFFFFu;
+        if (tid < 48) s_best[tid] = BEST_MAX;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         for (int i = tid; i < NPB * ncols; i += NW * 32) {
             const int b = i / ncols, o = i - b * ncols;
@@ -230,19 +250,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int i = lane + 32 * h, row = i >> 2, j = i & 3;
-                s = sad4(s_cur[i], s_win[(y00 + row) * RS + x00 + 4 * j], s);
+                s = dist4(s_cur[i], s_win[(y00 + row) * RS + x00 + 4 * j], s);
             }
             s = __reduce_add_sync(0xFFFFFFFFu, s);
             if (lane == 0) {
-                const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + s_key[y00 * ncols + x00] -
-                                   ((unsigned)bonus << JMME_KEY_BITS);
-                atomicMin(&s_best[0], v);
+                if constexpr (WIDE) {
+                    const unsigned c32 = (unsigned)d_dscale(dom, (int)s) + s_T[s_bx[x00] + s_by[y00]] - (unsigned)bonus;
+                    atomicMin(&s_best[0], ((best_t)c32 << JMME_KEY_BITS) | s_key[y00 * ncols + x00]);
+                } else {
+                    const unsigned v = (s << JMME_KEY_BITS) + s_T[s_bx[x00] + s_by[y00]] + s_key[y00 * ncols + x00] -
+                                       ((unsigned)bonus << JMME_KEY_BITS);
+                    atomicMin(&s_best[0], (best_t)v);
+                }
             }
         }
 
-        uint32_t best[NB];
+        best_t best[NB];
 #pragma unroll
-        for (int b = 0; b < NB; b++) best[b] = 0xFFFFFFFFu;
+        for (int b = 0; b < NB; b++) best[b] = BEST_MAX;
 
         for (int task = warp; task < n_tasks; task += NW) {
             int run, xoff;
@@ -272,50 +297,58 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
                     const int cr = rr - k;               // current-MB row this reference row meets
                     if (cr >= 0 && cr < 16) {
                         const int a = ONLY16 ? 0 : (cr >> 2) * 4;
-                        acc[k][a + 0] = sad4(cur[cr][0], r0, acc[k][a + 0]);
-                        acc[k][a + 1] = sad4(cur[cr][1], r1, acc[k][a + 1]);
-                        acc[k][a + 2] = sad4(cur[cr][2], r2, acc[k][a + 2]);
-                        acc[k][a + 3] = sad4(cur[cr][3], r3, acc[k][a + 3]);
+                        acc[k][a + 0] = dist4(cur[cr][0], r0, acc[k][a + 0]);
+                        acc[k][a + 1] = dist4(cur[cr][1], r1, acc[k][a + 1]);
+                        acc[k][a + 2] = dist4(cur[cr][2], r2, acc[k][a + 2]);
+                        acc[k][a + 3] = dist4(cur[cr][3], r3, acc[k][a + 3]);
                     }
                 }
             }
 
-            // rate + key of candidate k (uniform predictor) or the key alone (per-block predictors)
+            // rate + key of candidate k (uniform predictor) or the key alone (per-block predictors); wide: the
+            // rate (+ bias) in the high word, the key in the low one
             const unsigned bx0 = s_bx[xoff];
-            auto kr_of = [&](int k) -> unsigned {
+            auto kr_of = [&](int k) -> best_t {
                 const int yoff = ybase + k;
                 const unsigned key = s_key[yoff * ncols + xoff];
-                return PER_BLOCK ? key : s_T[bx0 + s_by[yoff]] + key;
+                if constexpr (WIDE) return PER_BLOCK ? (best_t)key : (((best_t)s_T[bx0 + s_by[yoff]] << JMME_KEY_BITS) | key);
+                else return PER_BLOCK ? key : s_T[bx0 + s_by[yoff]] + key;
             };
-            auto pack = [&](int k, unsigned kr, unsigned (&pk)[NB]) {
+            auto pack = [&](int k, best_t kr, best_t (&pk)[NB]) {
+                auto one = [&](unsigned dist) -> best_t {      // distortion -> its place next to rate and key
+                    if constexpr (WIDE) return (best_t)(unsigned)d_dscale(dom, (int)dist) << JMME_KEY_BITS;
+                    else return dist << JMME_KEY_BITS;
+                };
                 if constexpr (ONLY16) {
                     const unsigned s = (acc[k][0] + acc[k][1]) + (acc[k][2] + acc[k][3]);
-                    pk[0] = (s << JMME_KEY_BITS) + kr;
+                    pk[0] = one(s) + kr;
                 } else {
                     unsigned o[JMME_NBLK];
                     larger_blocks(acc[k], o);
                     if constexpr (!PER_BLOCK) {
 #pragma unroll
-                        for (int b = 0; b < NB; b++) pk[b] = (o[b] << JMME_KEY_BITS) + kr;
+                        for (int b = 0; b < NB; b++) pk[b] = one(o[b]) + kr;
                     } else {
                         const int yoff = ybase + k;
 #pragma unroll
-                        for (int b = 0; b < NB; b++)
-                            pk[b] = (o[b] << JMME_KEY_BITS) + s_T[s_bx[b * ncols + xoff] + s_by[b * ncols + yoff]] + kr;
+                        for (int b = 0; b < NB; b++) {
+                            const unsigned rt = s_T[s_bx[b * ncols + xoff] + s_by[b * ncols + yoff]];
+                            pk[b] = one(o[b]) + (WIDE ? (best_t)rt << JMME_KEY_BITS : (best_t)rt) + kr;
+                        }
                     }
                 }
             };
             // candidates are folded two at a time: min(best, min(a, b)) is one VIMNMX3
 #pragma unroll
             for (int k = 0; k + 1 < K; k += 2) {
-                unsigned pa[NB], pb[NB];
+                best_t pa[NB], pb[NB];
                 pack(k, kr_of(k), pa);
                 pack(k + 1, kr_of(k + 1), pb);
 #pragma unroll
                 for (int b = 0; b < NB; b++) best[b] = min(best[b], min(pa[b], pb[b]));
             }
             if (K & 1) {
-                unsigned pa[NB];
+                best_t pa[NB];
                 pack(K - 1, kr_of(K - 1), pa);
 #pragma unroll
                 for (int b = 0; b < NB; b++) best[b] = min(best[b], pa[b]);
@@ -324,10 +357,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
 
         // ---- reduce: lanes -> warp (CREDUX.MIN), lane b keeps block b, two shared atomicMin ------
         {
-            unsigned m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+            best_t m0 = BEST_MAX, m1 = BEST_MAX;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
-                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, best[b]);
+                best_t m;
+                if constexpr (WIDE) {            // cost first, then the smallest key among the lanes that hold that cost
+                    const unsigned c = (unsigned)(best[b] >> JMME_KEY_BITS), kk = (unsigned)best[b] & JMME_KEY_MASK;
+                    const unsigned mc = __reduce_min_sync(0xFFFFFFFFu, c);
+                    const unsigned mk = __reduce_min_sync(0xFFFFFFFFu, c == mc ? kk : 0xFFFFFFFFu);
+                    m = ((best_t)mc << JMME_KEY_BITS) | mk;
+                } else {
+                    m = __reduce_min_sync(0xFFFFFFFFu, best[b]);
+                }
                 if (b < 32) m0 = (lane == b) ? m : m0;
                 else m1 = (lane == b - 32) ? m : m1;
             }
@@ -337,8 +378,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
         cp_async_wait_all();                             // next item's raw rows have landed
         __syncthreads();                                 // every warp is done with s_win / s_best
         if (tid < NB) {
-            const unsigned v = s_best[tid];
-            const unsigned key = v & JMME_KEY_MASK;
+            const best_t v = s_best[tid];
+            const unsigned key = (unsigned)v & JMME_KEY_MASK;
             int mvx = 0, mvy = 0;                        // key 0 = the MV (0,0) pre-test
             if (key) {
                 mvx = cx + P.spiral_xy[2 * (key - 1)];
@@ -359,18 +400,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
     }
 }
 
-template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16, int RS_CT>
+template <int K, int NW, int MINB, bool PER_BLOCK, bool ONLY16, int RS_CT, int MODE = 0>
 cudaError_t launch_one(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     SmemLayout<PER_BLOCK> L(P.R);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_kernel<K, NW, MINB, PER_BLOCK, ONLY16, RS_CT>;
+    auto kern = me_int_kernel<K, NW, MINB, PER_BLOCK, ONLY16, RS_CT, MODE>;
     static KernelState ks;                               // shared-memory opt-in and occupancy, per device
     int c_occ = 0;
     cudaError_t e = jmme_kernel_occupancy(kern, ks, NW * 32, bytes, &c_occ);
     if (e != cudaSuccess) return e;
-    snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN, "me_int_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,ONLY16=%d,RS_CT=%d>", K, NW,
-             MINB, (int)PER_BLOCK, (int)ONLY16, RS_CT);
+    snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN, "me_int_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,ONLY16=%d,RS_CT=%d,MODE=%d>", K, NW,
+             MINB, (int)PER_BLOCK, (int)ONLY16, RS_CT, MODE);
     int n_items = d_n_units(P) * P.num_refs;
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
@@ -396,8 +437,21 @@ cudaError_t launch_shape(const SearchParams &P, int num_sms, cudaStream_t st)
 //   c = 2: 4 warps, >= 3 CTAs/SM (<= 168 registers)
 cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int shape, cudaStream_t st);
 
+// the wide kernels (cost domain 1, SSE): one shape, 8 warps and one CTA per SM (the 64-bit minima double the registers)
+template <int MODE>
+cudaError_t launch_wide(const SearchParams &P, int num_sms, cudaStream_t st)
+{
+    const bool per_block = P.pred_policy == JMME_PRED_PER_BLOCK;
+    if (P.blocktype_mask == JMME_MASK_16x16 && !per_block) return launch_one<2, 8, 1, false, true, 0, MODE>(P, num_sms, st);
+    if (P.ncols < 2) return cudaErrorInvalidValue;
+    if (per_block) return launch_one<2, 8, 1, true, false, 0, MODE>(P, num_sms, st);
+    return launch_one<2, 8, 1, false, false, 0, MODE>(P, num_sms, st);
+}
+
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st)
 {
+    if (P.metric[0] == JMME_DIST_SSE) return launch_wide<2>(P, num_sms, st);
+    if (P.cost_domain) return launch_wide<1>(P, num_sms, st);
     // default: measured best per search range; a wavefront step has fewer MBs than SMs, so
     // it takes the widest CTA (12 warps per MB)
     if (variant <= 0) variant = P.R <= 32 ? (P.mb_list ? 64 : 68) : 51;

@@ -28,25 +28,6 @@ __device__ __forceinline__ int block_of_cell(int t, int cx4, int cy4)
     }
 }
 
-__device__ __forceinline__ int satd16(const int (&d)[16], int satd_round)
-{
-    int t[16], s = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int a = d[4 * i], b = d[4 * i + 1], c = d[4 * i + 2], e = d[4 * i + 3];
-        int s0 = a + e, s1 = b + c, d0 = a - e, d1 = b - c;
-        t[4 * i] = s0 + s1; t[4 * i + 1] = d0 + d1; t[4 * i + 2] = s0 - s1; t[4 * i + 3] = d0 - d1;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int a = t[i], b = t[4 + i], c = t[8 + i], e = t[12 + i];
-        int s0 = a + e, s1 = b + c, d0 = a - e, d1 = b - c;
-        // |s0+s1| + |s0-s1| = 2*max(|s0|,|s1|): the last butterfly stage folds into a max
-        s += 2 * max(abs(s0), abs(s1)) + 2 * max(abs(d0), abs(d1));
-    }
-    return satd_round ? (s + 1) >> 1 : s >> 1;
-}
-
 // need[t]: XOR offsets (within the 16 cells of an MB, cell = 4*cy4 + cx4) that gather the cells of one
 // block of blocktype t: 16x16 all, 16x8 {1,2,4}, 8x16 {1,4,8}, 8x8 {1,4}, 8x4 {1}, 4x8 {4}, 4x4 none
 __device__ __forceinline__ int need_of_type(int t) { return (0x0415D7F0u >> (4 * t)) & 15; }
@@ -61,7 +42,11 @@ __device__ __forceinline__ int need_of_type(int t) { return (0x0415D7F0u >> (4 *
 // NG = 3 (with LAT): three groups of 128 threads share the positions of a step (3 + 3 + 3, then 2 + 3 + 3),
 // each runs the strict-< scan over its own and the groups' (cost, position) minima meet in shared memory:
 // the lowest position among equal costs wins, as in the sequential scan.  A third of the dependent chain.
-template <bool LAT, int NG>
+// EXT (P.ext): the general form of the stages — either cost domain, SAD / SSE / Hadamard per stage, 8x8
+// Hadamard for blocktypes 1..4 (two cross-cell butterfly stages over SHFL before the 4x4 transform: the four
+// cells of an 8x8 are lanes c, c^1, c^4, c^5), chroma ME (2x2 chroma samples per cell and plane, eighth-pel
+// bilinear on the fly).  The legacy instantiation keeps its instruction stream.
+template <bool LAT, int NG, bool EXT>
 __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams P)
 {
     __shared__ long long s_pk[NG > 1 ? 2 : 1][NG > 1 ? NG : 1][NG > 1 ? JMME_NBLK : 1];
@@ -78,9 +63,10 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
     const int b = t <= 7 ? block_of_cell(t, cx4, cy4) : 0;
     const int need = t <= 7 ? need_of_type(t) : 0;
     BlkRes *res = P.res + ((size_t)ref * n_mb + mb) * JMME_NBLK;
-    const int bonus = (!P.rdopt && ref == 0 && b == 0) ? d_weighted_cost(P.lambda_factor, 16) : 0;
+    const bool has_bonus = !P.rdopt && ref == 0 && b == 0;
     const size_t psz = (size_t)P.pstride * P.pheight;
     const uint8_t *planes = P.planes[ref];
+    const bool had8w = EXT && P.t8 && warp < 2;          // this warp's blocktypes (1..4) use the 8x8 transform
 
     // this cell of the current MB: raw words (SAD) and 16-bit lane pairs (c0|c2<<16), (c1|c3<<16) per row (SATD)
     uint32_t cw[4], ca[4], cb[4];
@@ -93,6 +79,18 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
             cb[y] = __byte_perm(cw[y], 0, 0x4341);
         }
     }
+    int cc[2][4] = {};                                   // EXT chroma ME: this cell's 2x2 samples of Cb and Cr
+    if constexpr (EXT) {
+        if (P.chroma_me) {
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const uint8_t *q = P.cur_c[k] + (size_t)(8 * mby + 2 * cy4 + j) * P.cur_cs + 8 * mbx + 2 * cx4;
+                    cc[k][2 * j] = q[0]; cc[k][2 * j + 1] = q[1];
+                }
+        }
+    }
     if constexpr (LAT) {                                 // (the loads above read the current picture only)
         pdl_trigger();
         pdl_wait();
@@ -101,7 +99,7 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
     {
         const BlkRes r = res[b];
         mvx = r.mvx; mvy = r.mvy;
-        mn = P.use_hadamard ? INT_MAX : r.cost;
+        mn = r.cost;
         if (P.pred) {
             const int npb = P.pred_policy == JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
             const int16_t *pr = P.pred + ((size_t)ref * n_mb + mb) * npb * 2 + (npb == 1 ? 0 : 2 * b);
@@ -111,10 +109,18 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
     // reference position of this cell at MV (0,0), in padded-plane coordinates
     const int rx0 = P.pad + 16 * mbx + 4 * cx4, ry0 = P.pad + 16 * mby + 4 * cy4;
     const int pw = P.pstride >> 2;
-    const unsigned lf = (unsigned)P.lambda_factor;       // lambda_factor * bits < 2^31: 32-bit product is exact
 
+    int prev_metric = P.metric[0];
     for (int step = 2; step >= 1; step--) {
-        const int pos0 = (step == 2 && P.use_hadamard) ? 0 : 1;
+        // a stage whose metric differs from the previous stage's (or any stage with chroma ME) starts at
+        // position 0 with the minimum reset (JM start_me_refinement_hp / _qp)
+        const int st = 3 - step, metric = P.metric[st];
+        const bool restart = metric != prev_metric || (EXT && P.chroma_me);
+        prev_metric = metric;
+        if (restart) mn = INT_MAX;
+        const int pos0 = restart ? 0 : 1;
+        const unsigned lf = (unsigned)P.lf[st];          // legacy: lambda_factor * bits < 2^31, the 32-bit product is exact
+        const int bonus = has_bonus ? d_wcost(EXT ? P.cost_domain : 0, P.lf[st], 16) : 0;
         const int ox = mvx, oy = mvy;
         int best = 0;
         // MV bits of the three x and three y offsets of this step (the nine positions combine them)
@@ -141,48 +147,129 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
             if (pos < pos0 || (NG > 1 && pos / 3 != grp)) continue;  // (uniform per warp)
             const int sx = c_sp9h[pos][0], sy = c_sp9h[pos][1];     // compile-time after unrolling
             const int qx = ox + step * sx, qy = oy + step * sy;
-            int v = 0;
+            int v = 0, vc = 0;                                       // luma and (EXT) chroma distortion of this cell
+            uint32_t w[4] = {0, 0, 0, 0};
             if (active) {
                 const size_t off = psz * ((qy & 3) * 4 + (qx & 3)) + (size_t)(ry0 + (qy >> 2)) * P.pstride + (rx0 + (qx >> 2));
                 const uint32_t *rp = (const uint32_t *)(planes + (off & ~(size_t)3));
                 const int sh = (int)(off & 3) * 8;
-                uint32_t w[4];
 #pragma unroll
                 for (int y = 0; y < 4; y++)
                     w[y] = LAT ? __funnelshift_r(raw[pos][2 * y], raw[pos][2 * y + 1], sh)
                                : __funnelshift_r(__ldg(rp + y * pw), __ldg(rp + y * pw + 1), sh);
-                if (P.use_hadamard) {
-                    // 4x4 Hadamard on 16-bit lane pairs held as plain integers (hi*65536 + lo, |lane| <= 2040):
-                    // ordinary 32-bit add/sub act on both lanes.  The last butterfly stage pairs the two
-                    // lanes of one register: |lo+hi| + |lo-hi| = 2 max(|lo|,|hi|), so SATD = sum of the maxima.
-                    int s4[4], t4[4];
+            }
+            if (metric == JMME_DIST_HADAMARD) {
+                // 4x4 Hadamard on 16-bit lane pairs held as plain integers (hi*65536 + lo, |lane| <= 16320):
+                // ordinary 32-bit add/sub act on both lanes.  The last butterfly stage pairs the two
+                // lanes of one register: |lo+hi| + |lo-hi| = 2 max(|lo|,|hi|), so SATD = sum of the maxima.
+                int da[4], db[4];
 #pragma unroll
-                    for (int y = 0; y < 4; y++) {
-                        const int da = (int)(ca[y] - __byte_perm(w[y], 0, 0x4240));   // (d0, d2)
-                        const int db = (int)(cb[y] - __byte_perm(w[y], 0, 0x4341));   // (d1, d3)
-                        s4[y] = da + db;                                               // (d0+d1, d2+d3)
-                        t4[y] = da - db;                                               // (d0-d1, d2-d3)
-                    }
-                    unsigned acc = 0;
+                for (int y = 0; y < 4; y++) {
+                    da[y] = (int)(ca[y] - __byte_perm(w[y], 0, 0x4240));   // (d0, d2)
+                    db[y] = (int)(cb[y] - __byte_perm(w[y], 0, 0x4341));   // (d1, d3)
+                }
+                if constexpr (EXT) {
+                    if (had8w) {
+                        // 8x8 transform = the butterflies over the cell index (cells c^1, then c^4) followed by the
+                        // 4x4 transform inside each cell; a whole cell may carry the opposite sign (abs follows)
 #pragma unroll
-                    for (int g = 0; g < 2; g++) {
-                        const int *r4 = g ? t4 : s4;
-                        const int u0 = r4[0] + r4[1], u1 = r4[0] - r4[1], u2 = r4[2] + r4[3], u3 = r4[2] - r4[3];
-                        const int y4[4] = {u0 + u2, u0 - u2, u1 + u3, u1 - u3};
+                        for (int y = 0; y < 4; y++) {
+                            int u = __shfl_xor_sync(0xFFFFFFFFu, da[y], 1), u2 = __shfl_xor_sync(0xFFFFFFFFu, db[y], 1);
+                            da[y] = (cx4 & 1) ? u - da[y] : da[y] + u;
+                            db[y] = (cx4 & 1) ? u2 - db[y] : db[y] + u2;
+                        }
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int lo = (int)(short)y4[k];
-                            const int hi = (y4[k] - lo) >> 16;
-                            acc += (unsigned)max(abs(lo), abs(hi));
+                        for (int y = 0; y < 4; y++) {
+                            int u = __shfl_xor_sync(0xFFFFFFFFu, da[y], 4), u2 = __shfl_xor_sync(0xFFFFFFFFu, db[y], 4);
+                            da[y] = (cy4 & 1) ? u - da[y] : da[y] + u;
+                            db[y] = (cy4 & 1) ? u2 - db[y] : db[y] + u2;
                         }
                     }
-                    v = (int)acc;                        // = sum|coef| / 2 exactly, for both satd_round settings
-                } else {
-                    unsigned acc = 0;
-#pragma unroll
-                    for (int y = 0; y < 4; y++) acc = sad4(cw[y], w[y], acc);
-                    v = (int)acc;
                 }
+                int s4[4], t4[4];
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    s4[y] = da[y] + db[y];                                         // (d0+d1, d2+d3)
+                    t4[y] = da[y] - db[y];                                         // (d0-d1, d2-d3)
+                }
+                unsigned acc = 0;
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const int *r4 = g ? t4 : s4;
+                    const int u0 = r4[0] + r4[1], u1 = r4[0] - r4[1], u2 = r4[2] + r4[3], u3 = r4[2] - r4[3];
+                    const int y4[4] = {u0 + u2, u0 - u2, u1 + u3, u1 - u3};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int lo = (int)(short)y4[k];
+                        const int hi = (y4[k] - lo) >> 16;
+                        acc += (unsigned)max(abs(lo), abs(hi));
+                    }
+                }
+                v = active ? (int)acc : 0;           // = sum|coef| / 2 of this cell's 16 coefficients, exactly
+            } else if (EXT && metric == JMME_DIST_SSE) {
+                unsigned acc = 0;
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    const unsigned d = __vabsdiffu4(cw[y], w[y]);
+                    acc = __dp4a(d, d, acc);
+                }
+                v = active ? (int)acc : 0;
+            } else {
+                unsigned acc = 0;
+#pragma unroll
+                for (int y = 0; y < 4; y++) acc = sad4(cw[y], w[y], acc);
+                v = active ? (int)acc : 0;
+            }
+            if constexpr (EXT) {
+                if (P.chroma_me) {
+                    // 4:2:0: the luma vector in quarter-pel units is the chroma vector in eighth-pel units; this
+                    // cell's 2x2 chroma samples of Cb and Cr, bilinear from 3x3 integer samples [STD 8.4.2.2.2]
+                    const int xf = qx & 7, yf = qy & 7;
+                    const int w00 = (8 - xf) * (8 - yf), w01 = xf * (8 - yf), w10 = (8 - xf) * yf, w11 = xf * yf;
+                    const bool chad = metric == JMME_DIST_HADAMARD && warp < 2;   // chroma block >= 4x4: 4x4 Hadamard
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        int d[4] = {0, 0, 0, 0};
+                        if (active) {
+                            const uint8_t *q = P.cplanes[ref][k] + (size_t)(P.cpad + 8 * mby + 2 * cy4 + (qy >> 3)) * P.cstride +
+                                               (P.cpad + 8 * mbx + 2 * cx4 + (qx >> 3));
+                            int a[3][3];
+#pragma unroll
+                            for (int j = 0; j < 3; j++)
+#pragma unroll
+                                for (int i = 0; i < 3; i++) a[j][i] = __ldg(q + j * P.cstride + i);
+#pragma unroll
+                            for (int j = 0; j < 2; j++)
+#pragma unroll
+                                for (int i = 0; i < 2; i++)
+                                    d[2 * j + i] = cc[k][2 * j + i] -
+                                                   ((w00 * a[j][i] + w01 * a[j][i + 1] + w10 * a[j + 1][i] + w11 * a[j + 1][i + 1] + 32) >> 6);
+                        }
+                        if (chad) {
+                            // the 4x4 chroma tile of an 8x8 luma quadrant lives in the four cells c, c^1, c^4, c^5
+                            int p0 = d[1] * 65536 + d[0], p1 = d[3] * 65536 + d[2];
+                            int s = p0 + p1, tt = p0 - p1;
+                            int u = __shfl_xor_sync(0xFFFFFFFFu, s, 1), u2 = __shfl_xor_sync(0xFFFFFFFFu, tt, 1);
+                            s = (cx4 & 1) ? u - s : s + u; tt = (cx4 & 1) ? u2 - tt : tt + u2;
+                            u = __shfl_xor_sync(0xFFFFFFFFu, s, 4); u2 = __shfl_xor_sync(0xFFFFFFFFu, tt, 4);
+                            s = (cy4 & 1) ? u - s : s + u; tt = (cy4 & 1) ? u2 - tt : tt + u2;
+                            const int slo = (int)(short)s, shi = (s - slo) >> 16, tlo = (int)(short)tt, thi = (tt - tlo) >> 16;
+                            vc += active ? max(abs(slo), abs(shi)) + max(abs(tlo), abs(thi)) : 0;   // sum|coef| / 2 of 4 coefficients
+                        } else if (metric == JMME_DIST_SSE) {
+                            vc += d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3];
+                        } else {
+                            vc += abs(d[0]) + abs(d[1]) + abs(d[2]) + abs(d[3]);
+                        }
+                    }
+                }
+                if (had8w && metric == JMME_DIST_HADAMARD) {
+                    // luma: gather the 8x8 (cells c^1, c^4), then JM's (sum|coef| + 2) >> 2 per 8x8; v is sum|coef| / 2
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+                    v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+                    v = P.satd_round ? (v + 1) >> 1 : v >> 1;
+                    v = ((cell & 5) == 0) ? v : 0;           // one lane of the four carries the 8x8's value on
+                }
+                v += vc;
             }
             // sum the cells of this block: masked XOR butterfly inside the half-warp
 #pragma unroll
@@ -190,7 +277,9 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
                 const int u = __shfl_xor_sync(0xFFFFFFFFu, v, o);
                 if (need & o) v += u;
             }
-            int cst = (int)((lf * (unsigned)(bitx[sx + 1] + bity[sy + 1])) >> 16) + v;
+            int cst;
+            if constexpr (EXT) cst = d_wcost(P.cost_domain, P.lf[st], bitx[sx + 1] + bity[sy + 1]) + d_dscale(P.cost_domain, v);
+            else cst = (int)((lf * (unsigned)(bitx[sx + 1] + bity[sy + 1])) >> 16) + v;
             if (qx == 0 && qy == 0) cst -= bonus;
             if (cst < mn) { mn = cst; best = pos; }
         }
@@ -224,7 +313,7 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
         if (owner) {
             o->mv[b][0] = active ? (int16_t)mvx : (int16_t)0;
             o->mv[b][1] = active ? (int16_t)mvy : (int16_t)0;
-            o->cost[b] = active ? mn + d_ref_cost(P.lambda_factor, P.rdopt, 0) : INT_MAX;
+            o->cost[b] = active ? mn + d_ref_cost_of(P, 0) : INT_MAX;
             o->ref_idx[b] = active ? (int8_t)0 : (int8_t)-1;
             if (q) {
                 q->mv[b][0] = o->mv[b][0]; q->mv[b][1] = o->mv[b][1];
@@ -244,7 +333,7 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
             __shared__ uint32_t s_mv[JMME_NBLK];
             __shared__ int8_t s_ref[JMME_NBLK];
             if (owner) {
-                s_cost[b] = active ? mn + d_ref_cost(P.lambda_factor, P.rdopt, 0) : INT_MAX;
+                s_cost[b] = active ? mn + d_ref_cost_of(P, 0) : INT_MAX;
                 s_mv[b] = active ? ((uint32_t)(uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16)) : 0u;
                 s_ref[b] = active ? (int8_t)0 : (int8_t)-1;
             }
@@ -283,7 +372,7 @@ __global__ void select_ref_kernel(const SearchParams P)
             q->mv[b][0] = on ? v.mvx : 0; q->mv[b][1] = on ? v.mvy : 0;
             q->cost[b] = on ? v.cost : INT_MAX; q->ref_idx[b] = on ? (int8_t)r : (int8_t)-1;
         }
-        const int tot = v.cost + d_ref_cost(P.lambda_factor, P.rdopt, r);
+        const int tot = v.cost + d_ref_cost_of(P, r);
         if (on && tot < bc) { bc = tot; br = r; bx = v.mvx; by = v.mvy; }
     }
     if (work) { o->mv[b][0] = (int16_t)bx; o->mv[b][1] = (int16_t)by; o->cost[b] = bc; o->ref_idx[b] = (int8_t)br; }
@@ -334,13 +423,18 @@ cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.gridDim = dim3((unsigned)n_items); cfg.blockDim = dim3(128);
+        cfg.gridDim = dim3((unsigned)n_items); cfg.blockDim = dim3(384);
         cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
-        cfg.blockDim = dim3(384);
-        return cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3>, P);
+        return P.ext ? cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3, true>, P)
+                     : cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3, false>, P);
     }
-    if (P.mb_list) me_subpel_kernel<true, 3><<<n_items, 384, 0, st>>>(P);
-    else me_subpel_kernel<false, 1><<<n_items, 128, 0, st>>>(P);
+    if (P.mb_list) {
+        if (P.ext) me_subpel_kernel<true, 3, true><<<n_items, 384, 0, st>>>(P);
+        else me_subpel_kernel<true, 3, false><<<n_items, 384, 0, st>>>(P);
+    } else {
+        if (P.ext) me_subpel_kernel<false, 1, true><<<n_items, 128, 0, st>>>(P);
+        else me_subpel_kernel<false, 1, false><<<n_items, 128, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
 

@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 3          # JMME_ABI_VERSION of include/jmme.h
+ABI_VERSION = 4          # JMME_ABI_VERSION of include/jmme.h
 BLOCKS_PER_MB = 41
 MAX_REFS = 4
 MAX_GPUS = 8
@@ -20,6 +20,7 @@ INT32_MAX = 2**31 - 1
 OK, ERR_PARAM, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_STATE, ERR_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 SEARCH_FASTFULL, SEARCH_FULL = 0, 1
 PRED_ZERO, PRED_PER_MB, PRED_PER_BLOCK, PRED_MEDIAN = 0, 1, 2, 3
+DIST_SAD, DIST_SSE, DIST_HADAMARD = 0, 1, 2
 MASK_16x16, MASK_ALL = 0x02, 0xFE
 
 # block geometry (JM blc_size): blocktype -> (w, h); result index bases
@@ -43,7 +44,9 @@ class Params(C.Structure):
         "width", "height", "search_range", "num_refs", "blocktype_mask", "lambda_factor", "qp", "rdopt",
         "use_hadamard", "subpel", "search_mode", "pred_policy", "satd_round", "cost_domain",
         "mb_row_begin", "mb_row_end", "n_gpus")] + [("device_ids", C.c_int32 * MAX_GPUS),
-                                                     ("async_reference", C.c_int32), ("slice_rows", C.c_int32)]
+                                                     ("async_reference", C.c_int32), ("slice_rows", C.c_int32)] + \
+        [(n, C.c_int32) for n in ("me_distortion", "me_distortion_fpel", "me_distortion_hpel", "me_distortion_qpel",
+                                  "transform8x8", "chroma_me")]
 
 
 class Tuning(C.Structure):
@@ -59,13 +62,13 @@ assert MBRESULT_DTYPE.itemsize == 372, MBRESULT_DTYPE.itemsize
 EXPORTS = [
     "jmme_default_params", "jmme_create", "jmme_destroy", "jmme_strerror", "jmme_last_error", "jmme_backend",
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
-    "jmme_lambda_factor", "jmme_set_reference", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
-    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev",
+    "jmme_lambda_factor", "jmme_set_reference", "jmme_set_reference_chroma", "jmme_set_current_chroma", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
+    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_set_reference_chroma_dev", "jmme_set_current_chroma_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev",
     "jmme_launch_count", "jmme_set_tuning", "jmme_get_tuning", "jmme_last_kernel",
     "jmme_set_profiling",
     "jmme_get_kernel_times", "jmme_InitMotionSearchModule", "jmme_SetMotionVectorPredictor",
     "jmme_commit_field", "jmme_predict_frame",
-    "jmme_getSubImagesLuma", "jmme_SATD", "jmme_SetupFastFullPelSearch", "jmme_FastFullPelBlockMotionSearch",
+    "jmme_getSubImagesLuma", "jmme_getSubImagesChroma", "jmme_SATD", "jmme_HadamardSAD8x8", "jmme_SetupFastFullPelSearch", "jmme_FastFullPelBlockMotionSearch",
     "jmme_FullPelBlockMotionSearch", "jmme_SubPelBlockMotionSearch",
 ]
 
@@ -102,11 +105,15 @@ class Lib:
             "jmme_lambda_factor_of": (i32, [vp]),
             "jmme_lambda_factor": (i32, [i32, i32]),
             "jmme_set_reference": (i32, [vp, i32, pu8, i32]),
+            "jmme_set_reference_chroma": (i32, [vp, i32, pu8, pu8, i32]),
+            "jmme_set_current_chroma": (i32, [vp, pu8, pu8, i32]),
             "jmme_search_frame": (i32, [vp, pu8, i32, pi16, vp, vp]),
             "jmme_get_predictors": (i32, [vp, pi16]),
             "jmme_get_subimage": (i32, [vp, i32, i32, i32, pu8, i32]),
             "jmme_set_reference_dev": (i32, [vp, i32, vp, i32, vp]),
             "jmme_search_frame_dev": (i32, [vp, vp, i32, vp, vp, vp, vp]),
+            "jmme_set_reference_chroma_dev": (i32, [vp, i32, vp, vp, i32, vp]),
+            "jmme_set_current_chroma_dev": (i32, [vp, vp, vp, i32, vp]),
             "jmme_push_stripe_dev": (i32, [vp, vp, C.POINTER(vp), i32, vp]),
             "jmme_set_peer_fields_dev": (i32, [vp, C.POINTER(vp), i32]),
             "jmme_launch_count": (C.c_longlong, [vp]),
@@ -121,6 +128,8 @@ class Lib:
             "jmme_predict_frame": (i32, [vp, pi16, C.POINTER(C.c_int8), pi16]),
             "jmme_getSubImagesLuma": (i32, [pu8, i32, i32, i32, i32, pu8]),
             "jmme_SATD": (i32, [pi16, i32, i32, pi32]),
+            "jmme_HadamardSAD8x8": (i32, [pi16, i32, i32, pi32]),
+            "jmme_getSubImagesChroma": (i32, [pu8, i32, i32, i32, i32, pu8]),
             "jmme_SetupFastFullPelSearch": (i32, [pu8, i32, pu8, i32, i32, i32, i32, i32, i32, i32, pi32]),
             "jmme_FastFullPelBlockMotionSearch": (i32, [pi32, i32, i32, i32, i32, i32, i32, i32, pi16, pi16, pi32]),
             "jmme_FullPelBlockMotionSearch": (i32, [pu8, i32, pu8, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
@@ -205,6 +214,22 @@ class Lib:
                                       out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
+    def hadamard_sad8x8(self, diffs, satd_round=1):
+        d = np.ascontiguousarray(diffs, dtype=np.int16).reshape(-1, 64)
+        out = np.zeros(len(d), np.int32)
+        self.check(self.dll.jmme_HadamardSAD8x8(d.ctypes.data_as(C.POINTER(C.c_int16)), len(d), satd_round,
+                                                out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def get_sub_images_chroma(self, chroma, pad):
+        """The 64 eighth-pel planes [yF][xF] of one chroma component, padded by `pad`."""
+        chroma, p = _u8(chroma)
+        h, w = chroma.shape
+        out = np.zeros((8, 8, h + 2 * pad, w + 2 * pad), np.uint8)
+        self.check(self.dll.jmme_getSubImagesChroma(p, w, h, chroma.strides[0], pad,
+                                                    out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
     def setup_fast_full_pel_search(self, cur_mb, ref_padded, pad, mb_x, mb_y, cx, cy, R, bonus=0):
         cur_mb, pc = _u8(cur_mb)
         ref_padded, _ = _u8(ref_padded)
@@ -283,6 +308,18 @@ class Context:
     def set_reference(self, ref_idx, luma):
         luma, p = _u8(luma)
         self.lib.check(self.lib.dll.jmme_set_reference(self.handle, ref_idx, p, luma.strides[0]), self.handle)
+
+    def set_reference_chroma(self, ref_idx, cb, cr):
+        cb, pb = _u8(cb)
+        cr, pr = _u8(cr)
+        assert cb.shape == cr.shape and cb.strides == cr.strides
+        self.lib.check(self.lib.dll.jmme_set_reference_chroma(self.handle, ref_idx, pb, pr, cb.strides[0]), self.handle)
+
+    def set_current_chroma(self, cb, cr):
+        cb, pb = _u8(cb)
+        cr, pr = _u8(cr)
+        assert cb.shape == cr.shape and cb.strides == cr.strides
+        self.lib.check(self.lib.dll.jmme_set_current_chroma(self.handle, pb, pr, cb.strides[0]), self.handle)
 
     def search_frame(self, cur, pred=None, per_ref=False):
         cur, p = _u8(cur)

@@ -4,7 +4,8 @@ JM's lencod reads `Key = value  # comment` lines from a configuration file (`-d 
 applies `-p Key=value` overrides.  Only the keys that bear on motion estimation are mapped; everything else
 is carried along untouched in `EncoderCfg.raw`.  Key names are the public JM ones, recalled, not read from
 the mounted reference (which has no sources): both the old (`UseHadamard`, `UseFME`, `QPFirstFrame`) and the
-newer (`MEDistortionHPel/QPel`, `SearchMode`, `QPPSlice`) spellings are understood.
+newer (`MEDistortionFPel/HPel/QPel`, `Transform8x8Mode`, `ChromaMEEnable`, `SearchMode`, `QPPSlice`) spellings are
+understood.
 """
 from __future__ import annotations
 
@@ -66,9 +67,10 @@ class EncoderCfg:
     def frames(self):
         return self._int("FramesToBeEncoded", default=2)
 
-    def params(self) -> dict:
+    def params(self, cost_domain=0) -> dict:
         """Keyword arguments of `Lib.context(...)`.  Raises ValueError for ME modes this library does not
-        implement (UMHex / EPZS fast searches, SSE distortion: SURVEY.md §2.2, out of scope)."""
+        implement (UMHex / EPZS fast searches, a Hadamard integer-pel stage: SURVEY.md §2.2).
+        cost_domain: JM fixes it at compile time (JCOST_CALC_SCALEUP, JM >= 12), so it is an argument, not a key."""
         w, h = self._int("SourceWidth", "OutputWidth"), self._int("SourceHeight", "OutputHeight")
         if not w or not h:
             raise ValueError("SourceWidth / SourceHeight missing")
@@ -88,18 +90,28 @@ class EncoderCfg:
             raise ValueError(f"SearchMode = {sm} (UMHex / EPZS) is not implemented: -1 (full) or 0 (fast full)")
         if sm < 0 or self._int("UseFastFullSearch", default=1) == 0:
             mode = abi.SEARCH_FULL
-        # sub-pel distortion: `UseHadamard` (old) or MEDistortionHPel/QPel (0 SAD, 1 SSE, 2 Hadamard SAD)
+        # distortion: `UseHadamard` (old JM: SAD at integer pel, SAD or SATD below) or MEDistortionFPel/HPel/QPel
+        # (0 SAD, 1 SSE, 2 Hadamard SAD; JM's own defaults are 0 / 2 / 2)
         had = self._int("UseHadamard", default=None)
-        dh, dq = self._int("MEDistortionHPel", default=None), self._int("MEDistortionQPel", default=None)
-        if dh is not None or dq is not None:
-            if (dh if dh is not None else dq) != (dq if dq is not None else dh):
-                raise ValueError("MEDistortionHPel != MEDistortionQPel is not implemented")
-            d = dh if dh is not None else dq
-            if d == 1:
-                raise ValueError("SSE sub-pel distortion is not implemented")
-            had = 1 if d == 2 else 0
-        if self._int("MEDistortionFPel", default=0) != 0:
-            raise ValueError("integer-pel distortion other than SAD is not implemented")
+        dist = [self._int(k, default=None) for k in ("MEDistortionFPel", "MEDistortionHPel", "MEDistortionQPel")]
+        dkw = {}
+        if any(d is not None for d in dist):
+            dist = [d if d is not None else dflt for d, dflt in zip(dist, (0, 2, 2))]
+            if any(d not in (0, 1, 2) for d in dist):
+                raise ValueError(f"MEDistortionFPel/HPel/QPel = {dist}: 0 (SAD), 1 (SSE) or 2 (Hadamard SAD)")
+            if dist[0] == 2:
+                raise ValueError("a Hadamard integer-pel stage (MEDistortionFPel = 2) is not implemented")
+            dkw = dict(me_distortion=1, me_distortion_fpel=dist[0], me_distortion_hpel=dist[1], me_distortion_qpel=dist[2])
+            had = 1 if dist[1] == 2 else 0
+        if self._int("Transform8x8Mode", default=0):
+            dkw["transform8x8"] = 1
+        ce = self._int("ChromaMEEnable", default=0)
+        if ce not in (0, 1):
+            raise ValueError(f"ChromaMEEnable = {ce}: 0 or 1 (chroma in the sub-pel stages)")
+        if ce:
+            dkw["chroma_me"] = 1
+        if cost_domain:
+            dkw["cost_domain"] = int(cost_domain)
         kw = dict(width=w, height=h, search_range=self._int("SearchRange", default=16),
                   num_refs=min(self._int("NumberReferenceFrames", default=1), abi.MAX_REFS), blocktype_mask=mask,
                   qp=self._int("QPPSlice", "QPRemainingFrame", "QPFirstFrame", default=28),
@@ -111,4 +123,7 @@ class EncoderCfg:
             mbs, mb_w = self._int("SliceArgument", default=0), (w + 15) // 16
             if mbs and mbs % mb_w == 0:
                 kw["slice_rows"] = mbs // mb_w
+        kw.update(dkw)
+        if kw.get("chroma_me") and not kw["subpel"]:
+            raise ValueError("ChromaMEEnable = 1 with DisableSubpelME = 1: chroma enters at the sub-pel stages")
         return kw

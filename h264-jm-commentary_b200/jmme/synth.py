@@ -122,8 +122,25 @@ def read_yuv420_luma(path, w, h, frame=0):
     return np.frombuffer(buf, np.uint8).reshape(h, w).copy()
 
 
-def write_yuv420(path, lumas):
-    """Write luma planes as a planar YUV 4:2:0 sequence with flat chroma."""
+def read_yuv420(path, w, h, frame=0):
+    """(luma, cb, cr) of frame `frame` of a planar 8-bit YUV 4:2:0 file."""
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    with open(path, "rb") as f:
+        f.seek(frame * yuv420_frame_bytes(w, h))
+        buf = f.read(yuv420_frame_bytes(w, h))
+    if len(buf) != yuv420_frame_bytes(w, h):
+        raise ValueError(f"{path}: frame {frame} of {w}x{h} is not in the file")
+    a = np.frombuffer(buf, np.uint8)
+    return (a[:w * h].reshape(h, w).copy(), a[w * h:w * h + cw * ch].reshape(ch, cw).copy(),
+            a[w * h + cw * ch:].reshape(ch, cw).copy())
+
+
+def write_yuv420(path, frames):
+    """Write a planar YUV 4:2:0 sequence; a frame is a luma plane (flat chroma is written) or (luma, cb, cr)."""
     with open(path, "wb") as f:
-        for y in lumas:
-            f.write(yuv420_frame(np.ascontiguousarray(y, np.uint8)).tobytes())
+        for fr in frames:
+            if isinstance(fr, (tuple, list)):
+                for pl in fr:
+                    f.write(np.ascontiguousarray(pl, np.uint8).tobytes())
+            else:
+                f.write(yuv420_frame(np.ascontiguousarray(fr, np.uint8)).tobytes())

@@ -31,6 +31,19 @@ class DeviceSearch:
         self.lib.check(self.lib.dll.jmme_set_reference_dev(self.ctx.handle, ref_idx, C.c_void_p(luma.data_ptr()),
                                                            luma.stride(0), self._stream()), self.ctx.handle)
 
+    def set_reference_chroma(self, ref_idx: int, cb: torch.Tensor, cr: torch.Tensor):
+        """chroma_me: the 4:2:0 chroma planes of reference `ref_idx` (uint8 cuda tensors of equal stride)."""
+        assert cb.is_cuda and cr.is_cuda and cb.dtype == cr.dtype == torch.uint8 and cb.stride() == cr.stride() and cb.stride(1) == 1
+        self.lib.check(self.lib.dll.jmme_set_reference_chroma_dev(self.ctx.handle, ref_idx, C.c_void_p(cb.data_ptr()),
+                                                                  C.c_void_p(cr.data_ptr()), cb.stride(0), self._stream()),
+                       self.ctx.handle)
+
+    def set_current_chroma(self, cb: torch.Tensor, cr: torch.Tensor):
+        assert cb.is_cuda and cr.is_cuda and cb.dtype == cr.dtype == torch.uint8 and cb.stride() == cr.stride() and cb.stride(1) == 1
+        self.lib.check(self.lib.dll.jmme_set_current_chroma_dev(self.ctx.handle, C.c_void_p(cb.data_ptr()),
+                                                                C.c_void_p(cr.data_ptr()), cb.stride(0), self._stream()),
+                       self.ctx.handle)
+
     def search(self, cur: torch.Tensor, pred: torch.Tensor | None = None, per_ref: bool = False,
                out: torch.Tensor | None = None) -> torch.Tensor:
         """out: optional uint8 cuda tensor with room for mb_w*mb_h records (whole-frame indexing)."""

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define JMME_ABI_VERSION     3
+#define JMME_ABI_VERSION     4
 #define JMME_BLOCKS_PER_MB   41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 */
 #define JMME_MAX_REFS        4
 #define JMME_MAX_SEARCH_RANGE 64
@@ -86,7 +86,10 @@ typedef struct jmme_params {
     int32_t search_mode;         /* JMME_SEARCH_*                                                */
     int32_t pred_policy;         /* JMME_PRED_*                                                  */
     int32_t satd_round;          /* 0: satd>>1 per 4x4 (Gen A), 1: (satd+1)>>1 (Gen B)           */
-    int32_t cost_domain;         /* 0: Gen A Q16 scale-down (only value implemented)             */
+    int32_t cost_domain;         /* 0: JM <= 10: J = D + (lambda_factor*bits >> 16), lambda_factor Q16           */
+                                 /* 1: JM >= 12 (JCOST_CALC_SCALEUP): J = (D << 5) + lambda_factor*bits,         */
+                                 /*    lambda_factor = (int)(32*lambda + 0.5); every cost returned is in that    */
+                                 /*    scaled-up domain                                           */
     int32_t mb_row_begin;        /* stripe of MB rows searched by this context: [begin, end)     */
     int32_t mb_row_end;          /* 0 = to the last row                                          */
     int32_t n_gpus;              /* 0/1 = one device; >1 = split the stripe over device_ids      */
@@ -97,7 +100,26 @@ typedef struct jmme_params {
     int32_t slice_rows;          /* JMME_PRED_MEDIAN: MB rows per slice (neighbours outside the  */
                                  /* slice are unavailable); 0 = one slice = the frame.  Stripes  */
                                  /* (mb_row_begin/end, n_gpus) start and end on slice boundaries */
+    /* ---- ABI 4: JM >= 12 distortion selection (MEDistortionFPel/HPel/QPel, Transform8x8Mode, ChromaMEEnable) --- */
+    int32_t me_distortion;       /* 0: legacy — integer stage SAD, sub-pel stages SAD or (use_hadamard) SATD     */
+                                 /* 1: the three fields below select the metric of each stage                    */
+    int32_t me_distortion_fpel;  /* JMME_DIST_*: integer-pel stage (JMME_DIST_HADAMARD is refused there)         */
+    int32_t me_distortion_hpel;  /* half-pel stage                                                               */
+    int32_t me_distortion_qpel;  /* quarter-pel stage                                                            */
+                                 /* a stage restarts at position 0 with the minimum reset when its metric        */
+                                 /* differs from the previous stage's (or chroma_me is on); an SSE stage uses    */
+                                 /* lambda^2 (JM: lambda_me = lambda_md for SSE)                                 */
+    int32_t transform8x8;        /* 1: Hadamard distortion of blocktypes 1..4 (>= 8x8) is the sum of 8x8         */
+                                 /* transforms, (sum|coef| + 2) >> 2 each (JM HadamardSAD8x8)                    */
+    int32_t chroma_me;           /* 1: the sub-pel stages add the distortion of both chroma blocks (4:2:0,       */
+                                 /* 1/8-pel bilinear samples, H.264 8.4.2.2.2); needs jmme_set_reference_chroma  */
+                                 /* and jmme_set_current_chroma                                                  */
 } jmme_params;
+
+/* distortion metrics (JM MEDistortion*: 0 SAD, 1 SSE, 2 Hadamard SAD) */
+#define JMME_DIST_SAD        0
+#define JMME_DIST_SSE        1
+#define JMME_DIST_HADAMARD   2
 
 /* One macroblock's result.  Block order: blocktype 1..7, raster order inside the MB
  * (index bases 0,1,3,5,9,17,25).  mv in quarter-pel units.  cost = distortion + MV rate
@@ -133,6 +155,11 @@ int         jmme_lambda_factor(int qp, int rdopt);     /* (int)(65536*lambda_mot
  * quarter-pel planes. */
 int jmme_set_reference(jmme_ctx *ctx, int ref_idx, const uint8_t *luma, int stride);
 
+/* chroma_me: the chroma planes (4:2:0, width/2 x height/2 each) of reference `ref_idx`, and of the current
+ * picture for the next jmme_search_frame.  Borders are replicated like the luma's. */
+int jmme_set_reference_chroma(jmme_ctx *ctx, int ref_idx, const uint8_t *cb, const uint8_t *cr, int stride);
+int jmme_set_current_chroma(jmme_ctx *ctx, const uint8_t *cb, const uint8_t *cr, int stride);
+
 /* Search every MB of the context's stripe against every reference.
  *   pred         NULL for JMME_PRED_ZERO / JMME_PRED_MEDIAN, else int16 [num_refs][mb_count][nb][2] in
  *                quarter-pel units, nb = 1 (PER_MB) or 41 (PER_BLOCK); mb_count = whole frame
@@ -156,6 +183,8 @@ int jmme_get_subimage(jmme_ctx *ctx, int ref_idx, int xfrac, int yfrac,
 int jmme_set_reference_dev(jmme_ctx *ctx, int ref_idx, const void *d_luma, int stride, void *stream);
 int jmme_search_frame_dev(jmme_ctx *ctx, const void *d_cur_luma, int stride, const void *d_pred,
                           void *d_out, void *d_out_per_ref, void *stream);
+int jmme_set_reference_chroma_dev(jmme_ctx *ctx, int ref_idx, const void *d_cb, const void *d_cr, int stride, void *stream);
+int jmme_set_current_chroma_dev(jmme_ctx *ctx, const void *d_cb, const void *d_cr, int stride, void *stream);
 /* Multi-GPU gather without a collective library: copy this context's stripe of the MV field from
  * d_field_local (whole-frame indexed, as written by jmme_search_frame_dev) into the same offsets of
  * n_peers peer buffers — device pointers mapped into this process (CUDA IPC / symmetric memory); the
@@ -238,6 +267,15 @@ int jmme_getSubImagesLuma(const uint8_t *luma, int width, int height, int stride
 
 /* (a11) n 4x4 difference blocks (raster, int16) -> n SATD values */
 int jmme_SATD(const int16_t *diff4x4, int n, int satd_round, int32_t *out);
+
+/* (f2) JM HadamardSAD8x8: n 8x8 difference blocks (raster, int16) -> (sum|H8 D H8'| + 2) >> 2 each
+ * (satd_round = 0: >> 2 without the rounding offset) */
+int jmme_HadamardSAD8x8(const int16_t *diff8x8, int n, int satd_round, int32_t *out);
+
+/* (f3) JM getSubImagesChroma for 4:2:0: the 64 eighth-pel planes of one chroma component, H.264 8.4.2.2.2:
+ * ((8-xF)(8-yF)A + xF(8-yF)B + (8-xF)yF C + xF yF D + 32) >> 6 with edge replication.  out[(yF*8+xF)] planes
+ * are contiguous, each (width+2*pad) x (height+2*pad) bytes (width, height: the chroma size). */
+int jmme_getSubImagesChroma(const uint8_t *chroma, int width, int height, int stride, int pad, uint8_t *out_planes);
 
 /* (a6) SAD surfaces of one MB: out[41][(2R+1)^2] in spiral order around centre (cx,cy)
  * (integer pel), including the 16x16 (0,0) bonus when bonus != 0 (subtracted at MV (0,0)).

@@ -42,6 +42,13 @@ struct jmme_ctx {
     jmme_params p;
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor;
     int n_planes;                    /* 16 with subpel, else 1 */
+    int metric[3];                   /* JMME_DIST_* of the integer, half-pel and quarter-pel stage */
+    int lf[3];                       /* lambda factor of each stage in the context's cost domain (SSE: lambda^2) */
+    int cpad, cstride, cheight;      /* chroma_me: padded integer chroma planes (w16/2 + 2 cpad) x (h16/2 + 2 cpad) */
+    uint8_t *cplanes[JMME_MAX_REFS][2];
+    int cref_set[JMME_MAX_REFS];
+    uint8_t *cur_c[2];               /* current chroma, padded to w16/2 x h16/2 by replication */
+    int cur_c_set;
     uint8_t *planes[JMME_MAX_REFS];  /* [n_planes] padded planes, contiguous */
     int ref_set[JMME_MAX_REFS];
     int32_t *mvbits;                 /* centred table, index v + MAX_MVD */
@@ -110,13 +117,29 @@ int jmme_lambda_factor(int qp, int rdopt) { return (int)(65536.0 * lambda_motion
 
 static int weighted_cost(int f, int bits) { return (int)(((int64_t)f * bits) >> 16); }
 
+/* Cost domains.  0 = JM <= 10: J = D + ((lambda_factor * bits) >> 16), lambda_factor Q16.
+ * 1 = JM >= 12 with JCOST_CALC_SCALEUP: LAMBDA_ACCURACY_BITS = 5, lambda_factor = (int)(32 lambda + 0.5),
+ * J = (D << 5) + lambda_factor * bits — the rate is not truncated, so ties fall differently. */
+#define SCALEUP_BITS 5
+static int wcost(int domain, int f, int bits) { return domain ? f * bits : weighted_cost(f, bits); }
+static int dscale(int domain, int d) { return domain ? d << SCALEUP_BITS : d; }
+/* lambda factor of a stage from lambda_motion; an SSE stage works with lambda^2 (JM: lambda_me = lambda_md for
+ * SSE, its square root otherwise) */
+static int stage_lambda_factor(int domain, double lambda, int metric)
+{
+    if (metric == JMME_DIST_SSE) lambda *= lambda;
+    return (int)((domain ? 32.0 : 65536.0) * lambda + 0.5);
+}
+
 /* MV_COST(f,s,cx,cy,px,py) = WEIGHTED_COST(f, mvbits[(cx<<s)-px] + mvbits[(cy<<s)-py]) is written
  * out at its call sites below (s = 2 for integer candidates, 0 for sub-pel ones). */
+/* reference rate, charged with the lambda factor of the last stage that ran */
 static int ref_cost(const jmme_ctx *c, int ref)
 {
-    if (c->p.rdopt) return weighted_cost(c->lambda_factor, ue_bits(ref));
+    const int f = c->lf[c->p.subpel ? 2 : 0], dom = c->p.cost_domain;
+    if (c->p.rdopt) return wcost(dom, f, ue_bits(ref));
     /* (int)(2*lambda*min(ref,1)); lambda is an integer when !rdopt */
-    return ref ? (int)((2 * (int64_t)c->lambda_factor) >> 16) : 0;
+    return ref ? (dom ? 2 * f : (int)((2 * (int64_t)f) >> 16)) : 0;
 }
 
 /* ---- (a12) UnifiedOneForthPix ‖ getSubImagesLuma [STD 8.4.2.2.1] ------------------------- */
@@ -235,6 +258,100 @@ int jmme_SATD(const int16_t *diff, int n, int satd_round, int32_t *out)
     return JMME_OK;
 }
 
+/* ---- (f2) HadamardSAD8x8: sum |H8 D H8'| over an 8x8 difference block, (s + 2) >> 2 ------------------- */
+static int satd8x8(const int *d, int satd_round)
+{
+    int m[64], i, j, s = 0;
+    for (i = 0; i < 64; i++) m[i] = d[i];
+    for (j = 0; j < 2; j++) {                       /* rows, then columns (after the transpose below) */
+        int t[64];
+        for (i = 0; i < 8; i++) {
+            const int *r = m + 8 * i;
+            int a0 = r[0] + r[4], a1 = r[1] + r[5], a2 = r[2] + r[6], a3 = r[3] + r[7];
+            int a4 = r[0] - r[4], a5 = r[1] - r[5], a6 = r[2] - r[6], a7 = r[3] - r[7];
+            int b0 = a0 + a2, b1 = a1 + a3, b2 = a0 - a2, b3 = a1 - a3;
+            int b4 = a4 + a6, b5 = a5 + a7, b6 = a4 - a6, b7 = a5 - a7;
+            /* transposed store: the second pass transforms the columns */
+            t[0 * 8 + i] = b0 + b1; t[1 * 8 + i] = b0 - b1; t[2 * 8 + i] = b2 + b3; t[3 * 8 + i] = b2 - b3;
+            t[4 * 8 + i] = b4 + b5; t[5 * 8 + i] = b4 - b5; t[6 * 8 + i] = b6 + b7; t[7 * 8 + i] = b6 - b7;
+        }
+        memcpy(m, t, sizeof m);
+    }
+    for (i = 0; i < 64; i++) s += m[i] < 0 ? -m[i] : m[i];
+    return satd_round ? (s + 2) >> 2 : s >> 2;
+}
+int jmme_HadamardSAD8x8(const int16_t *diff, int n, int satd_round, int32_t *out)
+{
+    int i, k, d[64];
+    if (!diff || !out || n < 0) return JMME_ERR_PARAM;
+    for (i = 0; i < n; i++) {
+        for (k = 0; k < 64; k++) d[k] = diff[64 * i + k];
+        out[i] = satd8x8(d, satd_round);
+    }
+    return JMME_OK;
+}
+
+/* distortion of a bw x bh block of differences cur - ref under `metric` (JMME_DIST_*); t8: 8x8 transform tiles
+ * (both dimensions >= 8), else 4x4 tiles; blocks smaller than 4x4 in a dimension (chroma of the small luma
+ * partitions) fall back to SAD under the Hadamard metric (frozen choice) */
+static int block_dist(const uint8_t *cur, int cs, const uint8_t *ref, int rs, int bw, int bh, int metric, int t8,
+                      int satd_round)
+{
+    int x, y, x0, y0, s = 0, d[64];
+    if (metric == JMME_DIST_HADAMARD && (bw < 4 || bh < 4)) metric = JMME_DIST_SAD;
+    if (metric != JMME_DIST_HADAMARD) {
+        for (y = 0; y < bh; y++)
+            for (x = 0; x < bw; x++) {
+                const int e = (int)cur[y * cs + x] - (int)ref[y * rs + x];
+                s += metric == JMME_DIST_SSE ? e * e : (e < 0 ? -e : e);
+            }
+        return s;
+    }
+    if (t8 && bw >= 8 && bh >= 8) {
+        for (y0 = 0; y0 < bh; y0 += 8)
+            for (x0 = 0; x0 < bw; x0 += 8) {
+                for (y = 0; y < 8; y++)
+                    for (x = 0; x < 8; x++) d[8 * y + x] = (int)cur[(y0 + y) * cs + x0 + x] - (int)ref[(y0 + y) * rs + x0 + x];
+                s += satd8x8(d, satd_round);
+            }
+        return s;
+    }
+    for (y0 = 0; y0 < bh; y0 += 4)
+        for (x0 = 0; x0 < bw; x0 += 4) {
+            for (y = 0; y < 4; y++)
+                for (x = 0; x < 4; x++) d[4 * y + x] = (int)cur[(y0 + y) * cs + x0 + x] - (int)ref[(y0 + y) * rs + x0 + x];
+            s += satd4x4(d, satd_round);
+        }
+    return s;
+}
+
+/* ---- (f3) chroma samples at eighth-pel positions [STD 8.4.2.2.2] ------------------------------------------ */
+/* plane: padded integer chroma plane, (0,0) of the picture at (cpad, cpad); (x, y) integer chroma position,
+ * (xf, yf) in 0..7.  The caller keeps x+1, y+1 inside the padded plane. */
+static int chroma_sample(const uint8_t *plane, int cstride, int cpad, int x, int y, int xf, int yf)
+{
+    const uint8_t *a = plane + (size_t)(y + cpad) * cstride + (x + cpad);
+    return ((8 - xf) * (8 - yf) * a[0] + xf * (8 - yf) * a[1] + (8 - xf) * yf * a[cstride] + xf * yf * a[cstride + 1] + 32) >> 6;
+}
+int jmme_getSubImagesChroma(const uint8_t *chroma, int width, int height, int stride, int pad, uint8_t *out)
+{
+    int x, y, xf, yf;
+    const int ps = width + 2 * pad, ph = height + 2 * pad;
+    if (!chroma || !out || width <= 0 || height <= 0 || pad < 0 || stride < width) return JMME_ERR_PARAM;
+    for (yf = 0; yf < 8; yf++)
+        for (xf = 0; xf < 8; xf++) {
+            uint8_t *o = out + (size_t)ps * ph * (yf * 8 + xf);
+            for (y = 0; y < ph; y++)
+                for (x = 0; x < ps; x++) {
+#define CS(xx, yy) chroma[(size_t)clampi((yy) - pad, 0, height - 1) * stride + clampi((xx) - pad, 0, width - 1)]
+                    o[(size_t)y * ps + x] = (uint8_t)(((8 - xf) * (8 - yf) * CS(x, y) + xf * (8 - yf) * CS(x + 1, y) +
+                                                       (8 - xf) * yf * CS(x, y + 1) + xf * yf * CS(x + 1, y + 1) + 32) >> 6);
+#undef CS
+                }
+        }
+    return JMME_OK;
+}
+
 /* ---- context ----------------------------------------------------------------------------- */
 static int set_err(jmme_ctx *c, int code, const char *msg)
 {
@@ -261,9 +378,17 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
         (p->blocktype_mask & ~JMME_MASK_ALL) || !(p->blocktype_mask & JMME_MASK_ALL) ||
         p->qp < 0 || p->qp > 51 || p->lambda_factor < 0 ||
         p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 3 ||
-        p->satd_round < 0 || p->satd_round > 1 || p->slice_rows < 0)
+        p->satd_round < 0 || p->satd_round > 1 || p->slice_rows < 0 || p->cost_domain < 0 || p->cost_domain > 1 ||
+        p->me_distortion < 0 || p->me_distortion > 1 || p->transform8x8 < 0 || p->transform8x8 > 1 ||
+        p->chroma_me < 0 || p->chroma_me > 1)
         return JMME_ERR_PARAM;
-    if (p->cost_domain != 0) return JMME_ERR_UNSUPPORTED;
+    if (p->me_distortion &&
+        (p->me_distortion_fpel < 0 || p->me_distortion_fpel > 2 || p->me_distortion_hpel < 0 || p->me_distortion_hpel > 2 ||
+         p->me_distortion_qpel < 0 || p->me_distortion_qpel > 2))
+        return JMME_ERR_PARAM;
+    /* the integer stage builds its surfaces from per-pixel sums (SAD or SSE); a Hadamard integer stage is refused */
+    if (p->me_distortion && p->me_distortion_fpel == JMME_DIST_HADAMARD) return JMME_ERR_UNSUPPORTED;
+    if (p->chroma_me && !p->subpel) return JMME_ERR_PARAM;      /* chroma enters at the sub-pel stages */
     c = (jmme_ctx *)calloc(1, sizeof *c);
     if (!c) return JMME_ERR_NOMEM;
     c->p = *p;
@@ -281,8 +406,18 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
     }
     c->pad = pad_for(p->search_range);
     c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
-    c->lambda_factor = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
-    if (c->lambda_factor > (96 << 16)) { free(c); return JMME_ERR_PARAM; }
+    {
+        const int lf16 = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
+        const double lambda = p->lambda_factor ? (double)p->lambda_factor / 65536.0 : lambda_motion(p->qp, p->rdopt);
+        int st;
+        if (lf16 > (96 << 16)) { free(c); return JMME_ERR_PARAM; }
+        c->metric[0] = p->me_distortion ? p->me_distortion_fpel : JMME_DIST_SAD;
+        c->metric[1] = p->me_distortion ? p->me_distortion_hpel : (p->use_hadamard ? JMME_DIST_HADAMARD : JMME_DIST_SAD);
+        c->metric[2] = p->me_distortion ? p->me_distortion_qpel : (p->use_hadamard ? JMME_DIST_HADAMARD : JMME_DIST_SAD);
+        for (st = 0; st < 3; st++) c->lf[st] = stage_lambda_factor(p->cost_domain, lambda, c->metric[st]);
+        c->lambda_factor = c->lf[0];
+    }
+    c->cpad = c->pad / 2; c->cstride = c->w16 / 2 + 2 * c->cpad; c->cheight = c->h16 / 2 + 2 * c->cpad;
     c->n_planes = p->subpel ? 16 : 1;
     c->ncand = (2 * p->search_range + 1) * (2 * p->search_range + 1);
     c->mvbits = (int32_t *)malloc(sizeof(int32_t) * (2 * MAX_MVD + 1));
@@ -298,7 +433,8 @@ int jmme_destroy(jmme_ctx *c)
 {
     int r;
     if (!c) return JMME_OK;
-    for (r = 0; r < JMME_MAX_REFS; r++) free(c->planes[r]);
+    for (r = 0; r < JMME_MAX_REFS; r++) { free(c->planes[r]); free(c->cplanes[r][0]); free(c->cplanes[r][1]); }
+    free(c->cur_c[0]); free(c->cur_c[1]);
     free(c->med_pred); free(c->fmv); free(c->fref);
     free(c->mvbits); free(c->spx); free(c->spy); free(c);
     return JMME_OK;
@@ -364,6 +500,46 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
     if (rc == JMME_OK) c->ref_set[r] = 1;
     return rc;
 }
+/* replicate a (w x h) chroma picture into a plane of (pw x ph) with `pad` border samples on every side */
+static uint8_t *pad_chroma(const uint8_t *src, int w, int h, int stride, int pw, int ph, int pad, uint8_t *dst)
+{
+    int x, y;
+    if (!dst) dst = (uint8_t *)malloc((size_t)pw * ph);
+    if (!dst) return NULL;
+    for (y = 0; y < ph; y++)
+        for (x = 0; x < pw; x++)
+            dst[(size_t)y * pw + x] = src[(size_t)clampi(y - pad, 0, h - 1) * stride + clampi(x - pad, 0, w - 1)];
+    return dst;
+}
+int jmme_set_reference_chroma(jmme_ctx *c, int r, const uint8_t *cb, const uint8_t *cr, int stride)
+{
+    const uint8_t *src[2];
+    int k;
+    if (!c || !cb || !cr || r < 0 || r >= c->p.num_refs || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
+    if (!c->p.chroma_me) return set_err(c, JMME_ERR_STATE, "chroma_me is off");
+    src[0] = cb; src[1] = cr;
+    for (k = 0; k < 2; k++) {
+        c->cplanes[r][k] = pad_chroma(src[k], (c->p.width + 1) / 2, (c->p.height + 1) / 2, stride, c->cstride, c->cheight,
+                                      c->cpad, c->cplanes[r][k]);
+        if (!c->cplanes[r][k]) return set_err(c, JMME_ERR_NOMEM, "chroma plane allocation failed");
+    }
+    c->cref_set[r] = 1;
+    return JMME_OK;
+}
+int jmme_set_current_chroma(jmme_ctx *c, const uint8_t *cb, const uint8_t *cr, int stride)
+{
+    const uint8_t *src[2];
+    int k;
+    if (!c || !cb || !cr || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
+    if (!c->p.chroma_me) return set_err(c, JMME_ERR_STATE, "chroma_me is off");
+    src[0] = cb; src[1] = cr;
+    for (k = 0; k < 2; k++) {
+        c->cur_c[k] = pad_chroma(src[k], (c->p.width + 1) / 2, (c->p.height + 1) / 2, stride, c->w16 / 2, c->h16 / 2, 0, c->cur_c[k]);
+        if (!c->cur_c[k]) return set_err(c, JMME_ERR_NOMEM, "chroma allocation failed");
+    }
+    c->cur_c_set = 1;
+    return JMME_OK;
+}
 int jmme_get_subimage(jmme_ctx *c, int r, int xf, int yf, uint8_t *dst, int dst_stride)
 {
     int y;
@@ -379,6 +555,10 @@ int jmme_get_subimage(jmme_ctx *c, int r, int xf, int yf, uint8_t *dst, int dst_
 }
 int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d, int s, void *st)
 { (void)r; (void)d; (void)s; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
+int jmme_set_reference_chroma_dev(jmme_ctx *c, int r, const void *a, const void *b, int s, void *st)
+{ (void)r; (void)a; (void)b; (void)s; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
+int jmme_set_current_chroma_dev(jmme_ctx *c, const void *a, const void *b, int s, void *st)
+{ (void)a; (void)b; (void)s; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
 int jmme_search_frame_dev(jmme_ctx *c, const void *a, int s, const void *b, void *o, void *o2, void *st)
 { (void)a; (void)s; (void)b; (void)o; (void)o2; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
 
@@ -388,32 +568,39 @@ static const uint8_t *plane_at(const uint8_t *base, int pstride, int pad, int x,
 {
     return base + (size_t)(y + pad) * pstride + (x + pad);
 }
-static int sad_block(const uint8_t *cur, int cs, const uint8_t *ref, int rs, int bw, int bh)
-{
-    int x, y, s = 0;
-    for (y = 0; y < bh; y++)
-        for (x = 0; x < bw; x++) {
-            int d = (int)cur[y * cs + x] - (int)ref[y * rs + x];
-            s += d < 0 ? -d : d;
-        }
-    return s;
-}
-/* distortion of a block at quarter-pel MV (qx,qy): SAD, or sum of 4x4 SATDs (a10/a11) */
+/* what the stages of one block search need beyond the pictures */
+typedef struct stage_cfg {
+    int domain;                      /* cost domain 0 / 1 */
+    int metric[3], lf[3], bonus[3];  /* per stage (integer, half, quarter): JMME_DIST_*, lambda factor, 16x16 (0,0) bonus */
+    int satd_round, t8;              /* SATD rounding; 8x8 transform tiles for blocks >= 8x8 */
+    int chroma;                      /* 1: sub-pel stages add both chroma blocks */
+    const uint8_t *cplane[2];        /* padded integer chroma planes of the reference */
+    int cstride, cpad;
+    const uint8_t *cur_c[2];         /* current chroma, stride cur_cs */
+    int cur_cs;
+} stage_cfg;
+
+/* distortion of a block at quarter-pel MV (qx,qy) under stage st's metric: luma from the 16 quarter-pel planes
+ * (a10/a11), plus — chroma ME, sub-pel stages — both chroma blocks sampled at eighth-pel positions */
 static int subpel_dist(const uint8_t *cur, int cs, const uint8_t *planes, int pstride, int pheight,
-                       int pad, int bx, int by, int bw, int bh, int qx, int qy, int hadamard,
-                       int satd_round)
+                       int pad, int bx, int by, int bw, int bh, int qx, int qy, const stage_cfg *g, int st)
 {
     const uint8_t *pl = planes + (size_t)pstride * pheight * ((qy & 3) * 4 + (qx & 3));
     const uint8_t *ref = plane_at(pl, pstride, pad, bx + (qx >> 2), by + (qy >> 2));
-    int x0, y0, x, y, s = 0, d[16];
-    if (!hadamard) return sad_block(cur, cs, ref, pstride, bw, bh);
-    for (y0 = 0; y0 < bh; y0 += 4)
-        for (x0 = 0; x0 < bw; x0 += 4) {
-            for (y = 0; y < 4; y++)
-                for (x = 0; x < 4; x++)
-                    d[4 * y + x] = (int)cur[(y0 + y) * cs + x0 + x] - (int)ref[(y0 + y) * pstride + x0 + x];
-            s += satd4x4(d, satd_round);
+    int s = block_dist(cur, cs, ref, pstride, bw, bh, g->metric[st], g->t8, g->satd_round);
+    if (g->chroma) {
+        /* 4:2:0: the luma vector in quarter-pel units is the chroma vector in eighth-pel units [STD 8.4.1.4] */
+        const int cw = bw / 2, ch = bh / 2, cx0 = bx / 2 + (qx >> 3), cy0 = by / 2 + (qy >> 3);
+        uint8_t pred[64];
+        int k, x, y;
+        for (k = 0; k < 2; k++) {
+            for (y = 0; y < ch; y++)
+                for (x = 0; x < cw; x++)
+                    pred[8 * y + x] = (uint8_t)chroma_sample(g->cplane[k], g->cstride, g->cpad, cx0 + x, cy0 + y, qx & 7, qy & 7);
+            s += block_dist(g->cur_c[k] + (size_t)(by / 2) * g->cur_cs + bx / 2, g->cur_cs, pred, 8, cw, ch,
+                            g->metric[st], 0, g->satd_round);
         }
+    }
     return s;
 }
 
@@ -422,7 +609,7 @@ static int subpel_dist(const uint8_t *cur, int cs, const uint8_t *planes, int ps
  * 16x16 <- 16x8.  out[41][ncand]. */
 static void setup_fastfull(const uint8_t *cur, int cs, const uint8_t *ref00, int rs, int mbx, int mby,
                            int cx, int cy, int ncand, const int16_t *spx, const int16_t *spy,
-                           int bonus, int32_t *out)
+                           int bonus, int metric, int32_t *out)
 {
     int pos, b, i, j;
     for (pos = 0; pos < ncand; pos++) {
@@ -431,7 +618,7 @@ static void setup_fastfull(const uint8_t *cur, int cs, const uint8_t *ref00, int
         int s44[4][4], s84[4][2], s48[2][4], s88[2][2];
         for (j = 0; j < 4; j++)
             for (i = 0; i < 4; i++)
-                s44[j][i] = sad_block(cur + 4 * j * cs + 4 * i, cs, r + 4 * j * rs + 4 * i, rs, 4, 4);
+                s44[j][i] = block_dist(cur + 4 * j * cs + 4 * i, cs, r + 4 * j * rs + 4 * i, rs, 4, 4, metric, 0, 0);
         for (j = 0; j < 4; j++) for (i = 0; i < 2; i++) s84[j][i] = s44[j][2 * i] + s44[j][2 * i + 1];
         for (j = 0; j < 2; j++) for (i = 0; i < 4; i++) s48[j][i] = s44[2 * j][i] + s44[2 * j + 1][i];
         for (j = 0; j < 2; j++) for (i = 0; i < 2; i++) s88[j][i] = s84[2 * j][i] + s84[2 * j + 1][i];
@@ -459,28 +646,30 @@ int jmme_SetupFastFullPelSearch(const uint8_t *cur, int cs, const uint8_t *ref, 
     sx = (int16_t *)malloc(2 * n); sy = (int16_t *)malloc(2 * n);
     if (!sx || !sy) { free(sx); free(sy); return JMME_ERR_NOMEM; }
     build_spiral(R, sx, sy);
-    setup_fastfull(cur, cs, ref, rs, mbx, mby, cx, cy, n, sx, sy, bonus, out);
+    setup_fastfull(cur, cs, ref, rs, mbx, mby, cx, cy, n, sx, sy, bonus, JMME_DIST_SAD, out);
     free(sx); free(sy);
     return JMME_OK;
 }
 
 /* ---- (a7) FastFullPelBlockMotionSearch ---------------------------------------------------- */
 static void fastfull_block(const int32_t *sad, int ncand, const int16_t *spx, const int16_t *spy,
-                           const int32_t *mvbits, int f, int cx, int cy, int px, int py, int pretest,
-                           int *best_pos, int *best_cost)
+                           const int32_t *mvbits, int domain, int f, int cx, int cy, int px, int py, int pretest,
+                           int bonus, int *best_pos, int *best_cost)
 {
     int pos, min = INT_MAX, bp = 0;
-#define MVC(mx, my) weighted_cost(f, mvbits[4 * (mx) - px + MAX_MVD] + mvbits[4 * (my) - py + MAX_MVD])
+    /* bonus: the 16x16 block's (0,0) bias when it has not been folded into the surface already */
+#define COST(p_, mx, my) (dscale(domain, sad[p_]) + wcost(domain, f, mvbits[4 * (mx) - px + MAX_MVD] + mvbits[4 * (my) - py + MAX_MVD]) \
+                          - (((mx) == 0 && (my) == 0) ? bonus : 0))
     if (pretest) {                                  /* MV (0,0) first when !rdopt */
         for (pos = 0; pos < ncand; pos++)
             if (cx + spx[pos] == 0 && cy + spy[pos] == 0) break;
-        if (pos < ncand) { min = sad[pos] + MVC(0, 0); bp = pos; }
+        if (pos < ncand) { min = COST(pos, 0, 0); bp = pos; }
     }
     for (pos = 0; pos < ncand; pos++) {
-        int c = sad[pos] + MVC(cx + spx[pos], cy + spy[pos]);
+        int c = COST(pos, cx + spx[pos], cy + spy[pos]);
         if (c < min) { min = c; bp = pos; }
     }
-#undef MVC
+#undef COST
     *best_pos = bp; *best_cost = min;
 }
 int jmme_FastFullPelBlockMotionSearch(const int32_t *sad, int R, int cx, int cy, int px, int py, int f,
@@ -496,7 +685,7 @@ int jmme_FastFullPelBlockMotionSearch(const int32_t *sad, int R, int cx, int cy,
     if (!sx || !sy || !mvb) { free(sx); free(sy); free(mvb); return JMME_ERR_NOMEM; }
     for (v = -MAX_MVD; v <= MAX_MVD; v++) mvb[v + MAX_MVD] = se_bits(v);
     build_spiral(R, sx, sy);
-    fastfull_block(sad, n, sx, sy, mvb, f, cx, cy, px, py, pretest, &bp, &bc);
+    fastfull_block(sad, n, sx, sy, mvb, 0, f, cx, cy, px, py, pretest, 0, &bp, &bc);
     *mvx = (int16_t)(cx + sx[bp]); *mvy = (int16_t)(cy + sy[bp]); *cost = bc;
     free(sx); free(sy); free(mvb);
     return JMME_OK;
@@ -505,14 +694,15 @@ int jmme_FastFullPelBlockMotionSearch(const int32_t *sad, int R, int cx, int cy,
 /* ---- (a8) FullPelBlockMotionSearch -------------------------------------------------------- */
 static void full_block(const uint8_t *cur, int cs, const uint8_t *ref00, int rs, int bx, int by, int bw,
                        int bh, int cx, int cy, int px, int py, int ncand, const int16_t *spx,
-                       const int16_t *spy, const int32_t *mvbits, int f, int bonus, int *bmx, int *bmy,
-                       int *bcost)
+                       const int16_t *spy, const int32_t *mvbits, int domain, int metric, int f, int bonus, int *bmx,
+                       int *bmy, int *bcost)
 {
     int pos, min = INT_MAX, mx0 = cx, my0 = cy;
     for (pos = 0; pos < ncand; pos++) {
         int mx = cx + spx[pos], my = cy + spy[pos];
-        int c = weighted_cost(f, mvbits[4 * mx - px + MAX_MVD] + mvbits[4 * my - py + MAX_MVD]);
-        c += sad_block(cur + (size_t)by * cs + bx, cs, ref00 + (size_t)(by + my) * rs + (bx + mx), rs, bw, bh);
+        int c = wcost(domain, f, mvbits[4 * mx - px + MAX_MVD] + mvbits[4 * my - py + MAX_MVD]);
+        c += dscale(domain, block_dist(cur + (size_t)by * cs + bx, cs, ref00 + (size_t)(by + my) * rs + (bx + mx), rs, bw, bh,
+                                       metric, 0, 0));
         if (mx == 0 && my == 0) c -= bonus;
         if (c < min) { min = c; mx0 = mx; my0 = my; }
     }
@@ -533,7 +723,7 @@ int jmme_FullPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *ref
     for (v = -MAX_MVD; v <= MAX_MVD; v++) mvb[v + MAX_MVD] = se_bits(v);
     build_spiral(R, sx, sy);
     cx = clampi(px / 4, -R, R); cy = clampi(py / 4, -R, R);
-    full_block(cur, cs, ref, rs, bx, by, bw, bh, cx, cy, px, py, n, sx, sy, mvb, f, bonus, &mx, &my, &mc);
+    full_block(cur, cs, ref, rs, bx, by, bw, bh, cx, cy, px, py, n, sx, sy, mvb, 0, JMME_DIST_SAD, f, bonus, &mx, &my, &mc);
     *mvx = (int16_t)mx; *mvy = (int16_t)my; *cost = mc;
     free(sx); free(sy); free(mvb);
     return JMME_OK;
@@ -541,26 +731,31 @@ int jmme_FullPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *ref
 
 /* ---- (a10) SubPelBlockMotionSearch -------------------------------------------------------- */
 /* In: integer MV (quarter-pel units, multiple of 4) and its integer-search cost.
- * Half-pel: spiral positions (0 when hadamard else 1)..8, step 2; quarter-pel: positions 1..8,
- * step 1, around the half-pel winner.  Strict <.  No early termination (result-neutral in JM
- * except in combination with the (0,0) bonus; the frozen spec is the plain argmin). */
+ * Half-pel: spiral positions 1..8, step 2; quarter-pel: positions 1..8, step 1, around the half-pel winner.
+ * A stage whose metric differs from the previous stage's (or any sub-pel stage with chroma ME) starts at
+ * position 0 with the running minimum reset (JM start_me_refinement_hp / _qp).  Strict <.  No early
+ * termination (result-neutral in JM except in combination with the (0,0) bonus; the frozen spec is the plain
+ * argmin). */
 static void subpel_block(const uint8_t *cur, int cs, const uint8_t *planes, int pstride, int pheight,
                          int pad, int bx, int by, int bw, int bh, int px, int py, const int32_t *mvbits,
-                         int f, int hadamard, int satd_round, int bonus, const int16_t *spx,
-                         const int16_t *spy, int *mvx, int *mvy, int *cost)
+                         const stage_cfg *g, const int16_t *spx, const int16_t *spy, int *mvx, int *mvy, int *cost)
 {
-    int pos, step, bmx = *mvx, bmy = *mvy, min = hadamard ? INT_MAX : *cost;
+    int pos, step, bmx = *mvx, bmy = *mvy, min = *cost, prev = g->metric[0];
     for (step = 2; step >= 1; step--) {
+        const int st = step == 2 ? 1 : 2;
+        const int restart = g->chroma || g->metric[st] != prev;
         int ox = bmx, oy = bmy, best = 0;
-        for (pos = (step == 2 && hadamard) ? 0 : 1; pos < 9; pos++) {
+        if (restart) min = INT_MAX;
+        for (pos = restart ? 0 : 1; pos < 9; pos++) {
             int qx = ox + step * spx[pos], qy = oy + step * spy[pos];
-            int c = weighted_cost(f, mvbits[qx - px + MAX_MVD] + mvbits[qy - py + MAX_MVD]);
-            c += subpel_dist(cur + (size_t)by * cs + bx, cs, planes, pstride, pheight, pad, bx, by, bw, bh,
-                             qx, qy, hadamard, satd_round);
-            if (qx == 0 && qy == 0) c -= bonus;
+            int c = wcost(g->domain, g->lf[st], mvbits[qx - px + MAX_MVD] + mvbits[qy - py + MAX_MVD]);
+            c += dscale(g->domain, subpel_dist(cur + (size_t)by * cs + bx, cs, planes, pstride, pheight, pad, bx, by, bw, bh,
+                                               qx, qy, g, st));
+            if (qx == 0 && qy == 0) c -= g->bonus[st];
             if (c < min) { min = c; best = pos; }
         }
         bmx = ox + step * spx[best]; bmy = oy + step * spy[best];
+        prev = g->metric[st];
     }
     *mvx = bmx; *mvy = bmy; *cost = min;
 }
@@ -571,7 +766,8 @@ int jmme_SubPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *plan
 {
     int16_t sx[9], sy[9];
     int32_t *mvb;
-    int v, x, y, c;
+    int v, x, y, c, st;
+    stage_cfg g;
     if (!cur || !planes || !mvx || !mvy || !cost) return JMME_ERR_PARAM;
     if (abs(px) > MAX_PRED || abs(py) > MAX_PRED) return JMME_ERR_PARAM;
     mvb = (int32_t *)malloc(sizeof(int32_t) * (2 * MAX_MVD + 1));
@@ -579,8 +775,12 @@ int jmme_SubPelBlockMotionSearch(const uint8_t *cur, int cs, const uint8_t *plan
     for (v = -MAX_MVD; v <= MAX_MVD; v++) mvb[v + MAX_MVD] = se_bits(v);
     build_spiral(1, sx, sy);
     x = *mvx; y = *mvy; c = *cost;
-    subpel_block(cur, cs, planes, width + 2 * pad, height + 2 * pad, pad, bx, by, bw, bh, px, py, mvb, f,
-                 hadamard, satd_round, bonus, sx, sy, &x, &y, &c);
+    memset(&g, 0, sizeof g);                        /* the leaf is the legacy (JM <= 10) form: domain 0 */
+    g.metric[0] = JMME_DIST_SAD; g.metric[1] = g.metric[2] = hadamard ? JMME_DIST_HADAMARD : JMME_DIST_SAD;
+    for (st = 0; st < 3; st++) { g.lf[st] = f; g.bonus[st] = bonus; }
+    g.satd_round = satd_round;
+    subpel_block(cur, cs, planes, width + 2 * pad, height + 2 * pad, pad, bx, by, bw, bh, px, py, mvb, &g,
+                 sx, sy, &x, &y, &c);
     *mvx = (int16_t)x; *mvy = (int16_t)y; *cost = c;
     free(mvb);
     return JMME_OK;
@@ -758,9 +958,14 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
 {
     const int R = c->p.search_range, nmb = c->mb_w * c->mb_h, mb = mby * c->mb_w + mbx;
     const int npb = c->p.pred_policy >= JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
-    const int bonus_base = c->p.rdopt ? 0 : weighted_cost(c->lambda_factor, 16);
+    const int dom = c->p.cost_domain;
     jmme_mbresult *o = &out[mb];
-    int r, t, b;
+    stage_cfg g;
+    int r, t, b, st;
+    memset(&g, 0, sizeof g);
+    g.domain = dom; g.satd_round = c->p.satd_round; g.t8 = c->p.transform8x8; g.chroma = c->p.chroma_me;
+    for (st = 0; st < 3; st++) { g.metric[st] = c->metric[st]; g.lf[st] = c->lf[st]; }
+    g.cstride = c->cstride; g.cpad = c->cpad; g.cur_c[0] = c->cur_c[0]; g.cur_c[1] = c->cur_c[1]; g.cur_cs = c->w16 / 2;
     for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
         o->mv[b][0] = o->mv[b][1] = 0; o->cost[b] = INT_MAX; o->ref_idx[b] = -1;
     }
@@ -768,10 +973,11 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
     for (r = 0; r < c->p.num_refs; r++) {
         const uint8_t *ref00 = plane_at(c->planes[r], c->pstride, c->pad, 0, 0);   /* integer plane */
         const int16_t *pr = pred ? pred + ((size_t)r * nmb + mb) * npb * 2 : NULL;
-        const int bonus = r == 0 ? bonus_base : 0;
+        const int has_bonus = !c->p.rdopt && r == 0;       /* 16x16 (0,0) bias: !rdopt, reference 0 */
         jmme_mbresult *opr = out_per_ref ? &out_per_ref[(size_t)r * nmb + mb] : NULL;
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
         const int cx = clampi(p16x / 4, -R, R), cy = clampi(p16y / 4, -R, R);
+        g.cplane[0] = c->cplanes[r][0]; g.cplane[1] = c->cplanes[r][1];
         if (opr) {
             for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
                 opr->mv[b][0] = opr->mv[b][1] = 0; opr->cost[b] = INT_MAX; opr->ref_idx[b] = -1;
@@ -780,11 +986,12 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
         }
         if (c->p.search_mode == JMME_SEARCH_FASTFULL)
             setup_fastfull(cur + (size_t)16 * mby * c->w16 + 16 * mbx, c->w16, ref00, c->pstride, mbx, mby, cx,
-                           cy, c->ncand, c->spx, c->spy, bonus, bsad);
+                           cy, c->ncand, c->spx, c->spy, 0, c->metric[0], bsad);
         for (t = 1; t <= 7; t++) {
             const int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh;
             int j, i;
             if (!(c->p.blocktype_mask & (1 << t))) continue;
+            for (st = 0; st < 3; st++) g.bonus[st] = (t == 1 && has_bonus) ? wcost(dom, c->lf[st], 16) : 0;
             for (j = 0; j < nby; j++)
                 for (i = 0; i < nbx; i++) {
                     const int blk = blk_base[t] + j * nbx + i;
@@ -794,20 +1001,18 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
                     int mvx, mvy, cost, total;
                     if (c->p.search_mode == JMME_SEARCH_FASTFULL) {
                         int bp;
-                        fastfull_block(bsad + (size_t)blk * c->ncand, c->ncand, c->spx, c->spy, c->mvbits,
-                                       c->lambda_factor, cx, cy, px, py, !c->p.rdopt, &bp, &cost);
+                        fastfull_block(bsad + (size_t)blk * c->ncand, c->ncand, c->spx, c->spy, c->mvbits, dom,
+                                       c->lf[0], cx, cy, px, py, !c->p.rdopt, g.bonus[0], &bp, &cost);
                         mvx = cx + c->spx[bp]; mvy = cy + c->spy[bp];
                     } else {
                         const int bcx = clampi(px / 4, -R, R), bcy = clampi(py / 4, -R, R);
                         full_block(cur, c->w16, ref00, c->pstride, bx, by, bw, bh, bcx, bcy, px, py, c->ncand,
-                                   c->spx, c->spy, c->mvbits, c->lambda_factor, t == 1 ? bonus : 0, &mvx, &mvy,
-                                   &cost);
+                                   c->spx, c->spy, c->mvbits, dom, c->metric[0], c->lf[0], g.bonus[0], &mvx, &mvy, &cost);
                     }
                     mvx *= 4; mvy *= 4;
                     if (c->p.subpel)
                         subpel_block(cur, c->w16, c->planes[r], c->pstride, c->pheight, c->pad, bx, by, bw, bh, px,
-                                     py, c->mvbits, c->lambda_factor, c->p.use_hadamard, c->p.satd_round,
-                                     t == 1 ? bonus : 0, c->spx, c->spy, &mvx, &mvy, &cost);
+                                     py, c->mvbits, &g, c->spx, c->spy, &mvx, &mvy, &cost);
                     if (opr) {
                         opr->mv[blk][0] = (int16_t)mvx; opr->mv[blk][1] = (int16_t)mvy;
                         opr->cost[blk] = cost; opr->ref_idx[blk] = (int8_t)r;
@@ -832,6 +1037,11 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
     else if (c->p.pred_policy != JMME_PRED_ZERO && !pred) return set_err(c, JMME_ERR_PARAM, "pred required");
     for (r = 0; r < c->p.num_refs; r++)
         if (!c->ref_set[r]) return set_err(c, JMME_ERR_STATE, "reference not set");
+    if (c->p.chroma_me) {
+        if (!c->cur_c_set) return set_err(c, JMME_ERR_STATE, "current chroma not set");
+        for (r = 0; r < c->p.num_refs; r++)
+            if (!c->cref_set[r]) return set_err(c, JMME_ERR_STATE, "reference chroma not set");
+    }
     nmb = c->mb_w * c->mb_h;
     npb = c->p.pred_policy == JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
     if (c->p.pred_policy == JMME_PRED_MEDIAN && !c->med_pred) {

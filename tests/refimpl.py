@@ -222,3 +222,108 @@ def commit_field(res, mb_w, mb_h, mask=0xFE):
                 mv4[4 * mby + cy, 4 * mbx + cx] = res[mb]["mv"][b]
                 ref4[4 * mby + cy, 4 * mbx + cx] = res[mb]["ref_idx"][b]
     return mv4, ref4, mode
+
+
+# ---- round 2: cost domains, SSE / 8x8 Hadamard, chroma ME — restated from DESIGN.md §2 -------------------
+H8 = np.kron(np.array([[1, 1], [1, -1]], dtype=np.int64), H4)          # any +-1 ordering: sum|.| is order-free
+
+
+def satd8x8(d, satd_round=1):
+    """JM HadamardSAD8x8: (sum |H8 D H8'| + 2) >> 2."""
+    d = np.asarray(d, dtype=np.int64).reshape(8, 8)
+    s = int(np.abs(H8 @ d @ H8.T).sum())
+    return (s + 2) >> 2 if satd_round else s >> 2
+
+
+def chroma_sample(img, x8, y8):
+    """H.264 8.4.2.2.2 at eighth-pel position (x8, y8) of an infinitely edge-replicated chroma picture."""
+    img = np.asarray(img)
+    hh, ww = img.shape
+    x, y, xf, yf = x8 >> 3, y8 >> 3, x8 & 7, y8 & 7
+    g = lambda xx, yy: int(img[min(max(yy, 0), hh - 1), min(max(xx, 0), ww - 1)])      # noqa: E731
+    return ((8 - xf) * (8 - yf) * g(x, y) + xf * (8 - yf) * g(x + 1, y) + (8 - xf) * yf * g(x, y + 1)
+            + xf * yf * g(x + 1, y + 1) + 32) >> 6
+
+
+def block_metric(a, b, metric, t8=False, satd_round=0):
+    """Distortion of two equally sized blocks: 0 SAD, 1 SSE, 2 Hadamard (4x4 tiles, or 8x8 tiles when t8 and the
+    block is at least 8x8; blocks thinner than 4 fall back to SAD)."""
+    d = np.asarray(a, dtype=np.int64) - np.asarray(b, dtype=np.int64)
+    bh, bw = d.shape
+    if metric == 2 and (bw < 4 or bh < 4):
+        metric = 0
+    if metric == 0:
+        return int(np.abs(d).sum())
+    if metric == 1:
+        return int((d * d).sum())
+    n = 8 if (t8 and bw >= 8 and bh >= 8) else 4
+    f = satd8x8 if n == 8 else satd4x4
+    return sum(f(d[y:y + n, x:x + n], satd_round) for y in range(0, bh, n) for x in range(0, bw, n))
+
+
+class StageSpec:
+    """Per-stage metric and lambda factor of a context, cost-domain arithmetic."""
+
+    def __init__(self, lam, domain=0, metrics=(0, 2, 2), t8=False, satd_round=0, chroma=False):
+        self.domain, self.metrics, self.t8, self.satd_round, self.chroma = domain, metrics, t8, satd_round, chroma
+        scale = 32.0 if domain else 65536.0
+        self.lf = [int(scale * (lam * lam if m == 1 else lam) + 0.5) for m in metrics]
+
+    def rate(self, st, bits):
+        return self.lf[st] * bits if self.domain else (self.lf[st] * bits) >> 16
+
+    def dist(self, d):
+        return d << 5 if self.domain else d
+
+
+def block_search(spec, cur, ref, bx, by, bw, bh, cx, cy, px, py, R, bonus16, pretest, subpel, cur_c=None, ref_c=None):
+    """One block through all stages (integer spiral scan with strict <, then half- and quarter-pel), written
+    directly from the definitions: per-sample interpolation (Interp / chroma_sample), no planes, no surfaces.
+    bonus16: the block is the 16x16 block of reference 0 with !rdopt.  Returns (mvx, mvy, cost) in quarter-pel."""
+    it = Interp(ref)
+    blk = np.asarray(cur)[by:by + bh, bx:bx + bw]
+
+    def luma_pred(qx, qy):
+        return np.array([[it.sample(4 * (bx + x) + qx, 4 * (by + y) + qy) for x in range(bw)] for y in range(bh)])
+
+    def cost_at(st, qx, qy):
+        d = block_metric(blk, luma_pred(qx, qy), spec.metrics[st], spec.t8, spec.satd_round)
+        if spec.chroma and st > 0:
+            for k in range(2):
+                cb = np.asarray(cur_c[k])[by // 2:(by + bh) // 2, bx // 2:(bx + bw) // 2]
+                pr = np.array([[chroma_sample(ref_c[k], 8 * (bx // 2 + x) + qx, 8 * (by // 2 + y) + qy)
+                                for x in range(bw // 2)] for y in range(bh // 2)])
+                d += block_metric(cb, pr, spec.metrics[st], False, spec.satd_round)
+        c = spec.dist(d) + spec.rate(st, se_bits(qx - px) + se_bits(qy - py))
+        if bonus16 and qx == 0 and qy == 0:
+            c -= spec.rate(st, 16)
+        return c
+
+    cands = spiral(R)
+    order = list(range(len(cands)))
+    if pretest:
+        order = [cands.index((-cx, -cy))] + order
+    best = None
+    for pos in order:
+        mx, my = cx + cands[pos][0], cy + cands[pos][1]
+        c = cost_at(0, 4 * mx, 4 * my)
+        if best is None or c < best[2]:
+            best = (4 * mx, 4 * my, c)
+    mvx, mvy, mn = best
+    if not subpel:
+        return mvx, mvy, mn
+    sp = spiral(1)
+    prev = spec.metrics[0]
+    for step, st in ((2, 1), (1, 2)):
+        restart = spec.chroma or spec.metrics[st] != prev
+        if restart:
+            mn = None
+        ox, oy, bp = mvx, mvy, 0
+        for pos in range(0 if restart else 1, 9):
+            qx, qy = ox + step * sp[pos][0], oy + step * sp[pos][1]
+            c = cost_at(st, qx, qy)
+            if mn is None or c < mn:
+                mn, bp = c, pos
+        mvx, mvy = ox + step * sp[bp][0], oy + step * sp[bp][1]
+        prev = spec.metrics[st]
+    return mvx, mvy, mn

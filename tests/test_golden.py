@@ -15,6 +15,10 @@ def replay(lib, g):
     with lib.context(width=w, height=h, search_range=R, num_refs=refs, pred_policy=pol, **kw) as ctx:
         for i in range(refs):
             ctx.set_reference(i, g["refs"][i])
+        if kw.get("chroma_me"):
+            for i in range(refs):
+                ctx.set_reference_chroma(i, g["ref_c"][i, 0], g["ref_c"][i, 1])
+            ctx.set_current_chroma(g["cur_c"][0], g["cur_c"][1])
         res, per = ctx.search_frame(g["cur"], pred, per_ref=True)
         planes = None
         if kw.get("subpel"):
@@ -34,7 +38,7 @@ def check(lib, path):
 
 
 def test_golden_files_exist():
-    assert len(GOLD) >= 7
+    assert len(GOLD) >= 12
 
 
 @pytest.mark.parametrize("path", GOLD, ids=lambda p: p.stem)

@@ -1,0 +1,189 @@
+"""GPU parity of the round-2 features against the oracle, through the C ABI: the JM >= 12 scaled-up cost domain
+(a2), SSE / 8x8-Hadamard distortion with per-stage metrics (f2), chroma ME (f3).  Bit-exact records."""
+import numpy as np
+import pytest
+
+from jmme import abi, synth
+from test_gpu_parity import assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+def chroma_pair(w, h, seed):
+    """Two chroma pictures correlated with a luma-like texture so that chroma changes the decisions."""
+    return [synth.gen_luma((w + 1) // 2, (h + 1) // 2, seed + k, "texture") for k in range(2)]
+
+
+def run(lib, cur, refs, pred=None, per_ref=False, chroma=None, tuning=None, **kw):
+    h, w = cur.shape
+    is_cuda = lib.backend().startswith("cuda")
+    with lib.context(width=w, height=h, num_refs=len(refs), tuning=tuning if is_cuda else None, **kw) as ctx:
+        for i, r in enumerate(refs):
+            ctx.set_reference(i, r)
+        if chroma is not None:
+            cur_c, ref_c = chroma
+            for i in range(len(refs)):
+                ctx.set_reference_chroma(i, *ref_c[i])
+            ctx.set_current_chroma(*cur_c)
+        out = ctx.search_frame(cur, pred, per_ref)
+        return out, (ctx.last_kernel() if is_cuda else None)
+
+
+def test_new_leaves(cuda, oracle):
+    rng = np.random.default_rng(11)
+    d = rng.integers(-255, 256, size=(2048, 64)).astype(np.int16)
+    d[0] = 255
+    d[1] = np.tile([255, -255], 32)
+    for rnd in (0, 1):
+        assert np.array_equal(cuda.hadamard_sad8x8(d, rnd), oracle.hadamard_sad8x8(d, rnd))
+    for (w, h, pad, kind) in ((24, 16, 5, "noise"), (40, 22, 9, "texture"), (8, 8, 3, "checker")):
+        img = synth.gen_luma(w, h, 3, kind)
+        assert np.array_equal(cuda.get_sub_images_chroma(img, pad), oracle.get_sub_images_chroma(img, pad))
+
+
+SSE3 = dict(me_distortion=1, me_distortion_fpel=1, me_distortion_hpel=1, me_distortion_qpel=1)
+CASES = [
+    # cost domain 1 (a2): integer only, with sub-pel (SATD / SAD), rdopt and not, per-block predictors come below
+    dict(cost_domain=1),
+    dict(cost_domain=1, rdopt=1, qp=33),
+    dict(cost_domain=1, subpel=1, qp=24),
+    dict(cost_domain=1, subpel=1, use_hadamard=0, rdopt=1, qp=30),
+    dict(cost_domain=1, subpel=1, blocktype_mask=abi.MASK_16x16),
+    dict(cost_domain=1, subpel=1, blocktype_mask=0x92, satd_round=1),
+    dict(cost_domain=1, search_mode=abi.SEARCH_FULL, qp=36),
+    # SSE (f2)
+    dict(subpel=1, qp=26, **SSE3),
+    dict(subpel=0, rdopt=1, qp=35, **SSE3),
+    dict(subpel=1, cost_domain=1, qp=22, **SSE3),
+    dict(subpel=1, blocktype_mask=abi.MASK_16x16, **SSE3),
+    dict(subpel=1, search_mode=abi.SEARCH_FULL, **SSE3),
+    # mixed metrics: every stage restarts
+    dict(me_distortion=1, me_distortion_fpel=1, me_distortion_hpel=0, me_distortion_qpel=2, subpel=1, qp=29),
+    dict(me_distortion=1, me_distortion_fpel=0, me_distortion_hpel=1, me_distortion_qpel=0, subpel=1, rdopt=1, qp=27),
+    dict(me_distortion=1, me_distortion_fpel=0, me_distortion_hpel=2, me_distortion_qpel=1, subpel=1, cost_domain=1),
+    # 8x8 Hadamard (f2)
+    dict(subpel=1, transform8x8=1),
+    dict(subpel=1, transform8x8=1, satd_round=1, rdopt=1, qp=31),
+    dict(subpel=1, transform8x8=1, cost_domain=1, satd_round=1),
+    dict(subpel=1, transform8x8=1, blocktype_mask=0x1E),                 # only the blocktypes that use it
+    dict(subpel=1, transform8x8=1, use_hadamard=0),                      # no Hadamard stage: the flag is inert
+]
+
+
+@pytest.mark.parametrize("kw", CASES)
+@pytest.mark.parametrize("policy", [abi.PRED_ZERO, abi.PRED_PER_BLOCK])
+def test_cost_domain_sse_hadamard8_match_oracle(cuda, oracle, kw, policy):
+    for (w, h, R, kind, seed) in ((64, 48, 5, "texture", 1), (52, 38, 9, "noise", 2)):
+        cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R, kind=kind, num_refs=2)
+        n_mb = ((w + 15) // 16) * ((h + 15) // 16)
+        pred = None if policy == abi.PRED_ZERO else synth.random_pred(2, n_mb, 41, seed, 4 * R + 20)
+        k2 = dict(kw, search_range=R, pred_policy=policy)
+        k2.setdefault("qp", 28)
+        (g, gp), kern = run(cuda, cur, refs, pred, True, **k2)
+        (o, op), _ = run(oracle, cur, refs, pred, True, **k2)
+        assert_same(gp, op, f"per-ref {kw} {kind} ({kern})")
+        assert_same(g, o, f"best {kw} {kind} ({kern})")
+        wide = kw.get("cost_domain") or kw.get("me_distortion_fpel") == 1
+        if wide and kw.get("search_mode", 0) == abi.SEARCH_FASTFULL:
+            assert kern.startswith("me_int_kernel<") and ("MODE=2" if kw.get("me_distortion_fpel") == 1 else "MODE=1") in kern, kern
+
+
+def test_extreme_costs_in_the_wide_kernels(cuda, oracle):
+    """0/255 opposition with the largest lambda: the largest SSE (16.6 M for 16x16, 2^29 in domain 1) and the
+    all-ties frames, where only the 64-bit (cost, key) order decides."""
+    cur = np.zeros((32, 32), np.uint8)
+    ref = np.full((32, 32), 255, np.uint8)
+    pred = synth.random_pred(1, 4, 41, seed=1, max_qpel=2048)
+    for kw in (dict(cost_domain=1), dict(**SSE3), dict(cost_domain=1, **SSE3)):
+        for rdopt in (0, 1):
+            k2 = dict(kw, search_range=4, qp=51, rdopt=rdopt, pred_policy=abi.PRED_PER_BLOCK, subpel=1)
+            assert_same(run(cuda, cur, [ref], pred, **k2)[0], run(oracle, cur, [ref], pred, **k2)[0], str(k2))
+    for kind in ("const", "checker"):
+        img = synth.gen_luma(48, 48, 0, kind)
+        for kw in (dict(cost_domain=1), dict(**SSE3), dict(cost_domain=1, transform8x8=1)):
+            for rdopt in (0, 1):
+                for lf in (0, 1):
+                    k2 = dict(kw, search_range=6, rdopt=rdopt, lambda_factor=lf, subpel=1)
+                    assert_same(run(cuda, img, [img], **k2)[0], run(oracle, img, [img], **k2)[0], f"{kind} {k2}")
+
+
+CHROMA_CASES = [
+    dict(subpel=1, chroma_me=1, qp=27),
+    dict(subpel=1, chroma_me=1, use_hadamard=0, rdopt=1, qp=33),
+    dict(subpel=1, chroma_me=1, cost_domain=1, satd_round=1),
+    dict(subpel=1, chroma_me=1, transform8x8=1, qp=30),
+    dict(subpel=1, chroma_me=1, **SSE3),
+    dict(subpel=1, chroma_me=1, me_distortion=1, me_distortion_fpel=0, me_distortion_hpel=1, me_distortion_qpel=2, cost_domain=1),
+    dict(subpel=1, chroma_me=1, blocktype_mask=0x92),
+    dict(subpel=1, chroma_me=1, search_mode=abi.SEARCH_FULL),
+]
+
+
+@pytest.mark.parametrize("kw", CHROMA_CASES)
+def test_chroma_me_matches_oracle(cuda, oracle, kw):
+    for (w, h, R, nref, policy) in ((64, 48, 6, 2, abi.PRED_ZERO), (52, 38, 9, 1, abi.PRED_PER_BLOCK), (96, 32, 32, 1, abi.PRED_PER_MB)):
+        cur, refs = synth.frame_pair(w, h, seed=3, search_range=R, num_refs=nref)
+        chroma = (chroma_pair(w, h, 50), [chroma_pair(w, h, 60 + 7 * i) for i in range(nref)])
+        n_mb = ((w + 15) // 16) * ((h + 15) // 16)
+        nb = {abi.PRED_ZERO: 0, abi.PRED_PER_MB: 1, abi.PRED_PER_BLOCK: 41}[policy]
+        pred = synth.random_pred(nref, n_mb, nb, 5, 4 * R + 20) if nb else None
+        k2 = dict(kw, search_range=R, pred_policy=policy)
+        (g, gp), kern = run(cuda, cur, refs, pred, True, chroma=chroma, **k2)
+        (o, op), _ = run(oracle, cur, refs, pred, True, chroma=chroma, **k2)
+        assert_same(gp, op, f"per-ref {kw} {w}x{h}")
+        assert_same(g, o, f"best {kw} {w}x{h}")
+        # chroma really takes part: without it some decision differs
+        (g0, _), _ = run(cuda, cur, refs, pred, True, **{k: v for k, v in k2.items() if k != "chroma_me"})
+        assert g0.tobytes() != g.tobytes()
+
+
+def test_in_frame_median_with_the_new_cost_functions(cuda, oracle):
+    """The wavefront (JMME_PRED_MEDIAN) with cost domain 1 / SSE / 8x8 Hadamard / chroma: the wide integer kernels
+    take their predictors from the wave-step kernel, the general sub-pel kernel commits."""
+    w, h, R = 96, 64, 6
+    cur, refs = synth.frame_pair(w, h, seed=4, search_range=R, num_refs=2)
+    chroma = (chroma_pair(w, h, 70), [chroma_pair(w, h, 80 + i) for i in range(2)])
+    for kw, ch in ((dict(cost_domain=1, subpel=1), None), (dict(subpel=1, **SSE3), None), (dict(subpel=1, transform8x8=1, slice_rows=2), None),
+                   (dict(subpel=1, chroma_me=1, slice_rows=1), chroma), (dict(cost_domain=1, subpel=0), None)):
+        k2 = dict(kw, search_range=R, pred_policy=abi.PRED_MEDIAN, qp=30)
+        (g, gp), kern = run(cuda, cur, refs, None, True, chroma=ch, **k2)
+        (o, op), _ = run(oracle, cur, refs, None, True, chroma=ch, **k2)
+        assert_same(gp, op, f"per-ref {kw} ({kern})")
+        assert_same(g, o, f"best {kw} ({kern})")
+
+
+def test_errors_of_the_new_parameters_mirror_the_oracle(cuda, oracle):
+    for lib in (cuda, oracle):
+        for kw, code in ((dict(cost_domain=2), abi.ERR_PARAM), (dict(me_distortion=1, me_distortion_hpel=3), abi.ERR_PARAM),
+                         (dict(me_distortion=1, me_distortion_fpel=2), abi.ERR_UNSUPPORTED), (dict(chroma_me=1), abi.ERR_PARAM),
+                         (dict(transform8x8=2), abi.ERR_PARAM)):
+            with pytest.raises(abi.JmmeError) as e:
+                lib.context(width=32, height=32, **kw)
+            assert e.value.code == code, kw
+        with lib.context(width=32, height=32, search_range=2, subpel=1, chroma_me=1) as ctx:
+            ctx.set_reference(0, np.zeros((32, 32), np.uint8))
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.search_frame(np.zeros((32, 32), np.uint8))
+            assert e.value.code == abi.ERR_STATE
+        with lib.context(width=32, height=32, search_range=2) as ctx:
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.set_current_chroma(np.zeros((16, 16), np.uint8), np.zeros((16, 16), np.uint8))
+            assert e.value.code == abi.ERR_STATE
+
+
+def test_chroma_device_api(cuda, oracle):
+    import torch
+    from jmme.torch_api import DeviceSearch
+    w, h, R = 64, 48, 6
+    cur, refs = synth.frame_pair(w, h, seed=3, search_range=R)
+    cur_c, ref_c = chroma_pair(w, h, 50), chroma_pair(w, h, 60)
+    kw = dict(search_range=R, subpel=1, chroma_me=1, qp=29)
+    ds = DeviceSearch(cuda, width=w, height=h, **kw)
+    ds.set_reference(0, torch.from_numpy(refs[0]).cuda())
+    ds.set_reference_chroma(0, *[torch.from_numpy(x).cuda() for x in ref_c])
+    ds.set_current_chroma(*[torch.from_numpy(x).cuda() for x in cur_c])
+    got = ds.to_numpy(ds.search(torch.from_numpy(cur).cuda()))
+    torch.cuda.synchronize()
+    (o, _), _ = run(oracle, cur, refs, None, True, chroma=(cur_c, [ref_c]), **kw)
+    assert_same(got, o, "device chroma API")
+    ds.close()

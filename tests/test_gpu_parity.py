@@ -244,7 +244,7 @@ def test_errors_mirror_the_oracle(cuda, oracle):
                 lib.context(**kw)
             assert e.value.code == abi.ERR_PARAM
         with pytest.raises(abi.JmmeError) as e:
-            lib.context(width=16, height=16, cost_domain=1)
+            lib.context(width=16, height=16, me_distortion=1, me_distortion_fpel=abi.DIST_HADAMARD)
         assert e.value.code == abi.ERR_UNSUPPORTED
         with lib.context(width=32, height=32, search_range=4) as ctx:
             with pytest.raises(abi.JmmeError) as e:

@@ -68,7 +68,10 @@ def test_create_rejects_bad_params(oracle):
             oracle.context(**kw)
         assert e.value.code == abi.ERR_PARAM
     with pytest.raises(abi.JmmeError) as e:
-        oracle.context(width=16, height=16, cost_domain=1)
+        oracle.context(width=16, height=16, cost_domain=2)
+    assert e.value.code == abi.ERR_PARAM
+    with pytest.raises(abi.JmmeError) as e:                       # a Hadamard integer stage is the one refused metric
+        oracle.context(width=16, height=16, me_distortion=1, me_distortion_fpel=abi.DIST_HADAMARD)
     assert e.value.code == abi.ERR_UNSUPPORTED
 
 

@@ -1,14 +1,11 @@
 #!/bin/bash
-# bench + ncu launch list + ncu full capture of the three hot kernels
-set -x
+# ncu launch list + ncu full capture (with source) of the hot kernels of the bench step; run after gpu_round.sh
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 3000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err
-python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 &&
+python bench.py --steps 2 --warmup 3 --no-cpu --no-parity > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain2.log 2>&1 &&
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-parity > gpurun_out/ncu_launches.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu --no-parity > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'me_int|me_subpel|interp_kernel' -s 6 -c 3 \
-    -o gpurun_out/prof_r01 -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
-tail -5 gpurun_out/ncu_full.log
-ls -la gpurun_out
+    -o gpurun_out/prof_r02 -f python bench.py --steps 2 --warmup 3 --no-cpu --no-parity > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out | head -30

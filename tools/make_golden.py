@@ -26,6 +26,15 @@ CASES = {
     # in-frame median (JMME_PRED_MEDIAN): slices of two MB rows with two references; one slice = the frame
     "median_slices2_2refs_qpel": (80, 96, 8, 2, dict(qp=30, subpel=1, slice_rows=2), 3),
     "median_wholeframe_rdopt_r6": (96, 64, 6, 1, dict(qp=34, rdopt=1, subpel=1, slice_rows=0), 3),
+    # round 2: JM >= 12 scaled-up cost domain, SSE / mixed per-stage metrics, 8x8 Hadamard, chroma ME
+    "costdomain1_r8_2refs_qpel_perblock": (64, 48, 8, 2, dict(qp=29, subpel=1, cost_domain=1), 2),
+    "sse_all_stages_r6": (64, 48, 6, 1, dict(qp=26, subpel=1, me_distortion=1, me_distortion_fpel=1, me_distortion_hpel=1,
+                                             me_distortion_qpel=1), 0),
+    "mixed_metrics_hadamard8_r6_domain1": (64, 64, 6, 1, dict(qp=31, rdopt=1, subpel=1, me_distortion=1, me_distortion_fpel=1,
+                                                              me_distortion_hpel=0, me_distortion_qpel=2, transform8x8=1,
+                                                              satd_round=1, cost_domain=1), 1),
+    "chroma_me_r6_2refs": (64, 48, 6, 2, dict(qp=28, subpel=1, chroma_me=1), 0),
+    "chroma_me_hadamard8_median": (80, 64, 5, 1, dict(qp=30, subpel=1, chroma_me=1, transform8x8=1, slice_rows=2), 3),
 }
 
 
@@ -44,6 +53,14 @@ def main():
                 pred = synth.random_pred(refs, n_mb, 1 if pol == 1 else 41, seed=5, max_qpel=4 * R + 20)
             for i, r in enumerate(ref_l):
                 ctx.set_reference(i, r)
+            cur_c = ref_c = np.zeros(0, np.uint8)
+            if kw.get("chroma_me"):
+                cur_c = np.stack([synth.gen_luma(w // 2, h // 2, 40 + k, "texture") for k in range(2)])
+                ref_c = np.stack([np.stack([synth.gen_luma(w // 2, h // 2, 50 + 3 * i + k, "texture") for k in range(2)])
+                                  for i in range(refs)])
+                for i in range(refs):
+                    ctx.set_reference_chroma(i, ref_c[i, 0], ref_c[i, 1])
+                ctx.set_current_chroma(cur_c[0], cur_c[1])
             res, per = ctx.search_frame(cur, pred, per_ref=True)
             planes = None
             if kw.get("subpel"):
@@ -53,7 +70,7 @@ def main():
         np.savez_compressed(out / f"{name}.npz", cur=cur, refs=np.stack(ref_l), pred=pred if pred is not None else np.zeros(0, np.int16),
                             params=np.array([w, h, R, refs, pol], np.int32), kw_keys=np.array(list(kw.keys())),
                             kw_vals=np.array(list(kw.values()), np.int32), mv=res["mv"], cost=res["cost"], ref_idx=res["ref_idx"],
-                            per_mv=per["mv"], per_cost=per["cost"],
+                            per_mv=per["mv"], per_cost=per["cost"], cur_c=cur_c, ref_c=ref_c,
                             planes_crop=planes if planes is not None else np.zeros(0, np.uint8))
         print(name, (out / f"{name}.npz").stat().st_size, "bytes")
 

@@ -19,9 +19,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("-d", "--cfg", required=True, help="JM encoder.cfg")
 ap.add_argument("-p", action="append", default=[], help="Key=value override, as in lencod")
 ap.add_argument("--median", action="store_true", help="in-frame median predictors instead of zero predictors")
+ap.add_argument("--cost-domain", type=int, default=0, help="1: JM >= 12 scaled-up costs (JCOST_CALC_SCALEUP)")
 a = ap.parse_args()
 cfg = EncoderCfg.load(a.cfg, a.p)
-kw = cfg.params()
+kw = cfg.params(cost_domain=a.cost_domain)
 src = pathlib.Path(cfg.input_file or "")
 if not src.is_absolute():
     src = pathlib.Path(a.cfg).resolve().parent / src
@@ -31,7 +32,7 @@ if not a.median:
     kw.pop("slice_rows", None)
 w, h = kw.pop("width"), kw.pop("height")
 tot_mb, tot_s = 0, 0.0
-for n, rec, sec in search_sequence(lib, yuv_frames(src, w, h, cfg.frames), policy, **kw):
+for n, rec, sec in search_sequence(lib, yuv_frames(src, w, h, cfg.frames, chroma=bool(kw.get("chroma_me"))), policy, **kw):
     c16 = rec["cost"][:, 0].astype(np.int64)
     print(f"frame {n}: {len(rec)} MBs in {1e3 * sec:.2f} ms, mean 16x16 cost {c16.mean():.1f}, "
           f"zero-MV 16x16 blocks {100.0 * np.mean(np.all(rec['mv'][:, 0] == 0, axis=1)):.1f} %")
