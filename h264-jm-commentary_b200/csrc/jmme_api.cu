@@ -342,6 +342,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
         for (int k = 0; k < 2; k++) P.cplanes[r][k] = c->d_cplanes[r][k];
     P.cstride = c->cstride; P.cpad = c->cpad; P.cur_c[0] = c->d_cur_c[0]; P.cur_c[1] = c->d_cur_c[1]; P.cur_cs = c->w16 / 2;
     P.tune_group = c->tune.group; P.tune_cluster = c->tune.cluster; P.tune_lin = !c->tune.table_rate;
+    P.tune_split = !c->tune.no_split; P.tune_split_pdl = !c->tune.no_split_pdl;
 }
 
 // enqueue the whole search on `st`; nothing is synchronised here

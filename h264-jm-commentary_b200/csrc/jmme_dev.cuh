@@ -51,7 +51,14 @@ struct SearchParams {
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
     int tune_group, tune_cluster;        // host-side launch knobs (jmme_tuning.group / .cluster, defaults resolved)
     int tune_lin;                        // 0 (jmme_tuning.table_rate): per-block rate always from the table
+    int tune_split, tune_split_pdl;      // zero-predictor search as full rounds + a clustered tail (jmme_tuning.no_split = 0)
     int pdl;                             // wavefront steps: launch with programmatic stream serialization
+    // split launch of the zero-predictor search (me_int_tb.cu): full rounds of MB-pair items, then the remaining
+    // MBs one per cluster
+    int item_count;                      // > 0: only the first item_count items of the stripe
+    int range_first, range_count;        // range_count > 0: the items are the single MBs range_first .. (frame MB index)
+    int split_role;                      // 1: this launch has a programmatic dependent (trigger at once)
+                                         // 2: this launch is that dependent (wait for the primary before exiting)
     jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
     int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
     // ---- ABI 4: cost domain, per-stage metrics, 8x8 Hadamard, chroma ME ----
@@ -124,7 +131,7 @@ cudaError_t jmme_kernel_occupancy(Kern kern, KernelState &ks, int threads, size_
 }
 // name of the integer-search kernel instantiation a launch function picked (jmme_last_kernel); per host thread
 char *jmme_kernel_name_buf();
-#define JMME_KNAME_LEN 192
+#define JMME_KNAME_LEN 320
 
 // Programmatic dependent launch (sm_90+).  pdl_trigger: the next kernel of the stream may start its prologue;
 // pdl_wait: results of the previous kernel are complete and visible from here on.  Both are no-ops for a

@@ -16,6 +16,7 @@
 //   K            up to 8 candidates per run: 4*(7+K)/K row words per thread and candidate
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include <cooperative_groups.h>
 
@@ -114,7 +115,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
     const int ppr = (P.mb_w + NM - 1) / NM;              // items per MB row
-    const int n_it_stripe = P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ppr;   // a list: one MB per item
+    // a list or a range: one MB per item; item_count: the first items of the stripe only (split launch)
+    const int n_it_stripe = P.mb_list ? P.n_list
+                                      : (P.range_count ? P.range_count
+                                                       : (P.item_count ? P.item_count : (P.mb_row_end - P.mb_row_begin) * ppr));
     const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
@@ -167,8 +171,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     auto decode_item = [&](int item, Item &it) {           // called by all threads of the CTA together
         it.ref = item / n_it_stripe;
         const int idx = item - it.ref * n_it_stripe;
-        if (P.mb_list) {
-            it.mb = P.mb_list[idx];
+        if (P.mb_list || P.range_count) {
+            it.mb = P.mb_list ? P.mb_list[idx] : P.range_first + idx;
             it.mby = it.mb / P.mb_w;
             it.mbx = it.mb - it.mby * P.mb_w;
             it.nmb = 1;
@@ -295,7 +299,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     Item cur_it, nxt_it;
     int item = blockIdx.x / CL, buf = 0;
     const int item_stride = gridDim.x / CL;
-    if (item >= n_items) return;                         // (the same for every CTA of a cluster)
+    // split launch: the two launches work on different MBs, so the second one may fill the SMs as the CTAs of the
+    // first retire; it only must not COMPLETE before the first (the next kernel of the stream reads both results)
+    if (P.split_role == 1) pdl_trigger();
+    if (item >= n_items) {                               // (the same for every CTA of a cluster)
+        if (P.split_role == 2) pdl_wait();
+        return;
+    }
     decode_item(item, cur_it);
     prefetch(cur_it, 0);
     cp_async_wait_all();
@@ -528,6 +538,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         cur_it = nxt_it;
         buf ^= 1;
     }
+    if (P.split_role == 2) pdl_wait();
 }
 
 template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1, int CL = 1,
@@ -544,8 +555,12 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
     snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN,
              "me_int_tb_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,RS_CT=%d,KEYG=%d,KRTAB=%d,NMB=%d,CL=%d,WP=%d,LIN=%d>", K, NW, MINB,
              (int)PER_BLOCK, RS_CT, (int)KEYG, (int)KRTAB, NMB, CL, (int)WP, (int)LIN);
-    int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
-    if (CL > 1 || P.pdl) {
+    int n_items = (P.mb_list ? P.n_list
+                             : (P.range_count ? P.range_count
+                                              : (P.item_count ? P.item_count : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)))) *
+                  P.num_refs;
+    if (n_items <= 0) return cudaSuccess;
+    if (CL > 1 || P.pdl || P.split_role == 2) {
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[2];
         int na = 0;
@@ -554,7 +569,7 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
             at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
             na++;
         }
-        if (P.pdl) {
+        if (P.pdl || P.split_role == 2) {
             at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[na].val.programmaticStreamSerializationAllowed = 1;
             na++;
@@ -567,6 +582,62 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
+}
+
+// resident CTAs of an instantiation on this device (the persistent grid of launch_tb)
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB>
+cudaError_t tb_capacity(const SearchParams &P, int num_sms, int *cap)
+{
+    TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
+    static KernelState ks;
+    int occ = 0;
+    cudaError_t e = jmme_kernel_occupancy(me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, 1, false, false>, ks,
+                                          NW * 32, (size_t)L.total_words * 4, &occ);
+    *cap = num_sms * occ;
+    return e;
+}
+
+// Zero predictors, R = 32, one reference: the stripe as full rounds of items of NMBM (2 or 4) adjacent MBs on the
+// persistent grid, and the MBs that are left over (less than one round of items) one per thread-block cluster of 2 or
+// 4 CTAs, so that the last, partial round costs a fraction of an item instead of a whole one (1080p in pairs: 9.19
+// rounds cost 9.3 instead of 10; a stripe of 9 MB rows on one of 8 GPUs: 1.22 rounds cost 1.3 instead of 2).  The two
+// launches work on different MBs: the second is a programmatic dependent of the first, so its CTAs fill the SMs as
+// the first's retire (P.tune_split_pdl).
+template <int K, int NW, int MINB, int NMBM, int RSM>
+cudaError_t launch_split(const SearchParams &P0, int num_sms, cudaStream_t st)
+{
+    int cap = 0;
+    cudaError_t e = tb_capacity<K, NW, MINB, false, RSM, false, true, NMBM>(P0, num_sms, &cap);
+    if (e != cudaSuccess) return e;
+    const int rows = P0.mb_row_end - P0.mb_row_begin, ppr = (P0.mb_w + NMBM - 1) / NMBM, total = rows * ppr;
+    const int full = cap > 0 ? (total / cap) * cap : 0;          // items in full rounds
+    if (full == total) return launch_tb<K, NW, MINB, false, RSM, false, true, NMBM>(P0, num_sms, st);
+    SearchParams P = P0;
+    // first MB after the full-round items, and how many are left
+    const int first = (P0.mb_row_begin + full / ppr) * P0.mb_w + (full % ppr) * NMBM;
+    const int left = P0.mb_row_end * P0.mb_w - first;
+    const bool pdl = P0.tune_split_pdl && full > 0;
+    char main_name[JMME_KNAME_LEN] = "";
+    if (full > 0) {
+        P.item_count = full; P.split_role = pdl ? 1 : 0;
+        e = launch_tb<K, NW, MINB, false, RSM, false, true, NMBM>(P, num_sms, st);
+        if (e != cudaSuccess) return e;
+        snprintf(main_name, sizeof main_name, "%s", jmme_kernel_name_buf());
+    }
+    P.item_count = 0; P.range_first = first; P.range_count = left; P.split_role = pdl ? 2 : 0;
+    int cap1 = 0;                                                // resident CTAs of the one-MB kernel
+    e = tb_capacity<K, NW, MINB, false, 78, false, true, 1>(P0, num_sms, &cap1);
+    if (e != cudaSuccess) return e;
+    if (4 * left <= cap1) e = launch_tb<K, NW, MINB, false, 78, false, true, 1, 4>(P, num_sms, st);
+    else if (2 * left <= cap1) e = launch_tb<K, NW, MINB, false, 78, false, true, 1, 2>(P, num_sms, st);
+    else e = launch_tb<K, NW, MINB, false, 78, false, true, 1, 1>(P, num_sms, st);
+    if (full > 0) {                                              // jmme_last_kernel names both launches
+        char both[JMME_KNAME_LEN];
+        const char *lt = strchr(jmme_kernel_name_buf(), '<');
+        snprintf(both, sizeof both, "%.150s + tail %.150s", main_name, lt ? lt : "");
+        snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN, "%s", both);
+    }
+    return e;
 }
 
 }  // namespace
@@ -606,6 +677,10 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
         if (P.R == 32 && !P.pred && !KG) {                                                                     \
             const int grp = P.tune_group;                           /* MBs per item, default 2 */             \
             if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4>(P, num_sms, st);            \
+            if (grp >= 4 && P.num_refs == 1 && !P.mb_list && P.tune_split)                                      \
+                return launch_split<KK, NWW, MB, 4, 126>(P, num_sms, st);                                       \
+            if (grp >= 2 && P.num_refs == 1 && !P.mb_list && P.tune_split)                                      \
+                return launch_split<KK, NWW, MB, 2, 94>(P, num_sms, st);                                        \
             if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2>(P, num_sms, st);             \
             return launch_tb<KK, NWW, MB, false, 78, false, true, 1>(P, num_sms, st);                           \
         }                                                                                                       \

@@ -34,12 +34,15 @@ def oracle_threads(oracle, n):
     return oracle.dll.jmme_oracle_set_threads(n)
 
 
+# regular expressions of the integer-search instantiation each BASELINE config launches by default (whole frame)
 DEFAULT_KERNELS = {
-    "config1": "me_int_kernel<K=3,NW=4,MINB=3,PER_BLOCK=0,ONLY16=1,RS_CT=0>",
-    "config2": "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0>",
-    "config3": "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0>",
-    "config4": "me_int_kernel<K=5,NW=8,MINB=1,PER_BLOCK=0,ONLY16=0,RS_CT=144>",
+    "config1": r"me_int_kernel<K=3,NW=4,MINB=3,PER_BLOCK=0,ONLY16=1,RS_CT=0,MODE=0>$",
+    # zero predictors, R = 32: full rounds of MB-group items + the left-over MBs one per cluster (launch_split)
+    "config2": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=\d+,KEYG=0,KRTAB=1,NMB=[24],CL=1,WP=0,LIN=0> \+ tail "
+               r"<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=78,KEYG=0,KRTAB=1,NMB=1,CL=[124],WP=0,LIN=0>$",
+    "config4": r"me_int_kernel<K=5,NW=8,MINB=1,PER_BLOCK=0,ONLY16=0,RS_CT=144,MODE=0>$",
 }
+DEFAULT_KERNELS["config3"] = DEFAULT_KERNELS["config2"]
 
 
 def assert_default_kernel(prefix):
@@ -348,17 +351,40 @@ def test_config4_and_config5_r64_four_refs(cuda, oracle, w, h, subpel):
 def test_default_kernels_of_the_baseline_configs(cuda):
     """Which integer-search instantiation each BASELINE config launches by default (jmme_last_kernel) — the
     names bench.py prints in its JSON line (`roofline.kernel_instance`).  Updated whenever a default changes."""
+    import re
     expect = {
         (352, 288, 16, 1, abi.MASK_16x16, abi.SEARCH_FULL): DEFAULT_KERNELS["config1"],
         (1280, 720, 32, 1, abi.MASK_ALL, abi.SEARCH_FASTFULL): DEFAULT_KERNELS["config2"],
         (1920, 1080, 32, 1, abi.MASK_ALL, abi.SEARCH_FASTFULL): DEFAULT_KERNELS["config3"],
         (1920, 1080, 64, 4, abi.MASK_ALL, abi.SEARCH_FASTFULL): DEFAULT_KERNELS["config4"],
     }
-    for (w, h, R, nref, mask, mode), name in expect.items():
+    for (w, h, R, nref, mask, mode), pat in expect.items():
         cur, refs = synth.frame_pair(w, h, seed=1, search_range=R, num_refs=nref)
-        # a two-row stripe is enough to see which kernel is picked
-        run(cuda, cur, refs, search_range=R, blocktype_mask=mask, search_mode=mode, mb_row_begin=2, mb_row_end=4)
-        assert LAST["kernel"] == name, (w, h, R, LAST)
+        run(cuda, cur, refs, search_range=R, blocktype_mask=mask, search_mode=mode)
+        assert re.match(pat, LAST["kernel"]), (w, h, R, LAST)
+
+
+@pytest.mark.parametrize("tuning", [dict(no_split=1), dict(no_split_pdl=1), dict(group=4), dict(group=4, no_split_pdl=1),
+                                    dict(group=1)])
+@pytest.mark.parametrize("w,h,rows", [(1920, 1080, None), (1920, 1080, (0, 9)), (1920, 1080, (59, 68)), (1280, 720, None),
+                                      (336, 64, None), (80, 48, None)])
+def test_split_launch_shapes_reproduce_the_single_launch(cuda, oracle, tuning, w, h, rows):
+    """The zero-predictor search as full rounds of MB-group items plus a clustered tail (launch_split), with and
+    without the programmatic dependent launch, in groups of 2 and 4, on whole frames, on the stripes an 8-GPU run
+    gives a rank, and on frames smaller than one round: every shape gives the field of the plain single launch
+    (and small frames are checked against the oracle)."""
+    R = 32
+    cur, refs = synth.frame_pair(w, h, seed=6, search_range=R)
+    kw = dict(search_range=R, qp=28, subpel=1)
+    if rows:
+        kw.update(mb_row_begin=rows[0], mb_row_end=rows[1])
+    ref = run(cuda, cur, refs, tuning=dict(no_split=1, group=2), **kw)
+    got = run(cuda, cur, refs, tuning=tuning, **kw)
+    assert got.tobytes() == ref.tobytes(), (tuning, LAST)
+    got2 = run(cuda, cur, refs, **kw)                              # the default
+    assert got2.tobytes() == ref.tobytes(), LAST
+    if w * h <= 336 * 64:
+        assert_same(got, run(oracle, cur, refs, **kw), f"{w}x{h} {tuning}")
 
 
 def test_launch_counter_counts_kernels(cuda):

@@ -23,6 +23,7 @@ ap.add_argument("--pred", type=int, default=0)
 ap.add_argument("--Ks", default="0,68,48,88,32,51")
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--group", type=int, default=0, help="jmme_tuning.group")
+ap.add_argument("--tuning", default="", help="more jmme_tuning fields: key=val,key=val")
 ap.add_argument("--rows", type=int, default=0, help="search only the first N MB rows (stripe)")
 a = ap.parse_args()
 
@@ -34,7 +35,7 @@ for K in [int(k) for k in a.Ks.split(",")]:
     for subpel in sorted({0, a.subpel}):
         s = DeviceSearch(lib, width=a.w, height=a.h, search_range=a.R, num_refs=a.refs, subpel=subpel,
                          blocktype_mask=a.mask, pred_policy=a.pred, qp=28, mb_row_end=a.rows,
-                         tuning=dict(variant=K, group=a.group))
+                         tuning=dict(variant=K, group=a.group, **{k: int(v) for k, v in (kv.split('=') for kv in a.tuning.split(',') if kv)}))
         pred = None
         if a.pred:
             nb = 1 if a.pred == 1 else 41
