@@ -41,6 +41,16 @@ cudaError_t jmme_launch_wave_step(const int *cur, int n_cur, int mb_w, int mb_h,
                                   const int16_t *mv4, const int8_t *ref4, int16_t *pred, cudaStream_t st);
 cudaError_t jmme_launch_pad_plane(const uint8_t *src, int w, int h, int stride, int pad, int pw, int ph, uint8_t *dst,
                                   cudaStream_t st);
+struct BipredArgs {                      // me_bipred.cu
+    const uint8_t *planes_l1;
+    const jmme_mbresult *l0, *l1;
+    const int16_t *pred0, *pred1;
+    const int16_t *spiral_xy;
+    int range, iterations, npb, n_planes;
+    jmme_bipred *out;
+    int *err;
+};
+cudaError_t jmme_launch_bipred(const SearchParams &P, const BipredArgs &A, cudaStream_t st);
 cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_dst, size_t n_words, cudaStream_t st);
 
 struct jmme_ctx {
@@ -53,6 +63,13 @@ struct jmme_ctx {
     bool cref_set[JMME_MAX_REFS], cur_c_set;
     uint8_t *d_cur_c[2];                  // current chroma, w16/2 x h16/2
     uint8_t *d_craw;                      // staging for host chroma uploads (two components)
+    // bi-predictive refinement (allocated by the first jmme_set_reference_l1)
+    uint8_t *d_planes_l1, *d_raw_l1;
+    bool l1_set;
+    jmme_mbresult *d_bi_l0, *d_bi_l1;
+    int16_t *d_bi_pred0, *d_bi_pred1, *d_bi_spiral;
+    jmme_bipred *d_bi_out;
+    int *d_bi_err;
     jmme_tuning tune;                     // launch knobs with the defaults resolved (jmme_set_tuning)
     char last_kernel[JMME_KNAME_LEN];     // integer-search kernel instantiation of the last search
     cudaStream_t stream;
@@ -152,6 +169,8 @@ void free_device(jmme_ctx *c)
         cudaFree(c->d_planes[r]); cudaFree(c->d_raw_ref[r]); cudaFree(c->d_cplanes[r][0]); cudaFree(c->d_cplanes[r][1]);
     }
     cudaFree(c->d_cur_c[0]); cudaFree(c->d_cur_c[1]); cudaFree(c->d_craw);
+    cudaFree(c->d_planes_l1); cudaFree(c->d_raw_l1); cudaFree(c->d_bi_l0); cudaFree(c->d_bi_l1); cudaFree(c->d_bi_pred0);
+    cudaFree(c->d_bi_pred1); cudaFree(c->d_bi_spiral); cudaFree(c->d_bi_out); cudaFree(c->d_bi_err);
     cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave); cudaFree(c->d_wave_tab);
@@ -670,6 +689,132 @@ int jmme_set_current_chroma(jmme_ctx *c, const uint8_t *cb, const uint8_t *cr, i
 {
     if (!c || !cb || !cr || stride < (c->p.width + 1) / 2) return JMME_ERR_PARAM;
     return chroma_from_host(c, -1, cb, cr, stride);
+}
+
+// ---- (f2) bi-predictive refinement ----------------------------------------------------------------------------
+int jmme_set_reference_l1(jmme_ctx *c, const uint8_t *luma, int stride)
+{
+    if (!c || !luma || stride < c->p.width) return JMME_ERR_PARAM;
+    if (c->n_sub) {
+        for (int g = 0; g < c->n_sub; g++) {
+            int rc = jmme_set_reference_l1(c->sub[g], luma, stride);
+            if (rc != JMME_OK) return fail(c, rc, c->sub[g]->err);
+        }
+        return JMME_OK;
+    }
+    CU(c, cudaSetDevice(c->device));
+    const size_t n_mb = (size_t)c->mb_w * c->mb_h, psz = (size_t)c->pstride * c->pheight;
+    if (!c->d_planes_l1) {
+        const size_t n_pred = sizeof(int16_t) * 2 * JMME_NBLK * n_mb;
+        CU(c, cudaMalloc(&c->d_planes_l1, psz * c->n_planes));
+        CU(c, cudaMalloc(&c->d_raw_l1, (size_t)c->p.width * c->p.height));
+        CU(c, cudaMalloc(&c->d_bi_l0, sizeof(jmme_mbresult) * n_mb));
+        CU(c, cudaMalloc(&c->d_bi_l1, sizeof(jmme_mbresult) * n_mb));
+        CU(c, cudaMalloc(&c->d_bi_pred0, n_pred * c->p.num_refs));
+        CU(c, cudaMalloc(&c->d_bi_pred1, n_pred));
+        CU(c, cudaMalloc(&c->d_bi_spiral, sizeof(int16_t) * 2 * 31 * 31));
+        CU(c, cudaMalloc(&c->d_bi_out, sizeof(jmme_bipred) * n_mb));
+        CU(c, cudaMalloc(&c->d_bi_err, sizeof(int)));
+    }
+    CU(c, upload_rows(c->d_raw_l1, luma, stride, c->p.width, c->p.height, c->stream));
+    // every plane row: the refined vectors may leave the rows a uni-directional search of this stripe can reach
+    CU(c, jmme_launch_interp(c->d_raw_l1, c->p.width, c->p.height, c->p.width, c->pad, c->pstride, c->pheight, c->n_planes,
+                             c->d_planes_l1, 0, c->pheight, c->stream));
+    c->launches++;
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->l1_set = true;
+    return JMME_OK;
+}
+
+int jmme_search_frame_bipred(jmme_ctx *c, const uint8_t *cur, int stride, const jmme_mbresult *l0, const jmme_mbresult *l1,
+                             const int16_t *pred0, const int16_t *pred1, int range, int iterations, jmme_bipred *out)
+{
+    if (!c || !cur || !l0 || !l1 || !out || stride < c->p.width || range < 1 || range > 15 || iterations < 1 || iterations > 8)
+        return JMME_ERR_PARAM;
+    if (c->n_sub) {
+        for (int g = 0; g < c->n_sub; g++) {
+            int rc = jmme_search_frame_bipred(c->sub[g], cur, stride, l0, l1, pred0, pred1, range, iterations, out);
+            if (rc != JMME_OK) return fail(c, rc, c->sub[g]->err);
+        }
+        return JMME_OK;
+    }
+    if (!c->l1_set) return fail(c, JMME_ERR_STATE, "list-1 reference not set");
+    for (int r = 0; r < c->p.num_refs; r++)
+        if (!c->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
+    // list-0 planes of a stripe context cover only the rows its own search reaches: the refinement needs the same
+    // margin the header promises (pad - 1), so a stripe context must hold whole planes
+    if (c->p.mb_row_begin != 0 || c->p.mb_row_end != c->mb_h) {
+        // rows outside [y_begin, y_end) of the list-0 planes were never written: refuse instead of reading them
+        const int R = c->p.search_range;
+        // quarter-pel, worst case: a uni-directional vector reaches R around the window centre, the centre R around
+        // (0,0) when predictors are given; each iteration of a list moves it by up to `range`
+        const int reach = 4 * (c->p.pred_policy == JMME_PRED_ZERO ? R : 2 * R) + 3 + 4 * range * ((iterations + 1) / 2);
+        const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - 2 * R - 4);
+        const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
+        const int need_b = c->pad + 16 * c->p.mb_row_begin - std::min((reach >> 2) + 1, c->pad - 1);
+        const int need_e = c->pad + 16 * c->p.mb_row_end + std::min((reach >> 2) + 1, c->pad - 1);
+        if (need_b < yb || need_e > ye) return fail(c, JMME_ERR_UNSUPPORTED, "bi-pred refinement on a stripe context: range * iterations exceeds the halo");
+    }
+    CU(c, cudaSetDevice(c->device));
+    const size_t n_mb = (size_t)c->mb_w * c->mb_h;
+    const int npb = c->p.pred_policy >= JMME_PRED_PER_BLOCK ? JMME_NBLK : 1;
+    const size_t off = (size_t)c->p.mb_row_begin * c->mb_w, cnt = (size_t)(c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w;
+    for (int k = 0; k < 2; k++) {                           // predictor range, the stripe's rows only
+        const int16_t *pr = k ? pred1 : pred0;
+        for (int r = 0; pr && r < (k ? 1 : c->p.num_refs); r++) {
+            const int16_t *q = pr + ((size_t)r * n_mb + off) * npb * 2;
+            for (size_t i = 0; i < cnt * npb * 2; i++)
+                if (q[i] > JMME_MAX_PRED_QPEL || q[i] < -JMME_MAX_PRED_QPEL) return fail(c, JMME_ERR_PARAM, "pred out of range");
+        }
+    }
+    // spiral of the refinement range
+    {
+        const int nc = (2 * range + 1) * (2 * range + 1);
+        std::vector<int16_t> xy(2 * (size_t)nc);
+        for (int dy = -range; dy <= range; dy++)
+            for (int dx = -range; dx <= range; dx++) {
+                const int k = spiral_index(dx, dy);
+                xy[2 * (size_t)k] = (int16_t)dx; xy[2 * (size_t)k + 1] = (int16_t)dy;
+            }
+        CU(c, cudaMemcpyAsync(c->d_bi_spiral, xy.data(), sizeof(int16_t) * 2 * nc, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));            // xy leaves scope
+    }
+    {
+        const int s0 = std::min(16 * c->p.mb_row_begin, c->p.height - 1), s1 = std::min(16 * c->p.mb_row_end, c->p.height);
+        CU(c, upload_rows(c->d_raw + (size_t)s0 * c->p.width, cur + (size_t)s0 * stride, stride, c->p.width, std::max(s1 - s0, 1), c->stream));
+    }
+    CU(c, cudaMemcpyAsync(c->d_bi_l0 + off, l0 + off, cnt * sizeof(jmme_mbresult), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_bi_l1 + off, l1 + off, cnt * sizeof(jmme_mbresult), cudaMemcpyHostToDevice, c->stream));
+    if (pred0)
+        for (int r = 0; r < c->p.num_refs; r++)
+            CU(c, cudaMemcpyAsync(c->d_bi_pred0 + ((size_t)r * n_mb + off) * npb * 2, pred0 + ((size_t)r * n_mb + off) * npb * 2,
+                                  cnt * npb * 2 * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+    if (pred1)
+        CU(c, cudaMemcpyAsync(c->d_bi_pred1 + off * npb * 2, pred1 + off * npb * 2, cnt * npb * 2 * sizeof(int16_t),
+                              cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemsetAsync(c->d_bi_err, 0, sizeof(int), c->stream));
+    const uint8_t *d_cur = c->d_raw;
+    int cs = c->p.width, cur_h = c->p.height;
+    if (c->w16 != c->p.width) {
+        CU(c, jmme_launch_pad_cur(c->d_raw, c->p.width, c->p.height, c->p.width, c->w16, c->h16, c->d_cur16, c->stream));
+        c->launches++;
+        d_cur = c->d_cur16; cs = c->w16; cur_h = c->h16;
+    }
+    SearchParams P;
+    fill_search_params(c, P, d_cur, cs, nullptr, nullptr, nullptr);
+    P.cur_h = cur_h;
+    BipredArgs A;
+    A.planes_l1 = c->d_planes_l1; A.l0 = c->d_bi_l0; A.l1 = c->d_bi_l1;
+    A.pred0 = pred0 ? c->d_bi_pred0 : nullptr; A.pred1 = pred1 ? c->d_bi_pred1 : nullptr;
+    A.spiral_xy = c->d_bi_spiral; A.range = range; A.iterations = iterations; A.npb = npb; A.n_planes = c->n_planes;
+    A.out = c->d_bi_out; A.err = c->d_bi_err;
+    CU(c, jmme_launch_bipred(P, A, c->stream));
+    c->launches++;
+    int err = 0;
+    CU(c, cudaMemcpyAsync(out + off, c->d_bi_out + off, cnt * sizeof(jmme_bipred), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(&err, c->d_bi_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return err ? fail(c, JMME_ERR_PARAM, "l0 / l1 records: reference index or vector phase not usable") : JMME_OK;
 }
 
 int jmme_set_profiling(jmme_ctx *c, int enable)

@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 4          # JMME_ABI_VERSION of include/jmme.h
+ABI_VERSION = 5          # JMME_ABI_VERSION of include/jmme.h
 BLOCKS_PER_MB = 41
 MAX_REFS = 4
 MAX_GPUS = 8
@@ -59,11 +59,15 @@ class Tuning(C.Structure):
 MBRESULT_DTYPE = np.dtype([("mv", np.int16, (BLOCKS_PER_MB, 2)), ("cost", np.int32, (BLOCKS_PER_MB,)),
                            ("ref_idx", np.int8, (BLOCKS_PER_MB,)), ("reserved", np.int8, (3,))], align=True)
 assert MBRESULT_DTYPE.itemsize == 372, MBRESULT_DTYPE.itemsize
+BIPRED_DTYPE = np.dtype([("mv0", np.int16, (BLOCKS_PER_MB, 2)), ("mv1", np.int16, (BLOCKS_PER_MB, 2)),
+                         ("cost", np.int32, (BLOCKS_PER_MB,)), ("ref0", np.int8, (BLOCKS_PER_MB,)), ("reserved", np.int8, (3,))],
+                        align=True)
+assert BIPRED_DTYPE.itemsize == 536, BIPRED_DTYPE.itemsize
 
 EXPORTS = [
     "jmme_default_params", "jmme_create", "jmme_destroy", "jmme_strerror", "jmme_last_error", "jmme_backend",
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
-    "jmme_lambda_factor", "jmme_set_reference", "jmme_set_reference_chroma", "jmme_set_current_chroma", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
+    "jmme_lambda_factor", "jmme_set_reference_l1", "jmme_search_frame_bipred", "jmme_set_reference", "jmme_set_reference_chroma", "jmme_set_current_chroma", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
     "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_set_reference_chroma_dev", "jmme_set_current_chroma_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev",
     "jmme_launch_count", "jmme_set_tuning", "jmme_get_tuning", "jmme_last_kernel",
     "jmme_set_profiling",
@@ -106,6 +110,8 @@ class Lib:
             "jmme_lambda_factor_of": (i32, [vp]),
             "jmme_lambda_factor": (i32, [i32, i32]),
             "jmme_set_reference": (i32, [vp, i32, pu8, i32]),
+            "jmme_set_reference_l1": (i32, [vp, pu8, i32]),
+            "jmme_search_frame_bipred": (i32, [vp, pu8, i32, vp, vp, pi16, pi16, i32, i32, vp]),
             "jmme_set_reference_chroma": (i32, [vp, i32, pu8, pu8, i32]),
             "jmme_set_current_chroma": (i32, [vp, pu8, pu8, i32]),
             "jmme_search_frame": (i32, [vp, pu8, i32, pi16, vp, vp]),
@@ -337,6 +343,29 @@ class Context:
         self.lib.check(self.lib.dll.jmme_search_frame(self.handle, p, cur.strides[0], pp, out.ctypes.data,
                                                       opr.ctypes.data if per_ref else None), self.handle)
         return (out, opr) if per_ref else out
+
+    def set_reference_l1(self, luma):
+        luma, p = _u8(luma)
+        self.lib.check(self.lib.dll.jmme_set_reference_l1(self.handle, p, luma.strides[0]), self.handle)
+
+    def search_frame_bipred(self, cur, l0, l1, pred0=None, pred1=None, search_range=8, iterations=2):
+        """Bi-predictive refinement of the vector pairs of two uni-directional searches -> BIPRED_DTYPE records."""
+        cur, p = _u8(cur)
+        l0, l1 = np.ascontiguousarray(l0), np.ascontiguousarray(l1)
+        n = self.mb_w * self.mb_h
+        assert l0.dtype == MBRESULT_DTYPE and l1.dtype == MBRESULT_DTYPE and len(l0) == len(l1) == n
+        out = np.zeros(n, BIPRED_DTYPE)
+        pp = []
+        for pr in (pred0, pred1):
+            if pr is None:
+                pp.append(None)
+            else:
+                pr = np.ascontiguousarray(pr, dtype=np.int16)
+                pp.append((pr, pr.ctypes.data_as(C.POINTER(C.c_int16))))
+        self.lib.check(self.lib.dll.jmme_search_frame_bipred(self.handle, p, cur.strides[0], l0.ctypes.data, l1.ctypes.data,
+                                                             pp[0][1] if pp[0] else None, pp[1][1] if pp[1] else None,
+                                                             search_range, iterations, out.ctypes.data), self.handle)
+        return out
 
     def commit_field(self, res):
         """ME-only mode decision -> (mv4 [4mb_h,4mb_w,2] int16, ref4 [4mb_h,4mb_w] int8, mode [n_mb,5] uint8)."""

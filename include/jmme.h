@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define JMME_ABI_VERSION     4
+#define JMME_ABI_VERSION     5
 #define JMME_BLOCKS_PER_MB   41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 */
 #define JMME_MAX_REFS        4
 #define JMME_MAX_SEARCH_RANGE 64
@@ -168,6 +168,33 @@ int jmme_set_current_chroma(jmme_ctx *ctx, const uint8_t *cb, const uint8_t *cr,
  *                rate (JM all_mv / motion_cost) */
 int jmme_search_frame(jmme_ctx *ctx, const uint8_t *cur_luma, int stride,
                       const int16_t *pred, jmme_mbresult *out, jmme_mbresult *out_per_ref);
+
+/* ---- (f2) bi-predictive refinement (JM BiPredMotionEstimation / BiPredMERefinements / BiPredMESearchRange) ------
+ * List 0 = the context's references, list 1 = one more reference picture (jmme_set_reference_l1: uploaded and
+ * interpolated like a list-0 reference).  jmme_search_frame_bipred refines, block by block, the vector pair
+ * (mv0 towards reference l0.ref_idx of list 0, mv1 towards the list-1 picture) found by two uni-directional searches:
+ *   iteration i = 0 .. iterations-1 searches list s = i & 1 with the other list's vector held fixed: candidates
+ *   mv_s + 4 (dx, dy) over the spiral of `range` (position 0, the current pair, first; strict <), prediction =
+ *   (P_fixed + P_candidate + 1) >> 1 per sample [STD 8.4.2.3 default weighted prediction] taken from the quarter-pel
+ *   planes at each vector's own phase, cost = distortion (metric and cost domain of the integer stage) + the MV rate
+ *   of BOTH vectors against their predictors; candidates whose integer displacement leaves +-(pad - 1) are skipped.
+ * l0, l1: whole-frame jmme_search_frame outputs (host) of the list-0 context search and of a search against the
+ * list-1 picture; pred0 / pred1: predictors of the two lists in the layout of the context's pred_policy (NULL = zero;
+ * JMME_PRED_MEDIAN contexts take PER_BLOCK arrays here).  range 1..15, iterations 1..8.  Blocks whose blocktype is
+ * masked out: vectors 0, cost INT32_MAX, ref0 -1.  Only the stripe's rows are written.  A context that searches a
+ * stripe holds the list-0 planes for the rows its own search can reach (+-(2 R + 4) around the stripe): the product
+ * library answers JMME_ERR_UNSUPPORTED when range x iterations could leave them. */
+typedef struct jmme_bipred {
+    int16_t mv0[JMME_BLOCKS_PER_MB][2];
+    int16_t mv1[JMME_BLOCKS_PER_MB][2];
+    int32_t cost[JMME_BLOCKS_PER_MB];
+    int8_t  ref0[JMME_BLOCKS_PER_MB];
+    int8_t  reserved[3];
+} jmme_bipred;
+int jmme_set_reference_l1(jmme_ctx *ctx, const uint8_t *luma, int stride);
+int jmme_search_frame_bipred(jmme_ctx *ctx, const uint8_t *cur_luma, int stride, const jmme_mbresult *l0,
+                             const jmme_mbresult *l1, const int16_t *pred0, const int16_t *pred1, int range,
+                             int iterations, jmme_bipred *out);
 
 /* The predictors the last jmme_search_frame of a JMME_PRED_MEDIAN context used:
  * int16 [num_refs][mb_w*mb_h][41][2] (only the stripe's rows are meaningful). */

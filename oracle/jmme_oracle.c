@@ -50,6 +50,7 @@ struct jmme_ctx {
     uint8_t *cur_c[2];               /* current chroma, padded to w16/2 x h16/2 by replication */
     int cur_c_set;
     uint8_t *planes[JMME_MAX_REFS];  /* [n_planes] padded planes, contiguous */
+    uint8_t *planes_l1;              /* bi-pred: the list-1 picture, same layout */
     int ref_set[JMME_MAX_REFS];
     int32_t *mvbits;                 /* centred table, index v + MAX_MVD */
     int16_t *spx, *spy;              /* spiral */
@@ -434,7 +435,7 @@ int jmme_destroy(jmme_ctx *c)
     int r;
     if (!c) return JMME_OK;
     for (r = 0; r < JMME_MAX_REFS; r++) { free(c->planes[r]); free(c->cplanes[r][0]); free(c->cplanes[r][1]); }
-    free(c->cur_c[0]); free(c->cur_c[1]);
+    free(c->cur_c[0]); free(c->cur_c[1]); free(c->planes_l1);
     free(c->med_pred); free(c->fmv); free(c->fref);
     free(c->mvbits); free(c->spx); free(c->spy); free(c);
     return JMME_OK;
@@ -1108,6 +1109,114 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
     }
     free(cur);
     return fail ? JMME_ERR_NOMEM : JMME_OK;
+}
+
+/* ---- (f2) bi-predictive refinement: JM BiPredBlockMotionSearch, restated per the header's definition -------- */
+int jmme_set_reference_l1(jmme_ctx *c, const uint8_t *luma, int stride)
+{
+    size_t sz;
+    if (!c || !luma || stride < c->p.width) return JMME_ERR_PARAM;
+    sz = (size_t)c->pstride * c->pheight * c->n_planes;
+    if (!c->planes_l1) c->planes_l1 = (uint8_t *)malloc(sz);
+    if (!c->planes_l1) return set_err(c, JMME_ERR_NOMEM, "plane allocation failed");
+    return build_planes(luma, c->p.width, c->p.height, stride, c->w16, c->h16, c->pad, c->n_planes, c->planes_l1);
+}
+
+/* sample block of reference planes `pl` at quarter-pel vector (qx, qy): pointer to its top-left sample */
+static const uint8_t *pred_block(const jmme_ctx *c, const uint8_t *pl, int bx, int by, int qx, int qy)
+{
+    const uint8_t *plane = pl + (size_t)c->pstride * c->pheight * ((qy & 3) * 4 + (qx & 3));
+    return plane_at(plane, c->pstride, c->pad, bx + (qx >> 2), by + (qy >> 2));
+}
+
+int jmme_search_frame_bipred(jmme_ctx *c, const uint8_t *cur_in, int stride, const jmme_mbresult *l0, const jmme_mbresult *l1,
+                             const int16_t *pred0, const int16_t *pred1, int range, int iterations, jmme_bipred *out)
+{
+    const int npb = c && c->p.pred_policy >= JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
+    int16_t *spx, *spy;
+    uint8_t *cur;
+    int x, y, mb, nmb, ncand, bad = 0;
+    if (!c || !cur_in || !l0 || !l1 || !out || stride < c->p.width || range < 1 || range > 15 || iterations < 1 || iterations > 8)
+        return JMME_ERR_PARAM;
+    if (!c->planes_l1) return set_err(c, JMME_ERR_STATE, "list-1 reference not set");
+    for (x = 0; x < c->p.num_refs; x++)
+        if (!c->ref_set[x]) return set_err(c, JMME_ERR_STATE, "reference not set");
+    nmb = c->mb_w * c->mb_h;
+    ncand = (2 * range + 1) * (2 * range + 1);
+    spx = (int16_t *)malloc(2 * ncand); spy = (int16_t *)malloc(2 * ncand);
+    cur = (uint8_t *)malloc((size_t)c->w16 * c->h16);
+    if (!spx || !spy || !cur) { free(spx); free(spy); free(cur); return JMME_ERR_NOMEM; }
+    build_spiral(range, spx, spy);
+    for (y = 0; y < c->h16; y++)
+        for (x = 0; x < c->w16; x++)
+            cur[(size_t)y * c->w16 + x] = cur_in[(size_t)clampi(y, 0, c->p.height - 1) * stride + clampi(x, 0, c->p.width - 1)];
+#pragma omp parallel for schedule(dynamic, 4) num_threads(g_threads)
+    for (mb = c->p.mb_row_begin * c->mb_w; mb < c->p.mb_row_end * c->mb_w; mb++) {
+        const int mbx = mb % c->mb_w, mby = mb / c->mb_w;
+        jmme_bipred *o = &out[mb];
+        int t, i, j;
+        memset(o, 0, sizeof *o);
+        for (i = 0; i < JMME_BLOCKS_PER_MB; i++) { o->cost[i] = INT_MAX; o->ref0[i] = -1; }
+        for (t = 1; t <= 7; t++) {
+            const int bw = blc_w[t], bh = blc_h[t], nbx = 16 / bw, nby = 16 / bh;
+            if (!(c->p.blocktype_mask & (1 << t))) continue;
+            for (j = 0; j < nby; j++)
+                for (i = 0; i < nbx; i++) {
+                    const int blk = blk_base[t] + j * nbx + i, bx = 16 * mbx + i * bw, by = 16 * mby + j * bh;
+                    const int r0 = l0[mb].ref_idx[blk];
+                    const uint8_t *pl[2];
+                    int mv[2][2], pr[2][2], it, best_cost = INT_MAX;
+                    if (r0 < 0 || r0 >= c->p.num_refs || l1[mb].ref_idx[blk] < 0) {
+#pragma omp atomic write
+                        bad = 1;
+                        continue;
+                    }
+                    pl[0] = c->planes[r0]; pl[1] = c->planes_l1;
+                    mv[0][0] = l0[mb].mv[blk][0]; mv[0][1] = l0[mb].mv[blk][1];
+                    mv[1][0] = l1[mb].mv[blk][0]; mv[1][1] = l1[mb].mv[blk][1];
+                    if (c->n_planes == 1 && ((mv[0][0] | mv[0][1] | mv[1][0] | mv[1][1]) & 3)) {
+#pragma omp atomic write
+                        bad = 1;
+                        continue;
+                    }
+                    {
+                        const int16_t *p0 = pred0 ? pred0 + ((size_t)r0 * nmb + mb) * npb * 2 + (npb == 1 ? 0 : 2 * blk) : NULL;
+                        const int16_t *p1 = pred1 ? pred1 + (size_t)mb * npb * 2 + (npb == 1 ? 0 : 2 * blk) : NULL;
+                        pr[0][0] = p0 ? p0[0] : 0; pr[0][1] = p0 ? p0[1] : 0;
+                        pr[1][0] = p1 ? p1[0] : 0; pr[1][1] = p1 ? p1[1] : 0;
+                    }
+                    for (it = 0; it < iterations; it++) {
+                        const int s = it & 1, f = 1 - s;
+                        const uint8_t *fb = pred_block(c, pl[f], bx, by, mv[f][0], mv[f][1]);
+                        const int fbits = c->mvbits[mv[f][0] - pr[f][0] + MAX_MVD] + c->mvbits[mv[f][1] - pr[f][1] + MAX_MVD];
+                        int pos, bp = -1, min = INT_MAX;
+                        for (pos = 0; pos < ncand; pos++) {
+                            const int qx = mv[s][0] + 4 * spx[pos], qy = mv[s][1] + 4 * spy[pos];
+                            const uint8_t *sb;
+                            int xx, yy, d = 0, cst;
+                            if ((qx >> 2) < -(c->pad - 1) || (qx >> 2) > c->pad - 1 || (qy >> 2) < -(c->pad - 1) || (qy >> 2) > c->pad - 1)
+                                continue;
+                            sb = pred_block(c, pl[s], bx, by, qx, qy);
+                            for (yy = 0; yy < bh; yy++)
+                                for (xx = 0; xx < bw; xx++) {
+                                    const int p = (fb[(size_t)yy * c->pstride + xx] + sb[(size_t)yy * c->pstride + xx] + 1) >> 1;
+                                    const int e = (int)cur[(size_t)(by + yy) * c->w16 + bx + xx] - p;
+                                    d += c->metric[0] == JMME_DIST_SSE ? e * e : (e < 0 ? -e : e);
+                                }
+                            cst = dscale(c->p.cost_domain, d) +
+                                  wcost(c->p.cost_domain, c->lf[0], fbits + c->mvbits[qx - pr[s][0] + MAX_MVD] + c->mvbits[qy - pr[s][1] + MAX_MVD]);
+                            if (cst < min) { min = cst; bp = pos; }
+                        }
+                        if (bp >= 0) { mv[s][0] += 4 * spx[bp]; mv[s][1] += 4 * spy[bp]; best_cost = min; }
+                    }
+                    o->mv0[blk][0] = (int16_t)mv[0][0]; o->mv0[blk][1] = (int16_t)mv[0][1];
+                    o->mv1[blk][0] = (int16_t)mv[1][0]; o->mv1[blk][1] = (int16_t)mv[1][1];
+                    o->cost[blk] = best_cost; o->ref0[blk] = (int8_t)r0;
+                }
+        }
+    }
+    free(spx); free(spy); free(cur);
+    return bad ? set_err(c, JMME_ERR_PARAM, "l0 / l1 records: reference index or vector phase not usable") : JMME_OK;
 }
 
 int jmme_get_predictors(jmme_ctx *c, int16_t *pred)

@@ -327,3 +327,34 @@ def block_search(spec, cur, ref, bx, by, bw, bh, cx, cy, px, py, R, bonus16, pre
         mvx, mvy = ox + step * sp[bp][0], oy + step * sp[bp][1]
         prev = spec.metrics[st]
     return mvx, mvy, mn
+
+
+def bipred_block(spec, cur, refs0, ref1, bx, by, bw, bh, mv0, mv1, pr0, pr1, rng, iterations, pad):
+    """Bi-predictive refinement of one block (include/jmme.h, jmme_search_frame_bipred), sample by sample through
+    Interp: iteration i searches list i & 1 over the spiral of `rng` around its current vector, the other list
+    fixed; prediction (a + b + 1) >> 1; rate of both vectors.  refs0: the list-0 picture.  Returns (mv0, mv1, cost)."""
+    its = [Interp(refs0), Interp(ref1)]
+    blk = np.asarray(cur, dtype=np.int64)[by:by + bh, bx:bx + bw]
+    mv = [[int(v) for v in mv0], [int(v) for v in mv1]]
+    pr = [[int(v) for v in pr0], [int(v) for v in pr1]]
+
+    def block(k, qx, qy):
+        return np.array([[its[k].sample(4 * (bx + x) + qx, 4 * (by + y) + qy) for x in range(bw)] for y in range(bh)], dtype=np.int64)
+
+    cost = None
+    for it in range(iterations):
+        s, f = it & 1, 1 - (it & 1)
+        fixed = block(f, mv[f][0], mv[f][1])
+        fbits = se_bits(mv[f][0] - pr[f][0]) + se_bits(mv[f][1] - pr[f][1])
+        best = None
+        for dx, dy in spiral(rng):
+            qx, qy = mv[s][0] + 4 * dx, mv[s][1] + 4 * dy
+            if not (-(pad - 1) <= (qx >> 2) <= pad - 1 and -(pad - 1) <= (qy >> 2) <= pad - 1):
+                continue
+            e = blk - ((fixed + block(s, qx, qy) + 1) >> 1)
+            d = int((e * e).sum()) if spec.metrics[0] == 1 else int(np.abs(e).sum())
+            c = spec.dist(d) + spec.rate(0, fbits + se_bits(qx - pr[s][0]) + se_bits(qy - pr[s][1]))
+            if best is None or c < best[0]:
+                best = (c, qx, qy)
+        cost, mv[s][0], mv[s][1] = best
+    return tuple(mv[0]), tuple(mv[1]), cost

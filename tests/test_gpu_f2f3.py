@@ -187,3 +187,76 @@ def test_chroma_device_api(cuda, oracle):
     (o, _), _ = run(oracle, cur, refs, None, True, chroma=(cur_c, [ref_c]), **kw)
     assert_same(got, o, "device chroma API")
     ds.close()
+
+
+@pytest.mark.parametrize("kw", [dict(subpel=1, qp=30), dict(subpel=0, rdopt=1, qp=26, cost_domain=1), dict(subpel=1, **SSE3),
+                                dict(subpel=1, blocktype_mask=0x92, qp=34)])
+@pytest.mark.parametrize("policy", [abi.PRED_ZERO, abi.PRED_PER_BLOCK])
+def test_bipred_refinement_matches_oracle(cuda, oracle, kw, policy):
+    """jmme_search_frame_bipred (f2): list 0 = two references, list 1 = one more picture; start pairs from the
+    uni-directional searches of each library (already bit-exact), refinement records compared bit for bit."""
+    for (w, h, R, rng, iters) in ((64, 48, 6, 3, 2), (52, 38, 9, 8, 3), (96, 64, 16, 15, 4)):
+        cur, refs = synth.frame_pair(w, h, seed=9, search_range=R, num_refs=2)
+        ref1 = synth.frame_pair(w, h, seed=10, search_range=R)[1][0]
+        n_mb = ((w + 15) // 16) * ((h + 15) // 16)
+        nb = 41 if policy == abi.PRED_PER_BLOCK else 0
+        pred0 = synth.random_pred(2, n_mb, nb, 3, 4 * R + 10) if nb else None
+        pred1 = synth.random_pred(1, n_mb, nb, 4, 4 * R + 10) if nb else None
+        outs = []
+        for lib in (cuda, oracle):
+            with lib.context(width=w, height=h, search_range=R, num_refs=2, pred_policy=policy, **kw) as ctx, \
+                    lib.context(width=w, height=h, search_range=R, num_refs=1, pred_policy=policy, **kw) as ctx1:
+                for i, r in enumerate(refs):
+                    ctx.set_reference(i, r)
+                ctx1.set_reference(0, ref1)
+                l0, l1 = ctx.search_frame(cur, pred0), ctx1.search_frame(cur, pred1)
+                ctx.set_reference_l1(ref1)
+                outs.append((l0, l1, ctx.search_frame_bipred(cur, l0, l1, pred0, pred1, rng, iters)))
+        assert outs[0][0].tobytes() == outs[1][0].tobytes() and outs[0][1].tobytes() == outs[1][1].tobytes()
+        g, o = outs[0][2], outs[1][2]
+        for f in ("mv0", "mv1", "cost", "ref0"):
+            bad = np.argwhere(g[f] != o[f])
+            assert len(bad) == 0, f"{w}x{h} {kw} {f}: {len(bad)} mismatches, first {bad[0]}: gpu {g[f][tuple(bad[0][:2])]} oracle {o[f][tuple(bad[0][:2])]}"
+        assert g.tobytes() == o.tobytes()
+        assert np.any(g["mv0"] != outs[0][0]["mv"]) or np.any(g["mv1"] != outs[0][1]["mv"])       # something was refined
+
+
+def test_bipred_stripes_virtual_devices_and_errors(cuda, oracle):
+    import torch
+    w, h, R = 64, 112, 6
+    cur, refs = synth.frame_pair(w, h, seed=5, search_range=R)
+    ref1 = synth.frame_pair(w, h, seed=6, search_range=R)[1][0]
+    kw = dict(width=w, height=h, search_range=R, subpel=1, qp=29)
+    with oracle.context(**kw) as o:
+        o.set_reference(0, refs[0])
+        l0 = o.search_frame(cur)
+        o.set_reference(0, ref1)
+        l1 = o.search_frame(cur)
+        o.set_reference(0, refs[0])
+        o.set_reference_l1(ref1)
+        exp = o.search_frame_bipred(cur, l0, l1, search_range=4, iterations=2)
+    ndev = torch.cuda.device_count()
+    for extra in (dict(), dict(n_gpus=3, device_ids=[i % ndev for i in range(3)]), dict(mb_row_begin=2, mb_row_end=5)):
+        with cuda.context(**kw, **extra) as g:
+            with pytest.raises(abi.JmmeError) as e:
+                g.set_reference(0, refs[0])
+                g.search_frame_bipred(cur, l0, l1)
+            assert e.value.code == abi.ERR_STATE
+            g.set_reference_l1(ref1)
+            got = g.search_frame_bipred(cur, l0, l1, search_range=4, iterations=2)
+            rb, re = extra.get("mb_row_begin", 0), extra.get("mb_row_end", 7)
+            assert got[rb * 4:re * 4].tobytes() == exp[rb * 4:re * 4].tobytes(), extra
+            assert not got[:rb * 4].tobytes().strip(b"\0") and not got[re * 4:].tobytes().strip(b"\0")
+    for lib in (cuda, oracle):
+        with lib.context(width=w, height=h, search_range=R, subpel=0) as c:          # integer plane only: qpel vectors refused
+            c.set_reference(0, refs[0])
+            c.set_reference_l1(ref1)
+            with pytest.raises(abi.JmmeError) as e:
+                c.search_frame_bipred(cur, l0, l1, search_range=2, iterations=1)
+            assert e.value.code == abi.ERR_PARAM
+            bad = l0.copy()
+            bad["mv"] = 0
+            bad["ref_idx"][3, 7] = 2                                                     # not a reference of the context
+            with pytest.raises(abi.JmmeError) as e:
+                c.search_frame_bipred(cur, bad, bad, search_range=2, iterations=1)
+            assert e.value.code == abi.ERR_PARAM

@@ -128,3 +128,67 @@ def test_new_parameter_errors(oracle):
         with pytest.raises(abi.JmmeError) as e:
             ctx.set_current_chroma(np.zeros((16, 16), np.uint8), np.zeros((16, 16), np.uint8))
         assert e.value.code == abi.ERR_STATE
+
+
+@pytest.mark.parametrize("kw,metric0", [(dict(subpel=1, qp=30), 0), (dict(subpel=0, rdopt=1, qp=26, cost_domain=1), 0),
+                                        (dict(subpel=1, me_distortion=1, me_distortion_fpel=1, me_distortion_hpel=2, me_distortion_qpel=2), 1)])
+def test_bipred_refinement_against_the_restatement(oracle, kw, metric0):
+    """jmme_search_frame_bipred: two uni-directional searches give the start pair, the refinement is compared block by
+    block with the per-sample restatement (quarter-pel fixed vectors, both rates, spiral order, strict <)."""
+    w, h, R, rng, iters = 32, 32, 3, 2, 3
+    cur, refs = synth.frame_pair(w, h, seed=9, search_range=R, num_refs=2)
+    ref1 = synth.frame_pair(w, h, seed=10, search_range=R)[1][0]
+    rdopt, qp = kw.get("rdopt", 0), kw.get("qp", 28)
+    pred0 = synth.random_pred(2, 4, 41, seed=3, max_qpel=7)
+    pred1 = synth.random_pred(1, 4, 41, seed=4, max_qpel=7)
+    with oracle.context(width=w, height=h, search_range=R, num_refs=2, pred_policy=abi.PRED_PER_BLOCK, **kw) as ctx, \
+            oracle.context(width=w, height=h, search_range=R, num_refs=1, pred_policy=abi.PRED_PER_BLOCK, **kw) as ctx1:
+        for i, r in enumerate(refs):
+            ctx.set_reference(i, r)
+        ctx1.set_reference(0, ref1)
+        l0, l1 = ctx.search_frame(cur, pred0), ctx1.search_frame(cur, pred1)
+        ctx.set_reference_l1(ref1)
+        got = ctx.search_frame_bipred(cur, l0, l1, pred0, pred1, rng, iters)
+        pad = ctx.pad
+    spec = refimpl.StageSpec(lam_of(qp, rdopt), kw.get("cost_domain", 0), (metric0, 2, 2))
+    assert len(np.unique(l0["ref_idx"])) > 1
+    moved = 0
+    for mb in range(4):
+        for b, (t, x0, y0, bw, bh) in enumerate(BLOCKS):
+            if b not in (0, 2, 3, 7, 10, 19, 33):
+                continue
+            r0 = int(l0[mb]["ref_idx"][b])
+            e0, e1, c = refimpl.bipred_block(spec, cur, refs[r0], ref1, 16 * (mb % 2) + x0, 16 * (mb // 2) + y0, bw, bh,
+                                             l0[mb]["mv"][b], l1[mb]["mv"][b], [int(v) for v in pred0[r0, mb, b]],
+                                             [int(v) for v in pred1[0, mb, b]], rng, iters, pad)
+            assert (tuple(got[mb]["mv0"][b]), tuple(got[mb]["mv1"][b]), int(got[mb]["cost"][b]), int(got[mb]["ref0"][b])) == (e0, e1, c, r0), (mb, b)
+            moved += e0 != tuple(l0[mb]["mv"][b]) or e1 != tuple(l1[mb]["mv"][b])
+    assert moved > 0                                                  # the refinement changes some pairs
+
+
+def test_bipred_errors_and_masks(oracle):
+    w, h, R = 32, 32, 3
+    cur, refs = synth.frame_pair(w, h, seed=9, search_range=R)
+    with oracle.context(width=w, height=h, search_range=R, blocktype_mask=0x92) as ctx:
+        ctx.set_reference(0, refs[0])
+        l0 = ctx.search_frame(cur)
+        with pytest.raises(abi.JmmeError) as e:
+            ctx.search_frame_bipred(cur, l0, l0)
+        assert e.value.code == abi.ERR_STATE                          # no list-1 picture yet
+        ctx.set_reference_l1(refs[0])
+        for bad in (dict(search_range=0), dict(search_range=16), dict(iterations=0), dict(iterations=9)):
+            with pytest.raises(abi.JmmeError) as e:
+                ctx.search_frame_bipred(cur, l0, l0, **bad)
+            assert e.value.code == abi.ERR_PARAM
+        out = ctx.search_frame_bipred(cur, l0, l0, search_range=2, iterations=2)
+        off = [b for b, blk in enumerate(BLOCKS) if blk[0] not in (1, 4, 7)]
+        assert np.all(out["ref0"][:, off] == -1) and np.all(out["cost"][:, off] == abi.INT32_MAX)
+        on = [b for b, blk in enumerate(BLOCKS) if blk[0] in (1, 4, 7)]
+        assert np.all(out["ref0"][:, on] == 0)
+        # identical pictures on both lists: averaging two copies of the best uni-directional block cannot cost more
+        # distortion than it, so the pair cost is at most the uni cost plus the second vector's rate
+        lf = ctx.lambda_factor
+        for mb in range(4):
+            for b in on:
+                bits = refimpl.se_bits(int(l0[mb]["mv"][b][0])) + refimpl.se_bits(int(l0[mb]["mv"][b][1]))
+                assert out[mb]["cost"][b] <= l0[mb]["cost"][b] + refimpl.weighted_cost(lf, bits) + 1

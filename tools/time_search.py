@@ -35,7 +35,7 @@ for K in [int(k) for k in a.Ks.split(",")]:
     for subpel in sorted({0, a.subpel}):
         s = DeviceSearch(lib, width=a.w, height=a.h, search_range=a.R, num_refs=a.refs, subpel=subpel,
                          blocktype_mask=a.mask, pred_policy=a.pred, qp=28, mb_row_end=a.rows,
-                         tuning=dict(variant=K, group=a.group, **{k: int(v) for k, v in (kv.split('=') for kv in a.tuning.split(',') if kv)}))
+                         tuning={**dict(variant=K, group=a.group), **{k: int(v) for k, v in (kv.split('=') for kv in a.tuning.split(',') if kv)}})
         pred = None
         if a.pred:
             nb = 1 if a.pred == 1 else 41
