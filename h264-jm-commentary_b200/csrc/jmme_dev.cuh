@@ -133,6 +133,14 @@ cudaError_t jmme_kernel_occupancy(Kern kern, KernelState &ks, int threads, size_
 char *jmme_kernel_name_buf();
 #define JMME_KNAME_LEN 320
 
+// Loops in front of a CTA barrier must have a warp-uniform trip count (`for (x0 = 0; x0 < n; x0 += 32) { x = x0 + lane;
+// if (x >= n) continue; ... }`, not `for (x = lane; x < n; x += 32)`).  ptxas 12.9 was seen to drop the reconvergence
+// point (BSSY/BSYNC) of a lane-strided loop — the window expansion of me_int_tb.cu, once an epilogue behind the item
+// loop turned its `break` into a branch: the lanes without a second trip ran ahead, reached BAR.SYNC while the warp
+// was still diverged (bar.sync is warp-aligned: the warp then counts as arrived) and the barrier released before the
+// other lanes had written their window columns.  An explicit __syncwarp() in front of the barrier does not help:
+// ptxas turns it into a NOP where its analysis says "converged".  Found by the whole-frame parity tests (every item
+// after a CTA's first was wrong), verified in the SASS.
 // Programmatic dependent launch (sm_90+).  pdl_trigger: the next kernel of the stream may start its prologue;
 // pdl_wait: results of the previous kernel are complete and visible from here on.  Both are no-ops for a
 // kernel launched without the programmatic-serialization attribute.

@@ -237,7 +237,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     auto expand = [&](const Item &it) {
         const int gx0 = P.pad + 16 * it.mbx + it.cx - R;
         const int t16 = gx0 & 15, np = RS >> 1;          // word pairs per row (RS is even)
-        for (int xp = lane; xp < np; xp += 32) {         // this lane's word pair(s): fixed across rows
+        // (warp-uniform trip count: see the note on loops in front of a barrier in jmme_dev.cuh)
+        for (int xp0 = 0; xp0 < np; xp0 += 32) {         // this lane's word pair(s): fixed across rows
+            const int xp = xp0 + lane;
+            if (xp >= np) continue;
             const int o0 = t16 + 2 * xp, i0 = o0 >> 2, b0 = o0 & 3;
             // words at byte offsets o0 and o0+1 out of three aligned raw words (byte permute)
             const unsigned sel0 = 0x3210u + 0x1111u * b0;
