@@ -8,7 +8,8 @@
 //   ms            CUDA events around the last launches of a >= 150 ms back-to-back run (steady clocks:
 //                 a full-issue integer kernel runs into the 1000 W power cap like a dense GEMM does,
 //                 and the SM clock settles well below clocks.max.sm — that IS the sustained peak)
-//   cycles        in-kernel clock64 of every CTA, averaged  ->  mhz_clock64 = cycles / ms
+//   cycles        in-kernel clock64 of every CTA, first instruction to the barrier behind its last warp; the slowest
+//                 CTA spans the launch  ->  mhz_clock64 = max cycles / ms
 //   mhz_nvml      SM clock sampled through NVML by a host thread while the run is in flight (median)
 //
 // warp_instr_per_clk_per_sm counts SASS instructions (ptxas fuses two dependent min.u32 into one
@@ -38,7 +39,7 @@
         }                                                                         \
     } while (0)
 
-constexpr int ITERS = 2048;
+constexpr int ITERS = 8192;
 constexpr int CH = 8;
 
 enum Op { VSAD, IADD3, IMAD, LEA, VIMNMX, VIMNMX3, LOP3, PRMT, SHF, MIX_SAD_IMAD, MIX_SAD_IMAD_MIN, MIX_ME, LDS32, LDS128,
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(256) k(unsigned *out, long long *cycles, unsig
                         asm volatile("min.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b + r));
         }
     }
-    long long t1 = clock64();
+    __syncthreads();                       // every warp of the CTA is done: the schedulers favour the older warps, so
+    long long t1 = clock64();              // warp 0's own loop time alone under-reports the time the SM was busy
     unsigned s = 0;
     for (int i = 0; i < CH; i++) s += a[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
@@ -197,21 +199,23 @@ void run(int sms, unsigned *d_out, long long *d_cyc, Nvml &nvml, double run_ms, 
     ms /= n_timed;
     std::vector<long long> cyc(blocks);
     CHECK(cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost));
-    double avg = 0;
-    for (long long v : cyc) avg += (double)v;
+    double avg = 0, mx = 0;
+    for (long long v : cyc) { avg += (double)v; mx = std::max(mx, (double)v); }
     avg /= blocks;
     const double sass_per_sm = kSassOps[OP] * ITERS * 32.0;       // SASS warp-instructions per SM (32 warps)
-    const double ipc_clock64 = sass_per_sm / avg;
-    const double mhz_clock64 = avg / (ms * 1e-3) * 1e-6;
+    const double ipc_clock64 = sass_per_sm / mx;
+    // the slowest CTA spans the kernel (the 4 CTAs of an SM share its schedulers): its cycles over the event time of
+    // one launch is the SM clock if launches follow each other without a gap
+    const double mhz_clock64 = mx / (ms * 1e-3) * 1e-6;
     const double ipc_nvml = mhz_nvml > 0 ? sass_per_sm / (ms * 1e-3 * mhz_nvml * 1e6) : 0;
     const double lane_ops_s = kAlgOps[OP] * ITERS * (double)blocks * threads / (ms * 1e-3);
     char buf[768];
     snprintf(buf, sizeof buf,
              "  \"%s\": {\"tera_lane_ops_per_s\": %.3f, \"ms\": %.4f, \"launches\": %d, \"first_launch_ms\": %.4f, "
              "\"sass_warp_instr_per_clk_per_sm\": %.3f, \"sass_warp_instr_per_clk_per_sm_nvml_clock\": %.3f, "
-             "\"avg_cycles\": %.0f, \"mhz_clock64\": %.0f, \"mhz_nvml\": %.0f, \"power_w_max\": %.0f, "
+             "\"avg_cycles\": %.0f, \"max_cycles\": %.0f, \"mhz_clock64\": %.0f, \"mhz_nvml\": %.0f, \"power_w_max\": %.0f, "
              "\"alg_ops_per_iter\": %.1f, \"sass_ops_per_iter\": %.1f},\n",
-             kNames[OP], lane_ops_s * 1e-12, ms, n, ms1, ipc_clock64, ipc_nvml, avg, mhz_clock64, mhz_nvml, watts,
+             kNames[OP], lane_ops_s * 1e-12, ms, n, ms1, ipc_clock64, ipc_nvml, avg, mx, mhz_clock64, mhz_nvml, watts,
              kAlgOps[OP], kSassOps[OP]);
     json += buf;
     cudaEventDestroy(e0);
@@ -258,7 +262,7 @@ int main(int argc, char **argv)
         run<LDS128>(sms, d_out, d_cyc, nvml, run_ms, json);
         run<CREDUX>(sms, d_out, d_cyc, nvml, run_ms, json);
     }
-    json += "  \"note\": \"8 independent chains/thread, 32 warps/SM, 2048 iterations per launch; launches back to back for run_ms, "
+    json += "  \"note\": \"8 independent chains/thread, 32 warps/SM, 8192 iterations per launch; launches back to back for run_ms, "
             "events around the last third; IPC counts SASS instructions, lane-op rates count algorithmic operations\"\n}\n";
     fputs(json.c_str(), stdout);
     return 0;
