@@ -86,6 +86,7 @@ struct jmme_ctx {
     int16_t *d_pred;
     uint16_t *d_spiral_key;
     int16_t *d_spiral_xy;
+    uint32_t *d_kr0;                      // zero-predictor rate + key table of the context (SearchParams::kr0)
     BlkRes *d_res;
     jmme_mbresult *d_out, *d_out_per_ref;
     long long launches;
@@ -171,7 +172,7 @@ void free_device(jmme_ctx *c)
     cudaFree(c->d_cur_c[0]); cudaFree(c->d_cur_c[1]); cudaFree(c->d_craw);
     cudaFree(c->d_planes_l1); cudaFree(c->d_raw_l1); cudaFree(c->d_bi_l0); cudaFree(c->d_bi_l1); cudaFree(c->d_bi_pred0);
     cudaFree(c->d_bi_pred1); cudaFree(c->d_bi_spiral); cudaFree(c->d_bi_out); cudaFree(c->d_bi_err);
-    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy);
+    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy); cudaFree(c->d_kr0);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave); cudaFree(c->d_wave_tab);
     free(c->wave_off);
@@ -304,6 +305,24 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
             }
         CUC(cudaMemcpy(c->d_spiral_key, key.data(), sizeof(uint16_t) * c->ncand, cudaMemcpyHostToDevice));
         CUC(cudaMemcpy(c->d_spiral_xy, xy.data(), sizeof(int16_t) * 2 * c->ncand, cudaMemcpyHostToDevice));
+        {
+            // zero predictors: centre (0,0) and the rate are the same for every MB, so ((rate + bias) << 15) + key of
+            // every candidate is a constant of the context (Gen A cost domain, the packed 32-bit minimum of me_int_tb.cu);
+            // the MV (0,0) pre-test of FASTFULL / !rdopt is key 0
+            const int lf = c->lambda_factor;
+            const unsigned bias = c->p.rdopt ? 0u : (unsigned)(((long long)lf * 16) >> 16);
+            const bool pt = !c->p.rdopt && c->p.search_mode == JMME_SEARCH_FASTFULL;
+            auto se_bits = [](int v) { int a = v < 0 ? -v : v, n = 1; while (a) { n += 2; a >>= 1; } return n; };
+            std::vector<uint32_t> kr((size_t)c->ncand);
+            for (int yo = 0; yo < c->ncols; yo++)
+                for (int xo = 0; xo < c->ncols; xo++) {
+                    const size_t i = (size_t)yo * c->ncols + xo;
+                    const unsigned rate = (unsigned)(((long long)lf * (se_bits(4 * (xo - R)) + se_bits(4 * (yo - R)))) >> 16);
+                    kr[i] = ((rate + bias) << JMME_KEY_BITS) + ((pt && xo == R && yo == R) ? 0u : (unsigned)key[i]);
+                }
+            CUC(cudaMalloc(&c->d_kr0, sizeof(uint32_t) * c->ncand));
+            CUC(cudaMemcpy(c->d_kr0, kr.data(), sizeof(uint32_t) * c->ncand, cudaMemcpyHostToDevice));
+        }
         if (p->pred_policy == JMME_PRED_MEDIAN) {
             // 2:1 wavefront inside every slice: MB (x, y) of a slice that starts at row y0 is decided in step
             // x + 2 (y - y0), after its left, upper-left, upper and upper-right neighbours
@@ -353,7 +372,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.pred_policy = c->p.pred_policy; P.blocktype_mask = c->p.blocktype_mask;
     P.use_hadamard = c->metric[1] == JMME_DIST_HADAMARD; P.satd_round = c->p.satd_round; P.subpel = c->p.subpel;
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
-    P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy;
+    P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy; P.kr0 = c->d_kr0;
     P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
     P.cost_domain = c->p.cost_domain; P.ext = c->ext; P.t8 = c->p.transform8x8; P.chroma_me = c->p.chroma_me;
     for (int st = 0; st < 3; st++) { P.metric[st] = c->metric[st]; P.lf[st] = c->lf[st]; }

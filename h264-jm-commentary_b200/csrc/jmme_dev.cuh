@@ -39,6 +39,8 @@ struct SearchParams {
     const int16_t *pred;                 // [ref][mb][nb][2] or null
     const uint16_t *spiral_key;          // [ncols*ncols]  (yoff*ncols+xoff) -> spiral index + 1
     const int16_t *spiral_xy;            // [ncols*ncols][2] spiral index -> (dx,dy)
+    const uint32_t *kr0;                 // [ncols*ncols] zero predictors: ((rate + bias) << 15) + key of every candidate
+                                         // (context constant, built once by the host: me_int_tb.cu KRTAB)
     BlkRes *res;                         // [ref][mb][41]
     jmme_mbresult *out;                  // [mb]
     jmme_mbresult *out_per_ref;          // [ref][mb] or null
@@ -185,6 +187,20 @@ __device__ __forceinline__ int d_clamp(int v, int lo, int hi) { return min(max(v
 // Predictor components as the kernels use them: the host entry points refuse |pred| > JMME_MAX_PRED_QPEL, the
 // device-pointer entry points cannot look, so every load clamps (keeps se_bits sums inside the rate tables).
 __device__ __forceinline__ int d_pred(int v) { return d_clamp(v, -JMME_MAX_PRED_QPEL, JMME_MAX_PRED_QPEL); }
+
+// spiral index k (0 = centre) -> (dx, dy), the inverse of the host's spiral_index(): ring l = max(|dx|, |dy|) starts
+// at (2l-1)^2 with its top/bottom rows interleaved (x = -l+1 .. l-1), then its left/right columns (y = -l .. l).
+// Arithmetic instead of the spiral_xy table: the result write of a search kernel has no dependent global load.
+__device__ __forceinline__ void d_spiral_xy(int k, int &dx, int &dy)
+{
+    if (k == 0) { dx = dy = 0; return; }
+    int s = (int)sqrtf((float)k);
+    s -= (s * s > k);
+    s += ((s + 1) * (s + 1) <= k);
+    const int l = (s + 1) >> 1, w = 2 * l - 1, off = k - w * w;
+    if (off < 2 * w) { dx = (off >> 1) - l + 1; dy = (off & 1) ? l : -l; }
+    else { const int o2 = off - 2 * w; dy = (o2 >> 1) - l; dx = (o2 & 1) ? l : -l; }
+}
 
 // 4 absolute byte differences summed and accumulated: one VABSDIFF4.U8.ACC
 __device__ __forceinline__ unsigned sad4(unsigned a, unsigned b, unsigned c)

@@ -48,7 +48,7 @@ struct TbLayout {
         // blocks' bits * 4, padded to 24 bytes, so that a thread fetches all of them as six words
         const int tw = per_block ? (2 * ncols * 24) / 4 : (ncols + 3) / 4;
         off_by = (off_bx + tw + 1) & ~1;
-        off_kr = off_by + tw;         // rate+key of every candidate (zero predictors only)
+        off_kr = (off_by + tw + 3) & ~3;   // rate+key of every candidate (zero predictors only), 16-byte aligned
         total_words = off_kr + (kr_table ? ncols * ncols : 0);
     }
 };
@@ -147,14 +147,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         const int run = i / nseg, seg = i - run * nseg;
         s_task[i] = (uint16_t)((min(run * K, ncols - K) << 8) | (16 * seg));
     }
-    if constexpr (KRTAB) {                               // needs s_T and s_key: built after a barrier
-        __syncthreads();
-        const bool pt = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
-        for (int i = tid; i < ncand; i += NW * 32) {
-            const int yo = i / ncols, xo = i - yo * ncols;
-            const unsigned key = (pt && xo == R && yo == R) ? 0u : (unsigned)P.spiral_key[i];    // MV (0,0) pre-test
-            s_kr[i] = s_T[d_se_bits(4 * (xo - R)) + d_se_bits(4 * (yo - R))] + key;
-        }
+    if constexpr (KRTAB) {                               // the context's table (jmme_api.cu build_kr0): one copy, 16 bytes per load
+        const uint4 *src = (const uint4 *)P.kr0;
+        for (int i = tid; i < (ncand >> 2); i += NW * 32) ((uint4 *)s_kr)[i] = src[i];
+        for (int i = (ncand & ~3) + tid; i < ncand; i += NW * 32) s_kr[i] = P.kr0[i];
     }
     int res_g = l16 / wr;                                // residual task: run offset and column of this lane
     int res_x = 16 * nseg + (l16 - res_g * wr);
@@ -525,8 +521,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             const unsigned key = v & JMME_KEY_MASK;
             int mvx = 0, mvy = 0;
             if (key) {
-                mvx = cx + P.spiral_xy[2 * (key - 1)];
-                mvy = cy + P.spiral_xy[2 * (key - 1) + 1];
+                d_spiral_xy((int)key - 1, mvx, mvy);
+                mvx += cx; mvy += cy;
             }
             BlkRes r;
             r.mvx = (int16_t)(4 * mvx);
