@@ -27,6 +27,7 @@ char *jmme_kernel_name_buf()
 
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st);
 cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st);
+bool jmme_me_int_balanced(const SearchParams &P, int variant, int num_sms, bool forced);      // me_int_tb.cu
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
                                int n_planes, uint8_t *out, int y_begin, int y_end, cudaStream_t st);
 cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stride, int w16, int h16, uint8_t *dst,
@@ -87,6 +88,8 @@ struct jmme_ctx {
     uint16_t *d_spiral_key;
     int16_t *d_spiral_xy;
     uint32_t *d_kr0;                      // zero-predictor rate + key table of the context (SearchParams::kr0)
+    uint32_t *d_gbest;                    // packed minima of a balanced integer search (SearchParams::gbest), all 0xFFFFFFFF
+    bool gbest_dirty;                     // a failed search may have left words behind: cleared before the next one
     BlkRes *d_res;
     jmme_mbresult *d_out, *d_out_per_ref;
     long long launches;
@@ -136,7 +139,7 @@ void resolve_tuning(const jmme_tuning *in, jmme_tuning *out)
     jmme_tuning t;
     memset(&t, 0, sizeof t);
     if (in) t = *in;
-    if (t.group <= 0) t.group = 2;                // MBs per work item of the zero-predictor kernel
+    if (t.group < 0) t.group = 0;                 // MBs per work item of the zero-predictor kernel (0: 4 balanced, else 2)
     if (t.cluster <= 0) t.cluster = 4;            // largest cluster of a wavefront step (1 = none)
     t.pipe_parts = t.pipe_parts <= 0 ? 3 : std::min(t.pipe_parts, 4);
     *out = t;
@@ -172,7 +175,7 @@ void free_device(jmme_ctx *c)
     cudaFree(c->d_cur_c[0]); cudaFree(c->d_cur_c[1]); cudaFree(c->d_craw);
     cudaFree(c->d_planes_l1); cudaFree(c->d_raw_l1); cudaFree(c->d_bi_l0); cudaFree(c->d_bi_l1); cudaFree(c->d_bi_pred0);
     cudaFree(c->d_bi_pred1); cudaFree(c->d_bi_spiral); cudaFree(c->d_bi_out); cudaFree(c->d_bi_err);
-    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy); cudaFree(c->d_kr0);
+    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy); cudaFree(c->d_kr0); cudaFree(c->d_gbest);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave); cudaFree(c->d_wave_tab);
     free(c->wave_off);
@@ -322,6 +325,9 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
                 }
             CUC(cudaMalloc(&c->d_kr0, sizeof(uint32_t) * c->ncand));
             CUC(cudaMemcpy(c->d_kr0, kr.data(), sizeof(uint32_t) * c->ncand, cudaMemcpyHostToDevice));
+            const size_t gb = sizeof(uint32_t) * JMME_NBLK * n_mb * p->num_refs;
+            CUC(cudaMalloc(&c->d_gbest, gb));
+            CUC(cudaMemset(c->d_gbest, 0xFF, gb));
         }
         if (p->pred_policy == JMME_PRED_MEDIAN) {
             // 2:1 wavefront inside every slice: MB (x, y) of a slice that starts at row y0 is decided in step
@@ -372,7 +378,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.pred_policy = c->p.pred_policy; P.blocktype_mask = c->p.blocktype_mask;
     P.use_hadamard = c->metric[1] == JMME_DIST_HADAMARD; P.satd_round = c->p.satd_round; P.subpel = c->p.subpel;
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
-    P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy; P.kr0 = c->d_kr0;
+    P.spiral_key = c->d_spiral_key; P.spiral_xy = c->d_spiral_xy; P.kr0 = c->d_kr0; P.gbest = c->d_gbest;
     P.res = c->d_res; P.out = d_out; P.out_per_ref = d_out_per_ref;
     P.cost_domain = c->p.cost_domain; P.ext = c->ext; P.t8 = c->p.transform8x8; P.chroma_me = c->p.chroma_me;
     for (int st = 0; st < 3; st++) { P.metric[st] = c->metric[st]; P.lf[st] = c->lf[st]; }
@@ -380,7 +386,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
         for (int k = 0; k < 2; k++) P.cplanes[r][k] = c->d_cplanes[r][k];
     P.cstride = c->cstride; P.cpad = c->cpad; P.cur_c[0] = c->d_cur_c[0]; P.cur_c[1] = c->d_cur_c[1]; P.cur_cs = c->w16 / 2;
     P.tune_group = c->tune.group; P.tune_cluster = c->tune.cluster; P.tune_lin = !c->tune.table_rate;
-    P.tune_split = !c->tune.no_split; P.tune_split_pdl = !c->tune.no_split_pdl;
+    P.tune_split = c->tune.balance != 2;
 }
 
 // enqueue the whole search on `st`; nothing is synchronised here
@@ -447,8 +453,18 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         c->searched = true;
         return JMME_OK;
     }
+    // zero predictors, R = 32: balanced task ranges, packed minima in d_gbest until the next kernel consumes them
+    // (me_int_tb.cu BAL); a search that failed half-way may have left words behind
+    const bool full_pb = c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK;
+    P.int_packed = !full_pb && jmme_me_int_balanced(P, c->tune.variant, c->num_sms, c->tune.balance == 1);
+    if (P.tune_group <= 0) P.tune_group = P.int_packed ? 4 : 2;      // MBs per item: measured best per mode
+    if (P.int_packed && c->gbest_dirty) {
+        CU(c, cudaMemsetAsync(c->d_gbest, 0xFF, sizeof(uint32_t) * JMME_NBLK * (size_t)c->mb_w * c->mb_h * c->p.num_refs, st));
+        c->gbest_dirty = false;
+    }
+    if (P.int_packed) c->gbest_dirty = true;         // until every launch of this search is queued
     if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[1][0], st));
-    if (c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK)
+    if (full_pb)
         CU(c, jmme_launch_me_full(P, st));           // a window per block: nothing to share (me_full.cu)
     else
         CU(c, jmme_launch_me_int(P, c->num_sms, c->tune.variant, st));
@@ -467,6 +483,7 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[3][1], st)); c->prof_valid[3] = true; }
         c->launches++;
     }
+    c->gbest_dirty = false;
     return JMME_OK;
 }
 

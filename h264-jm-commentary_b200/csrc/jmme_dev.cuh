@@ -53,14 +53,12 @@ struct SearchParams {
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
     int tune_group, tune_cluster;        // host-side launch knobs (jmme_tuning.group / .cluster, defaults resolved)
     int tune_lin;                        // 0 (jmme_tuning.table_rate): per-block rate always from the table
-    int tune_split, tune_split_pdl;      // zero-predictor search as full rounds + a clustered tail (jmme_tuning.no_split = 0)
+    int tune_split;                      // zero-predictor search with balanced task ranges (jmme_tuning.no_balance = 0)
     int pdl;                             // wavefront steps: launch with programmatic stream serialization
-    // split launch of the zero-predictor search (me_int_tb.cu): full rounds of MB-pair items, then the remaining
-    // MBs one per cluster
-    int item_count;                      // > 0: only the first item_count items of the stripe
-    int range_first, range_count;        // range_count > 0: the items are the single MBs range_first .. (frame MB index)
-    int split_role;                      // 1: this launch has a programmatic dependent (trigger at once)
-                                         // 2: this launch is that dependent (wait for the primary before exiting)
+    // balanced task ranges of the zero-predictor search (me_int_tb.cu BAL)
+    uint32_t *gbest;                     // [ref][mb][41] packed (cost + bias) << 15 | key minima, 0xFFFFFFFF between searches
+    int int_packed;                      // 1: the integer search leaves its result in gbest (not in res); the first kernel
+                                         //    that consumes it — sub-pel, else reference selection — decodes and resets
     jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
     int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
     // ---- ABI 4: cost domain, per-stage metrics, 8x8 Hadamard, chroma ME ----
@@ -200,6 +198,20 @@ __device__ __forceinline__ void d_spiral_xy(int k, int &dx, int &dy)
     const int l = (s + 1) >> 1, w = 2 * l - 1, off = k - w * w;
     if (off < 2 * w) { dx = (off >> 1) - l + 1; dy = (off & 1) ? l : -l; }
     else { const int o2 = off - 2 * w; dy = (o2 >> 1) - l; dx = (o2 & 1) ? l : -l; }
+}
+
+// integer result of (ref, mb, block) left by a balanced search: decode the packed minimum (zero predictors: window
+// centre (0,0)) and reset the word for the next search.  One caller per word, or callers of one warp with the reset
+// issued by one of them after all have read (me_subpel.cu).
+__device__ __forceinline__ BlkRes d_unpack_int(const SearchParams &P, unsigned v)
+{
+    BlkRes r;
+    int dx = 0, dy = 0;
+    const unsigned key = v & JMME_KEY_MASK;
+    if (key) d_spiral_xy((int)key - 1, dx, dy);
+    r.mvx = (int16_t)(4 * dx); r.mvy = (int16_t)(4 * dy);
+    r.cost = (int)(v >> JMME_KEY_BITS) - (P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16));
+    return r;
 }
 
 // 4 absolute byte differences summed and accumulated: one VABSDIFF4.U8.ACC

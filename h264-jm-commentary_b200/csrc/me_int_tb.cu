@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #include <cooperative_groups.h>
 
@@ -86,7 +87,15 @@ struct Item {
 // field itself (wave.cuh) instead of reading P.pred, which it fills for the sub-pel kernel.
 // LIN (with PER_BLOCK): lambda is an integer (every !rdopt lambda is), so the rate is linear in the bits and
 // one IMAD replaces the table look-up: rate << 15 = (4 bits) * (lambda * 8192).
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL, bool WP, bool LIN>
+// BAL (with KRTAB, zero predictors): the stripe's tasks — (2R+1)^2 candidates of an MB = n_tasks runs of K x 16 — are dealt
+// out evenly: CTA c takes the task range [c G / n, (c + 1) G / n) of the G = items x NMB x n_tasks tasks, i.e. a partial
+// first item, whole items, a partial last item.  Every CTA works the same number of tasks (+-1) whatever the stripe
+// size, so there is no partial last round (1080p: 9.19 rounds of 444 CTAs used to cost 10; a 9-row stripe of an 8-GPU
+// run 1.22 rounds cost 2).  An MB whose tasks are split over CTAs gets its minima combined by atomicMin on the packed
+// (cost, key) words in global memory (P.gbest) — the same operation as inside a CTA, so the result does not depend
+// on the partition; the kernel that consumes the integer result (sub-pel or reference selection) decodes the words
+// and resets them to 0xFFFFFFFF for the next search (d_take_packed).
+template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB, int CL, bool WP, bool LIN, bool BAL>
 __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchParams P)
 {
     __shared__ WaveNb s_wnb[WP ? 10 : 1];
@@ -115,10 +124,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
     const int ppr = (P.mb_w + NM - 1) / NM;              // items per MB row
-    // a list or a range: one MB per item; item_count: the first items of the stripe only (split launch)
-    const int n_it_stripe = P.mb_list ? P.n_list
-                                      : (P.range_count ? P.range_count
-                                                       : (P.item_count ? P.item_count : (P.mb_row_end - P.mb_row_begin) * ppr));
+    const int n_it_stripe = P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ppr;   // a list: one MB per item
     const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
@@ -167,8 +173,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     auto decode_item = [&](int item, Item &it) {           // called by all threads of the CTA together
         it.ref = item / n_it_stripe;
         const int idx = item - it.ref * n_it_stripe;
-        if (P.mb_list || P.range_count) {
-            it.mb = P.mb_list ? P.mb_list[idx] : P.range_first + idx;
+        if (P.mb_list) {
+            it.mb = P.mb_list[idx];
             it.mby = it.mb / P.mb_w;
             it.mbx = it.mb - it.mby * P.mb_w;
             it.nmb = 1;
@@ -297,14 +303,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
 
     Item cur_it, nxt_it;
     int item = blockIdx.x / CL, buf = 0;
-    const int item_stride = gridDim.x / CL;
-    // split launch: the two launches work on different MBs, so the second one may fill the SMs as the CTAs of the
-    // first retire; it only must not COMPLETE before the first (the next kernel of the stream reads both results)
-    if (P.split_role == 1) pdl_trigger();
-    if (item >= n_items) {                               // (the same for every CTA of a cluster)
-        if (P.split_role == 2) pdl_wait();
-        return;
+    int item_stride = gridDim.x / CL, item_end = n_items;
+    const int TPI = n_tasks * NM;                        // tasks of an item
+    int g0 = 0, g1 = 0;                                  // BAL: this CTA's range of the stripe's tasks
+    if constexpr (BAL) {
+        const long long gt = (long long)n_items * TPI;
+        g0 = (int)(gt * blockIdx.x / gridDim.x);
+        g1 = (int)(gt * (blockIdx.x + 1) / gridDim.x);
+        if (g0 >= g1) return;
+        item = g0 / TPI; item_end = (g1 - 1) / TPI + 1; item_stride = 1;
     }
+    if (item >= item_end) return;                        // (the same for every CTA of a cluster)
     decode_item(item, cur_it);
     prefetch(cur_it, 0);
     cp_async_wait_all();
@@ -312,9 +321,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     expand(cur_it);
     __syncthreads();
 
-    for (; item < n_items; item += item_stride) {
+    for (; item < item_end; item += item_stride) {
         const int nxt = item + item_stride;
-        const bool has_next = nxt < n_items;
+        const bool has_next = nxt < item_end;
         if (has_next) {
             decode_item(nxt, nxt_it);
             prefetch(nxt_it, buf ^ 1);
@@ -323,6 +332,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         const int bonus = (cur_it.ref == 0) ? bonus_base : 0;
         const int x00 = R - cx, y00 = R - cy;
       for (int m = 0; m < cur_it.nmb; m++) {               // the MB(s) of this item, one after the other
+        int lo = 0, hi = n_tasks;                        // this CTA's tasks of the MB
+        if constexpr (BAL) {
+            lo = max(g0 - item * TPI - n_tasks * m, 0);
+            hi = min(g1 - item * TPI - n_tasks * m, n_tasks);
+            if (lo >= hi) continue;                      // (uniform over the CTA)
+        }
         const uint32_t *s_cur = s_cur2 + buf * CURW + 64 * m;
         const int wx = 16 * m;                           // window column of this MB's offset 0
         uint32_t *s_bestm = s_best + 48 * m;
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             cur[r][0] = v.x; cur[r][1] = v.y; cur[r][2] = v.z; cur[r][3] = v.w;
         }
 
-        if (bonus != 0 && warp == 0 && crank == 0) {     // 16x16 at MV (0,0) with its bonus
+        if (bonus != 0 && warp == 0 && crank == 0 && lo == 0) {     // 16x16 at MV (0,0) with its bonus (BAL: by the CTA that has task 0)
             unsigned s = 0;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -361,10 +376,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         for (int b = 0; b < NL; b++) best[b] = 0xFFFFFFFFu;
 
         // second MB: the warp that starts at task 0 (one task more than the others) rotates
-        const int t0 = (warp + NM * NW - m) % NW + (int)crank * NW;
+        const int t0 = lo + (warp + NM * NW - m) % NW + (int)crank * NW;
         constexpr int TS = NW * CL;                              // task stride
         unsigned e_next = t0 < n_main ? s_task[t0] : 0u;         // task descriptor, fetched one task ahead
-        for (int task = t0; task < n_tasks; task += TS) {
+        for (int task = t0; task < hi; task += TS) {
             int ybase, xoff;
             if (task < n_main) {
                 ybase = e_next >> 8;
@@ -514,7 +529,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             if (crank != 0 && tid < JMME_NBLK) atomicMin(cluster.map_shared_rank(&s_best[tid], 0), s_best[tid]);
             cluster.sync();
         }
-        if (crank == 0)
+        if constexpr (BAL) {                             // packed minima -> global (combined across CTAs, decoded by the consumer)
+            for (int i = tid; i < JMME_NBLK * cur_it.nmb; i += NW * 32) {
+                const int m = i / JMME_NBLK, b = i - JMME_NBLK * m;
+                const unsigned v = s_best[48 * m + b];
+                if (v != 0xFFFFFFFFu) atomicMin(P.gbest + ((size_t)cur_it.ref * n_mb + cur_it.mb + m) * JMME_NBLK + b, v);
+            }
+        } else if (crank == 0)
         for (int i = tid; i < JMME_NBLK * cur_it.nmb; i += NW * 32) {
             const int m = i / JMME_NBLK, b = i - JMME_NBLK * m;
             const unsigned v = s_best[48 * m + b];
@@ -537,29 +558,34 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
         cur_it = nxt_it;
         buf ^= 1;
     }
-    if (P.split_role == 2) pdl_wait();
 }
 
 template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB = false, int NMB = 1, int CL = 1,
-          bool WP = false, bool LIN = false>
+          bool WP = false, bool LIN = false, bool BAL = false>
 cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
 {
     TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
     size_t bytes = (size_t)L.total_words * 4;
-    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL, WP, LIN>;
+    auto kern = me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, CL, WP, LIN, BAL>;
     static KernelState ks;                               // shared-memory opt-in and occupancy, per device
     int c_occ = 0;
     cudaError_t e = jmme_kernel_occupancy(kern, ks, NW * 32, bytes, &c_occ);
     if (e != cudaSuccess) return e;
     snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN,
-             "me_int_tb_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,RS_CT=%d,KEYG=%d,KRTAB=%d,NMB=%d,CL=%d,WP=%d,LIN=%d>", K, NW, MINB,
-             (int)PER_BLOCK, RS_CT, (int)KEYG, (int)KRTAB, NMB, CL, (int)WP, (int)LIN);
-    int n_items = (P.mb_list ? P.n_list
-                             : (P.range_count ? P.range_count
-                                              : (P.item_count ? P.item_count : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)))) *
-                  P.num_refs;
+             "me_int_tb_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,RS_CT=%d,KEYG=%d,KRTAB=%d,NMB=%d,CL=%d,WP=%d,LIN=%d,BAL=%d>", K, NW, MINB,
+             (int)PER_BLOCK, RS_CT, (int)KEYG, (int)KRTAB, NMB, CL, (int)WP, (int)LIN, (int)BAL);
+    int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
     if (n_items <= 0) return cudaSuccess;
-    if (CL > 1 || P.pdl || P.split_role == 2) {
+    if (BAL) {
+        // every resident CTA slot gets an equal share of the tasks; at least 8 tasks per CTA (a tiny stripe must not
+        // pay one window staging per task)
+        const int nruns = (P.ncols + K - 1) / K, wr = P.ncols & 15, n_tasks = nruns * (P.ncols >> 4) + (nruns + 16 / wr - 1) / (16 / wr);
+        const long long gt = (long long)n_items * n_tasks * NMB;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(num_sms * c_occ, gt / 8));
+        kern<<<grid, NW * 32, bytes, st>>>(P);
+        return cudaGetLastError();
+    }
+    if (CL > 1 || P.pdl) {
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[2];
         int na = 0;
@@ -568,7 +594,7 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
             at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
             na++;
         }
-        if (P.pdl || P.split_role == 2) {
+        if (P.pdl) {
             at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[na].val.programmaticStreamSerializationAllowed = 1;
             na++;
@@ -581,62 +607,6 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
     int grid = min(n_items, num_sms * c_occ);
     kern<<<grid, NW * 32, bytes, st>>>(P);
     return cudaGetLastError();
-}
-
-// resident CTAs of an instantiation on this device (the persistent grid of launch_tb)
-template <int K, int NW, int MINB, bool PER_BLOCK, int RS_CT, bool KEYG, bool KRTAB, int NMB>
-cudaError_t tb_capacity(const SearchParams &P, int num_sms, int *cap)
-{
-    TbLayout L(P.R, PER_BLOCK, !KEYG && !KRTAB, K, KRTAB, NMB);
-    static KernelState ks;
-    int occ = 0;
-    cudaError_t e = jmme_kernel_occupancy(me_int_tb_kernel<K, NW, MINB, PER_BLOCK, RS_CT, KEYG, KRTAB, NMB, 1, false, false>, ks,
-                                          NW * 32, (size_t)L.total_words * 4, &occ);
-    *cap = num_sms * occ;
-    return e;
-}
-
-// Zero predictors, R = 32, one reference: the stripe as full rounds of items of NMBM (2 or 4) adjacent MBs on the
-// persistent grid, and the MBs that are left over (less than one round of items) one per thread-block cluster of 2 or
-// 4 CTAs, so that the last, partial round costs a fraction of an item instead of a whole one (1080p in pairs: 9.19
-// rounds cost 9.3 instead of 10; a stripe of 9 MB rows on one of 8 GPUs: 1.22 rounds cost 1.3 instead of 2).  The two
-// launches work on different MBs: the second is a programmatic dependent of the first, so its CTAs fill the SMs as
-// the first's retire (P.tune_split_pdl).
-template <int K, int NW, int MINB, int NMBM, int RSM>
-cudaError_t launch_split(const SearchParams &P0, int num_sms, cudaStream_t st)
-{
-    int cap = 0;
-    cudaError_t e = tb_capacity<K, NW, MINB, false, RSM, false, true, NMBM>(P0, num_sms, &cap);
-    if (e != cudaSuccess) return e;
-    const int rows = P0.mb_row_end - P0.mb_row_begin, ppr = (P0.mb_w + NMBM - 1) / NMBM, total = rows * ppr;
-    const int full = cap > 0 ? (total / cap) * cap : 0;          // items in full rounds
-    if (full == total) return launch_tb<K, NW, MINB, false, RSM, false, true, NMBM>(P0, num_sms, st);
-    SearchParams P = P0;
-    // first MB after the full-round items, and how many are left
-    const int first = (P0.mb_row_begin + full / ppr) * P0.mb_w + (full % ppr) * NMBM;
-    const int left = P0.mb_row_end * P0.mb_w - first;
-    const bool pdl = P0.tune_split_pdl && full > 0;
-    char main_name[JMME_KNAME_LEN] = "";
-    if (full > 0) {
-        P.item_count = full; P.split_role = pdl ? 1 : 0;
-        e = launch_tb<K, NW, MINB, false, RSM, false, true, NMBM>(P, num_sms, st);
-        if (e != cudaSuccess) return e;
-        snprintf(main_name, sizeof main_name, "%s", jmme_kernel_name_buf());
-    }
-    P.item_count = 0; P.range_first = first; P.range_count = left; P.split_role = pdl ? 2 : 0;
-    int cap1 = 0;                                                // resident CTAs of the one-MB kernel
-    e = tb_capacity<K, NW, MINB, false, 78, false, true, 1>(P0, num_sms, &cap1);
-    if (e != cudaSuccess) return e;
-    if (4 * left <= cap1) e = launch_tb<K, NW, MINB, false, 78, false, true, 1, 4>(P, num_sms, st);
-    else if (2 * left <= cap1) e = launch_tb<K, NW, MINB, false, 78, false, true, 1, 2>(P, num_sms, st);
-    else e = launch_tb<K, NW, MINB, false, 78, false, true, 1, 1>(P, num_sms, st);
-    if (full > 0) {                                              // jmme_last_kernel names both launches
-        char both[JMME_KNAME_LEN];
-        const char *lt = strchr(jmme_kernel_name_buf(), '<');
-        snprintf(both, sizeof both, "%.150s + tail %.150s", main_name, lt ? lt : "");
-        snprintf(jmme_kernel_name_buf(), JMME_KNAME_LEN, "%s", both);
-    }
-    return e;
 }
 
 }  // namespace
@@ -675,11 +645,12 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
         if (P.R == 32 && !P.pred && !KG) {                                                                     \
             const int grp = P.tune_group;                           /* MBs per item, default 2 */             \
+            if (P.int_packed) {                                     /* balanced task ranges (BAL) */           \
+                if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4, 1, false, false, true>(P, num_sms, st);  \
+                if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2, 1, false, false, true>(P, num_sms, st);   \
+                return launch_tb<KK, NWW, MB, false, 78, false, true, 1, 1, false, false, true>(P, num_sms, st);                 \
+            }                                                                                                   \
             if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4>(P, num_sms, st);            \
-            if (grp >= 4 && P.num_refs == 1 && !P.mb_list && P.tune_split)                                      \
-                return launch_split<KK, NWW, MB, 4, 126>(P, num_sms, st);                                       \
-            if (grp >= 2 && P.num_refs == 1 && !P.mb_list && P.tune_split)                                      \
-                return launch_split<KK, NWW, MB, 2, 94>(P, num_sms, st);                                        \
             if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2>(P, num_sms, st);             \
             return launch_tb<KK, NWW, MB, false, 78, false, true, 1>(P, num_sms, st);                           \
         }                                                                                                       \
@@ -694,4 +665,22 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
     TB(6, 5, 6, 2, false) TB(6, 4, 12, 1, false)
 #undef TB
     return cudaErrorInvalidValue;
+}
+
+// Does the integer search of P run with balanced task ranges and leave its result as packed minima in P.gbest
+// (SearchParams::int_packed)?  Mirrors the dispatch above and in jmme_launch_me_int: the default two-thread kernel,
+// zero predictors, R = 32, whole stripes.
+bool jmme_me_int_balanced(const SearchParams &P, int variant, int num_sms, bool forced)
+{
+    if (!P.tune_split || !P.gbest || !P.kr0) return false;
+    // measured (tools/sweep_split.py, 1080p): with two or more rounds of MB-pair items on the 3 x SMs resident CTAs the
+    // balanced ranges in groups of 4 MBs win 2-6 %; below that a CTA's extra partial item (one more window staging)
+    // costs more than the balance returns — a lone CTA on an SM runs much faster than one of three, so a short last
+    // round is cheap anyway
+    if (!forced && (long long)(P.mb_row_end - P.mb_row_begin) * ((P.mb_w + 1) / 2) * P.num_refs < 6LL * num_sms) return false;
+    if (P.metric[0] == JMME_DIST_SSE || P.cost_domain || P.R != 32 || P.pred || P.mb_list) return false;
+    if (P.blocktype_mask == JMME_MASK_16x16) return false;
+    if (variant <= 0) variant = 68;
+    const int K = variant / 10, c = variant % 10;
+    return c >= 4 && c != 9 && K <= P.ncols;
 }

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
     }
     int mvx, mvy, mn, px = 0, py = 0;
     {
-        const BlkRes r = res[b];
+        // (a balanced integer search leaves packed minima: decoded here, reset by the block's owner lane below)
+        const BlkRes r = P.int_packed ? d_unpack_int(P, P.gbest[((size_t)ref * n_mb + mb) * JMME_NBLK + b]) : res[b];
         mvx = r.mvx; mvy = r.mvy;
         mn = r.cost;
         if (P.pred) {
@@ -301,6 +302,8 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
     }
     // the lane that owns the block's top-left cell publishes the result
     const bool owner = grp == 0 && t <= 7 && cell == (c_blk_y[b] >> 2) * 4 + (c_blk_x[b] >> 2);
+    // every lane of the block (all in this warp) has read the packed word before the shuffles above
+    if (P.int_packed && owner) P.gbest[((size_t)ref * n_mb + mb) * JMME_NBLK + b] = 0xFFFFFFFFu;
     if (active && owner) {
         BlkRes r;
         r.mvx = (int16_t)mvx; r.mvy = (int16_t)mvy; r.cost = mn;
@@ -366,7 +369,14 @@ __global__ void select_ref_kernel(const SearchParams P)
     const bool on = work && ((P.blocktype_mask >> c_blk_type[b]) & 1);
     int bc = INT_MAX, br = -1, bx = 0, by = 0;
     for (int r = 0; work && r < P.num_refs; r++) {
-        BlkRes v = P.res[((size_t)r * n_mb + mb) * JMME_NBLK + b];
+        BlkRes v;
+        if (P.int_packed && !P.subpel) {                   // balanced integer search, no sub-pel kernel in between
+            uint32_t *g = P.gbest + ((size_t)r * n_mb + mb) * JMME_NBLK + b;
+            v = d_unpack_int(P, *g);
+            *g = 0xFFFFFFFFu;
+        } else {
+            v = P.res[((size_t)r * n_mb + mb) * JMME_NBLK + b];
+        }
         if (P.out_per_ref) {
             jmme_mbresult *q = P.out_per_ref + (size_t)r * n_mb + mb;
             q->mv[b][0] = on ? v.mvx : 0; q->mv[b][1] = on ? v.mvy : 0;
@@ -428,6 +438,7 @@ cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
         return P.ext ? cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3, true>, P)
                      : cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3, false>, P);
     }
+    // (the wide form on whole stripes was measured: 2.6x slower on a 9-row stripe, 2x on the frame)
     if (P.mb_list) {
         if (P.ext) me_subpel_kernel<true, 3, true><<<n_items, 384, 0, st>>>(P);
         else me_subpel_kernel<true, 3, false><<<n_items, 384, 0, st>>>(P);

@@ -235,21 +235,21 @@ int64_t jmme_launch_count(const jmme_ctx *ctx);
  * searches of the context (and to every sub-context of an n_gpus parent). */
 typedef struct jmme_tuning {
     int32_t variant;         /* integer-search kernel: 10*K + launch shape (me_int.cu / me_int_tb.cu); 0 = by range */
-    int32_t group;           /* zero-predictor items of 1, 2 or 4 adjacent MBs sharing one window; 0 = default       */
+    int32_t group;           /* zero-predictor items of 1, 2 or 4 adjacent MBs sharing one window; 0 = by mode       */
     int32_t cluster;         /* largest thread-block cluster of a wavefront step: 1, 2, 4; 0 = default (4)           */
     int32_t table_rate;      /* 1: per-block rate always from the table (no linear-rate form for integer lambda)    */
     int32_t wave_step;       /* 1: in-frame median predictors always by the separate wave_step kernel                */
     int32_t no_pdl;          /* 1: no programmatic dependent launch between the kernels of a wavefront step         */
     int32_t pipe_parts;      /* host path: the stripe is searched in this many parts on separate streams (1..4)      */
-    int32_t no_split;        /* 1: zero-predictor search as one launch (no full-rounds + clustered-tail split)       */
-    int32_t no_split_pdl;    /* 1: the tail launch of the split waits for the main launch to drain                   */
-    int32_t reserved[7];
+    int32_t balance;         /* zero-predictor search, R = 32: 0 = balanced task ranges when the stripe has two or   */
+                             /* more rounds of items, 1 = always, 2 = never (whole MB items per CTA)                 */
+    int32_t reserved[8];
 } jmme_tuning;
 int jmme_set_tuning(jmme_ctx *ctx, const jmme_tuning *t);
 int jmme_get_tuning(const jmme_ctx *ctx, jmme_tuning *t);      /* the values in effect (defaults resolved)         */
 /* Name and template arguments of the integer-search kernel the last search of this context launched, e.g.
- * "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0>" ("" before the
- * first search; the oracle returns "cpu-oracle"; a split launch names "main + tail <...>").  The parity tests assert it so that a test of a BASELINE
+ * "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0,BAL=1>" ("" before the
+ * first search; the oracle returns "cpu-oracle").  The parity tests assert it so that a test of a BASELINE
  * config provably ran the kernel the bench times. */
 const char *jmme_last_kernel(const jmme_ctx *ctx);
 /* Per-kernel device times.  jmme_set_profiling(ctx,1) makes every later set_reference / search

@@ -37,12 +37,12 @@ def oracle_threads(oracle, n):
 # regular expressions of the integer-search instantiation each BASELINE config launches by default (whole frame)
 DEFAULT_KERNELS = {
     "config1": r"me_int_kernel<K=3,NW=4,MINB=3,PER_BLOCK=0,ONLY16=1,RS_CT=0,MODE=0>$",
-    # zero predictors, R = 32: full rounds of MB-group items + the left-over MBs one per cluster (launch_split)
-    "config2": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=\d+,KEYG=0,KRTAB=1,NMB=[24],CL=1,WP=0,LIN=0> \+ tail "
-               r"<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=78,KEYG=0,KRTAB=1,NMB=1,CL=[124],WP=0,LIN=0>$",
+    # zero predictors, R = 32: whole MB-pair items while a launch has less than two rounds of them (720p through the host
+    # path: three parts of 15 MB rows), else balanced task ranges over items of 4 MBs (BAL)
+    "config2": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0,BAL=0>$",
+    "config3": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=126,KEYG=0,KRTAB=1,NMB=4,CL=1,WP=0,LIN=0,BAL=1>$",
     "config4": r"me_int_kernel<K=5,NW=8,MINB=1,PER_BLOCK=0,ONLY16=0,RS_CT=144,MODE=0>$",
 }
-DEFAULT_KERNELS["config3"] = DEFAULT_KERNELS["config2"]
 
 
 def assert_default_kernel(prefix):
@@ -364,25 +364,31 @@ def test_default_kernels_of_the_baseline_configs(cuda):
         assert re.match(pat, LAST["kernel"]), (w, h, R, LAST)
 
 
-@pytest.mark.parametrize("tuning", [dict(no_split=1), dict(no_split_pdl=1), dict(group=4), dict(group=4, no_split_pdl=1),
-                                    dict(group=1)])
-@pytest.mark.parametrize("w,h,rows", [(1920, 1080, None), (1920, 1080, (0, 9)), (1920, 1080, (59, 68)), (1280, 720, None),
-                                      (336, 64, None), (80, 48, None)])
-def test_split_launch_shapes_reproduce_the_single_launch(cuda, oracle, tuning, w, h, rows):
-    """The zero-predictor search as full rounds of MB-group items plus a clustered tail (launch_split), with and
-    without the programmatic dependent launch, in groups of 2 and 4, on whole frames, on the stripes an 8-GPU run
-    gives a rank, and on frames smaller than one round: every shape gives the field of the plain single launch
-    (and small frames are checked against the oracle)."""
+@pytest.mark.parametrize("tuning", [dict(balance=1), dict(balance=1, group=2), dict(balance=1, group=1), dict(balance=1, variant=65), dict(balance=1, variant=48)])
+@pytest.mark.parametrize("w,h,rows,nref,subpel", [(1920, 1080, None, 1, 1), (1920, 1080, (0, 9), 1, 1), (1920, 1080, (59, 68), 1, 0),
+                                                  (1280, 720, None, 2, 0), (1288, 728, None, 1, 1), (336, 64, None, 2, 1),
+                                                  (80, 48, None, 1, 1), (16, 16, None, 1, 0)])
+def test_balanced_task_ranges_reproduce_whole_items(cuda, oracle, tuning, w, h, rows, nref, subpel):
+    """The zero-predictor search with balanced task ranges (me_int_tb.cu BAL: every CTA takes an equal range of the
+    stripe's tasks, MBs split over CTAs meet in global memory, the consuming kernel decodes) in groups of 1, 2 and 4
+    MBs and other CTA shapes, with one and two references, with the sub-pel kernel or the reference selection as
+    the consumer, on whole frames (odd MB counts too), on the stripes an 8-GPU run gives a rank and on frames much
+    smaller than the grid: every shape gives the field of the whole-item launch (balance = 2), twice in a row (the
+    consumer resets the packed words), and small frames are checked against the oracle."""
     R = 32
-    cur, refs = synth.frame_pair(w, h, seed=6, search_range=R)
-    kw = dict(search_range=R, qp=28, subpel=1)
+    cur, refs = synth.frame_pair(w, h, seed=6, search_range=R, num_refs=nref)
+    kw = dict(search_range=R, qp=28, subpel=subpel)
     if rows:
         kw.update(mb_row_begin=rows[0], mb_row_end=rows[1])
-    ref = run(cuda, cur, refs, tuning=dict(no_split=1, group=2), **kw)
-    got = run(cuda, cur, refs, tuning=tuning, **kw)
-    assert got.tobytes() == ref.tobytes(), (tuning, LAST)
-    got2 = run(cuda, cur, refs, **kw)                              # the default
-    assert got2.tobytes() == ref.tobytes(), LAST
+    ref = run(cuda, cur, refs, tuning=dict(balance=2, group=2), **kw)
+    assert "BAL=0" in LAST["kernel"], LAST
+    with cuda.context(width=w, height=h, num_refs=nref, tuning=tuning, **kw) as ctx:
+        for i, r in enumerate(refs):
+            ctx.set_reference(i, r)
+        for rep in range(2):
+            got = ctx.search_frame(cur)
+            assert "BAL=1" in ctx.last_kernel(), ctx.last_kernel()
+            assert got.tobytes() == ref.tobytes(), (tuning, rep, ctx.last_kernel())
     if w * h <= 336 * 64:
         assert_same(got, run(oracle, cur, refs, **kw), f"{w}x{h} {tuning}")
 

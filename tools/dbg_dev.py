@@ -13,7 +13,7 @@ cur, refs = synth.frame_pair(w, h, seed=1, search_range=R)
 with orc.context(width=w, height=h, search_range=R, qp=28, subpel=0) as c:
     c.set_reference(0, refs[0]); o = c.search_frame(cur)
 dcur, dref = torch.from_numpy(cur).cuda(), torch.from_numpy(refs[0]).cuda()
-for tn in (dict(), dict(no_split=1), dict(group=1, no_split=1)):
+for tn in (dict(), dict(balance=2), dict(group=1, balance=2)):
     ds = DeviceSearch(lib, width=w, height=h, search_range=R, qp=28, subpel=0, tuning=tn)
     ds.set_reference(0, dref); torch.cuda.synchronize()
     for rep in range(2):

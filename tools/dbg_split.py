@@ -18,7 +18,7 @@ for (w, h, seed) in ((1920, 1080, 1), (1280, 720, 1), (1280, 720, 6)):
     cur, refs = synth.frame_pair(w, h, seed=seed, search_range=R)
     for subpel in (0,):
         o, _ = run(orc, cur, refs, w, h, subpel=subpel)
-        tns = [dict()] + ([dict(no_split=1), dict(group=1)] if len(sys.argv) <= 1 else [])
+        tns = [dict()] + ([dict(balance=2), dict(group=1)] if len(sys.argv) <= 1 else [])
         for tn in tns:
             g, k = run(lib, cur, refs, w, h, tn, subpel=subpel)
             bad = np.nonzero(np.any(g["cost"] != o["cost"], axis=1))[0]
