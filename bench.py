@@ -410,13 +410,16 @@ def run_ours(args, rank, world, local_rank):
     # NVLink into symmetric memory (default) or by one in-place NCCL all-gather (--gather nccl)
     gather, gather_mode = None, "none (1 rank)"
     fused = False
-    if world > 1 and args.gather in ("p2p", "p2p-push"):
+    if world > 1 and args.gather in ("p2p", "p2p-peer", "p2p-push"):
         try:
             gather = PeerPushGather(mb_w, mb_h, "cuda", unit=slice_unit(args, mb_h))
-            fused = args.gather == "p2p"
+            fused = args.gather in ("p2p", "p2p-peer")
             if fused:
-                gather.attach(ds)
-                gather_mode = ("peer stores into symmetric memory from the kernels that write the records "
+                gather.attach(ds, multicast=args.gather == "p2p")
+                gather_mode = ("one multimem.st per record word through the NVLS multicast mapping of the symmetric field, from "
+                               "the kernels that write the records (jmme_set_multicast_field_dev) + symm-mem barriers"
+                               if gather.mode == "multicast" else
+                               "peer stores into symmetric memory from the kernels that write the records "
                                "(jmme_set_peer_fields_dev) + symm-mem barriers")
             else:
                 gather_mode = "peer stores into symmetric memory (jmme_push_stripe_dev) + symm-mem barrier"
@@ -666,9 +669,10 @@ def main():
     ap.add_argument("--parity-seconds", type=float, default=20.0,
                     help="CPU time budget of the oracle comparison (whole frame if it fits, else spread rows)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-push", "nccl"],
-                    help="N > 1: how the MV field is gathered: peer stores from the search kernels (p2p), from a "
-                         "separate push kernel (p2p-push), or one NCCL all-gather")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-peer", "p2p-push", "nccl"],
+                    help="N > 1: how the MV field is gathered: stores from the search kernels through the NVLS multicast "
+                         "mapping (p2p; peer stores when there is none), peer stores from the search kernels (p2p-peer), "
+                         "from a separate push kernel (p2p-push), or one NCCL all-gather")
     ap.add_argument("--watchdog", type=float, default=300.0, help="hard exit after this many seconds")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

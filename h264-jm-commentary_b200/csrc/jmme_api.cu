@@ -110,6 +110,7 @@ struct jmme_ctx {
     bool searched;                        // d_pred holds the predictors of a finished median search
     void *peer_fields[JMME_MAX_GPUS];     // jmme_set_peer_fields_dev
     int n_peer_fields;
+    void *mc_field;                       // jmme_set_multicast_field_dev
     bool dev_call;                        // inside jmme_search_frame_dev (the fused gather applies to that call only)
 };
 
@@ -416,7 +417,8 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     fill_search_params(c, P, cur, cs, d_pred, d_out, d_out_per_ref);
     P.cur_h = cur_h;
     P.fused_select = c->p.num_refs == 1 && c->p.subpel;
-    for (int i = 0; c->dev_call && i < c->n_peer_fields; i++)          // fused gather (jmme_set_peer_fields_dev)
+    if (c->dev_call && c->mc_field) { P.mc_out = (jmme_mbresult *)c->mc_field; P.n_peer_out = -1; }   // multicast gather
+    for (int i = 0; c->dev_call && !c->mc_field && i < c->n_peer_fields; i++)          // fused gather (jmme_set_peer_fields_dev)
         if (c->peer_fields[i] && c->peer_fields[i] != (void *)d_out) P.peer_out[P.n_peer_out++] = (jmme_mbresult *)c->peer_fields[i];
     if (rb >= 0) { P.mb_row_begin = rb; P.mb_row_end = re; }
     c->prof_valid[1] = c->prof_valid[2] = c->prof_valid[3] = false;
@@ -993,6 +995,14 @@ int jmme_set_peer_fields_dev(jmme_ctx *c, void *const *d_peers, int n_peers)
     if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
     for (int i = 0; i < n_peers; i++) c->peer_fields[i] = d_peers[i];
     c->n_peer_fields = n_peers;
+    return JMME_OK;
+}
+
+int jmme_set_multicast_field_dev(jmme_ctx *c, void *d_field_multicast)
+{
+    if (!c) return JMME_ERR_PARAM;
+    if (c->n_sub) return fail(c, JMME_ERR_UNSUPPORTED, "device-pointer calls need a single-device context");
+    c->mc_field = d_field_multicast;
     return JMME_OK;
 }
 

@@ -61,6 +61,8 @@ struct SearchParams {
                                          //    that consumes it — sub-pel, else reference selection — decodes and resets
     jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
     int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
+    jmme_mbresult *mc_out;               // non-null (then n_peer_out = -1: "fused gather on", no peer list): one multimem.st per
+                                         //               word through this NVLS multicast mapping reaches every rank's field
     // ---- ABI 4: cost domain, per-stage metrics, 8x8 Hadamard, chroma ME ----
     int cost_domain;                     // 0: D + (lf*bits >> 16)   1: (D << 5) + lf*bits
     int metric[3], lf[3];                // JMME_DIST_* and lambda factor of the integer / half-pel / quarter-pel stage
@@ -83,6 +85,8 @@ __device__ __forceinline__ void push_records(const SearchParams &P, int n_rec, F
         const int rec = j / RW, w = j - rec * RW, mb = mb_of(rec);
         if (mb < 0) continue;
         const uint32_t v = __ldcg((const uint32_t *)(P.out + mb) + w);
+        if (P.mc_out)                                      // the switch replicates the store to every rank
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"((uint32_t *)(P.mc_out + mb) + w), "r"(v) : "memory");
         for (int p = 0; p < P.n_peer_out; p++) ((uint32_t *)(P.peer_out[p] + mb))[w] = v;
     }
 }

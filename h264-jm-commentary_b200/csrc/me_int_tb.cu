@@ -128,15 +128,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
-    if (!KEYG && !KRTAB) {                               // 8 keys per load: one round trip instead of ncand / threads
-        const uint4 *src = (const uint4 *)P.spiral_key;
-        for (int i = tid; i < (ncand >> 3); i += NW * 32) ((uint4 *)s_key)[i] = src[i];
-        for (int i = (ncand & ~7) + tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
-    }
     const int bonus_base = P.rdopt ? 0 : d_weighted_cost(P.lambda_factor, 16);
     const unsigned bias = (unsigned)bonus_base;          // keeps (cost + bias) >= 0
-    for (int i = tid; i < JMME_NT; i += NW * 32)
-        s_T[i] = ((unsigned)d_weighted_cost(P.lambda_factor, i) + bias) << JMME_KEY_BITS;
     const bool pretest = (!P.rdopt) && P.search_mode == JMME_SEARCH_FASTFULL;
     int patched = -1;
 
@@ -149,15 +142,27 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int G = 16 / wr;
     const int n_main = nruns * nseg;
     const int n_tasks = n_main + (nruns + G - 1) / G;
-    for (int i = tid; i < n_main; i += NW * 32) {
-        const int run = i / nseg, seg = i - run * nseg;
-        s_task[i] = (uint16_t)((min(run * K, ncols - K) << 8) | (16 * seg));
-    }
-    if constexpr (KRTAB) {                               // the context's table (jmme_api.cu build_kr0): one copy, 16 bytes per load
-        const uint4 *src = (const uint4 *)P.kr0;
-        for (int i = tid; i < (ncand >> 2); i += NW * 32) ((uint4 *)s_kr)[i] = src[i];
-        for (int i = (ncand & ~3) + tid; i < ncand; i += NW * 32) s_kr[i] = P.kr0[i];
-    }
+    // the constant tables of the CTA (first read behind the barrier that follows the first prefetch): built while the
+    // first window is on its way, except in a wavefront step (WP), where they overlap the previous step's kernel
+    auto build_tables = [&]() {
+        if (!KEYG && !KRTAB) {                           // 8 keys per load: one round trip instead of ncand / threads
+            const uint4 *src = (const uint4 *)P.spiral_key;
+            for (int i = tid; i < (ncand >> 3); i += NW * 32) ((uint4 *)s_key)[i] = src[i];
+            for (int i = (ncand & ~7) + tid; i < ncand; i += NW * 32) s_key[i] = P.spiral_key[i];
+        }
+        for (int i = tid; i < JMME_NT; i += NW * 32)
+            s_T[i] = ((unsigned)d_weighted_cost(P.lambda_factor, i) + bias) << JMME_KEY_BITS;
+        for (int i = tid; i < n_main; i += NW * 32) {
+            const int run = i / nseg, seg = i - run * nseg;
+            s_task[i] = (uint16_t)((min(run * K, ncols - K) << 8) | (16 * seg));
+        }
+        if constexpr (KRTAB) {                           // the context's table (jmme_api.cu): one copy, 16 bytes per load
+            const uint4 *src = (const uint4 *)P.kr0;
+            for (int i = tid; i < (ncand >> 2); i += NW * 32) ((uint4 *)s_kr)[i] = src[i];
+            for (int i = (ncand & ~3) + tid; i < ncand; i += NW * 32) s_kr[i] = P.kr0[i];
+        }
+    };
+    if constexpr (WP) build_tables();
     int res_g = l16 / wr;                                // residual task: run offset and column of this lane
     int res_x = 16 * nseg + (l16 - res_g * wr);
     if (res_g >= G) { res_g = 0; res_x = 16 * nseg; }    // idle lanes repeat lane 0 (idempotent)
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     if (item >= item_end) return;                        // (the same for every CTA of a cluster)
     decode_item(item, cur_it);
     prefetch(cur_it, 0);
+    if constexpr (!WP) build_tables();
     cp_async_wait_all();
     __syncthreads();
     expand(cur_it);

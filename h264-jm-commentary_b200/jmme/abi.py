@@ -68,7 +68,7 @@ EXPORTS = [
     "jmme_default_params", "jmme_create", "jmme_destroy", "jmme_strerror", "jmme_last_error", "jmme_backend",
     "jmme_abi_version", "jmme_mb_width", "jmme_mb_height", "jmme_pad", "jmme_lambda_factor_of",
     "jmme_lambda_factor", "jmme_set_reference_l1", "jmme_search_frame_bipred", "jmme_set_reference", "jmme_set_reference_chroma", "jmme_set_current_chroma", "jmme_search_frame", "jmme_get_predictors", "jmme_get_subimage",
-    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_set_reference_chroma_dev", "jmme_set_current_chroma_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev",
+    "jmme_set_reference_dev", "jmme_search_frame_dev", "jmme_set_reference_chroma_dev", "jmme_set_current_chroma_dev", "jmme_push_stripe_dev", "jmme_set_peer_fields_dev", "jmme_set_multicast_field_dev",
     "jmme_launch_count", "jmme_set_tuning", "jmme_get_tuning", "jmme_last_kernel",
     "jmme_set_profiling",
     "jmme_get_kernel_times", "jmme_InitMotionSearchModule", "jmme_SetMotionVectorPredictor",
@@ -123,6 +123,7 @@ class Lib:
             "jmme_set_current_chroma_dev": (i32, [vp, vp, vp, i32, vp]),
             "jmme_push_stripe_dev": (i32, [vp, vp, C.POINTER(vp), i32, vp]),
             "jmme_set_peer_fields_dev": (i32, [vp, C.POINTER(vp), i32]),
+            "jmme_set_multicast_field_dev": (i32, [vp, vp]),
             "jmme_launch_count": (C.c_longlong, [vp]),
             "jmme_set_tuning": (i32, [vp, C.POINTER(Tuning)]),
             "jmme_get_tuning": (i32, [vp, C.POINTER(Tuning)]),

@@ -78,10 +78,16 @@ class PeerPushGather:
         return self.frame()
 
     # ---- fused variant: the search kernels store their records into the peers' fields themselves ----------
-    def attach(self, search):
+    def attach(self, search, multicast=True):
         """Every later search of `search` (with out=self.field) also writes its records into all peers' fields
         (jmme_set_peer_fields_dev): no push kernel; bracket the search with pre() and post()."""
-        search.set_peer_fields(self.peer_ptrs)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if mc and multicast:
+            search.set_multicast_field(mc)     # one multimem.st per word, replicated by the NVSwitch
+            self.mode = "multicast"
+        else:
+            search.set_peer_fields(self.peer_ptrs)
+            self.mode = "peer stores"
 
     def pre(self):
         self.hdl.barrier(channel=0)            # peers are done reading the previous field

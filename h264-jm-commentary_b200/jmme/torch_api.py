@@ -73,6 +73,11 @@ class DeviceSearch:
         arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
         self.lib.check(self.lib.dll.jmme_set_peer_fields_dev(self.ctx.handle, arr, len(peer_ptrs)), self.ctx.handle)
 
+    def set_multicast_field(self, mc_ptr):
+        """Every later search stores its records once through the NVLS multicast mapping `mc_ptr` of the symmetric
+        field (they land in every rank's field); 0 / None turns it off."""
+        self.lib.check(self.lib.dll.jmme_set_multicast_field_dev(self.ctx.handle, C.c_void_p(int(mc_ptr or 0))), self.ctx.handle)
+
     def stripe_rows(self):
         return self.ctx.params.mb_row_begin, (self.ctx.params.mb_row_end or self.ctx.mb_h)
 

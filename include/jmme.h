@@ -226,6 +226,12 @@ int jmme_push_stripe_dev(jmme_ctx *ctx, const void *d_field_local, void *const *
  * cross-rank barriers: before the search (the peers have finished reading the previous field) and after it
  * (every stripe has landed everywhere). */
 int jmme_set_peer_fields_dev(jmme_ctx *ctx, void *const *d_field_peers, int n_peers);
+/* The fused gather through an NVLS multicast mapping: d_field_multicast is the multicast address of the symmetric
+ * field the searches of every rank write into (e.g. torch.distributed._symmetric_memory: handle.multicast_ptr).  Every
+ * record is then stored ONCE with multimem.st and the NVSwitch delivers it to the field of every rank (its own
+ * included), instead of one peer store per rank; takes precedence over jmme_set_peer_fields_dev.  NULL turns it off.
+ * The caller provides the same two cross-rank barriers. */
+int jmme_set_multicast_field_dev(jmme_ctx *ctx, void *d_field_multicast);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 int64_t jmme_launch_count(const jmme_ctx *ctx);
 

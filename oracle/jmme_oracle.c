@@ -479,6 +479,11 @@ int jmme_set_peer_fields_dev(jmme_ctx *c, void *const *p, int n)
     (void)p; (void)n;
     return set_err(c, JMME_ERR_UNSUPPORTED, "device pointers: CUDA library only");
 }
+int jmme_set_multicast_field_dev(jmme_ctx *c, void *p)
+{
+    (void)p;
+    return c ? JMME_ERR_UNSUPPORTED : JMME_ERR_PARAM;
+}
 int jmme_push_stripe_dev(jmme_ctx *c, const void *l, void *const *p, int n, void *st)
 { (void)l; (void)p; (void)n; (void)st; return set_err(c, JMME_ERR_UNSUPPORTED, "oracle has no device path"); }
 int64_t jmme_launch_count(const jmme_ctx *c) { (void)c; return 0; }
