@@ -302,7 +302,7 @@ def _watchdog(seconds):
     t.start()
 
 
-def oracle_parity(args, fields):
+def oracle_parity(args, fields, search_mode=0):
     """Parity guard of the bench line: the field the GPU produced for every seed against the CPU oracle (all host
     threads, not timed).  Whole frame when the oracle needs about `--parity-seconds` or less for it, else MB rows
     spread over the frame (first, last and evenly in between, whole slices under the median policy).
@@ -316,7 +316,8 @@ def oracle_parity(args, fields):
     w, h, R, refs, subpel, mask = WORKLOADS[args.workload]
     mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
     unit = slice_unit(args, mb_h)
-    kw = dict(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP, **policy_kw(args))
+    kw = dict(width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP, search_mode=search_mode,
+              **policy_kw(args))
 
     def rows_of(seed, spans, timing=None):
         """oracle records of the MB-row spans [(rb, re)] of the frame pair of `seed` (one context per span: the stripe
@@ -367,6 +368,73 @@ def oracle_parity(args, fields):
     if mism:
         raise SystemExit(f"bench.py: GPU field differs from the oracle: {json.dumps(par)}")
     return par
+
+
+EXTRAS = [
+    # (workload, --pred-policy, --slice-rows, timed steps): the other BASELINE configs and the in-frame median policy,
+    # measured in the default N = 1 run after the headline so that the driver's record holds them too
+    ("cif_r16_16x16_int_1ref", "zero", 1, 10),
+    ("720p_r32_41blk_int_1ref", "zero", 1, 10),
+    ("1080p_r64_41blk_int_4ref", "zero", 1, 5),
+    ("2160p_r64_41blk_qpel_4ref", "zero", 1, 3),
+    ("1080p_r32_41blk_qpel_1ref", "median", 1, 5),
+]
+
+
+def measure_extra(args, lib, name, policy, slice_rows, steps, mix_peak, flush):
+    """One short device-resident measurement of another workload (whole frame on this GPU): `steps` timed steps of
+    set_reference + search with the L2 flushed in between, CUDA events per step; the field of the last step against
+    the oracle on MB rows spread over the frame (whole frame when the oracle does it in a few seconds)."""
+    import torch
+    from jmme import synth
+    from jmme.torch_api import DeviceSearch
+    a = argparse.Namespace(**vars(args))
+    a.workload, a.pred_policy, a.slice_rows, a.parity_seconds = name, policy, slice_rows, args.extra_parity_seconds
+    w, h, R, refs, subpel, mask = WORKLOADS[name]
+    mb_h, mb_w = (h + 15) // 16, (w + 15) // 16
+    cur, ref_l = synth.frame_pair(w, h, seed=SEEDS[0], search_range=R, num_refs=refs)
+    d_cur, d_refs = torch.from_numpy(cur).cuda(), [torch.from_numpy(r).cuda() for r in ref_l]
+    mode = 1 if mask == 0x02 else 0                                   # config 1: FullPelBlockMotionSearch (search_mode FULL)
+    ds = DeviceSearch(lib, width=w, height=h, search_range=R, num_refs=refs, subpel=subpel, blocktype_mask=mask, qp=QP,
+                      search_mode=mode, **policy_kw(a))
+    try:
+        def step():
+            for i, r in enumerate(d_refs):
+                ds.set_reference(i, r)
+            return ds.search(d_cur)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ms = []
+        for s in range(steps):
+            flush.fill_(s & 255)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        ms_step = float(np.mean(ms))
+        ds.ctx.set_profiling(True)
+        step()
+        torch.cuda.synchronize()
+        kt = ds.ctx.kernel_times()
+        field = ds.to_numpy(out).copy()
+        n_mb = mb_h * mb_w
+        ncand = (2 * R + 1) ** 2
+        ops = n_mb * refs * ncand * (OPS_PER_CAND_16 if mask == 0x02 else OPS_PER_CAND_41)
+        wave = policy == "median"
+        k_int = (ms_step - kt["interp"] * refs) if wave else kt["me_int"]
+        res = {"config": config_of(a), "value": n_mb / (ms_step * 1e-3), "unit": "MB/s", "ms_per_step": ms_step, "steps": steps,
+               "kernel_ms": {"interp": kt["interp"], "me_int": k_int, "me_subpel": kt["me_subpel"], "select_ref": kt["select"]},
+               "kernel_instance": ds.ctx.last_kernel(),
+               "roofline_frac": ops / (max(k_int, 1e-9) * 1e-3) * 1e-12 / mix_peak}
+        if not args.no_parity:
+            a.search_mode = mode
+            res["parity"] = oracle_parity(a, {SEEDS[0]: field}, search_mode=mode)
+        return res
+    finally:
+        ds.close()
 
 
 def run_ours(args, rank, world, local_rank):
@@ -634,6 +702,19 @@ def run_ours(args, rank, world, local_rank):
             line["parity"] = oracle_parity(args, fields)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
+        if world == 1 and headline and not args.no_extras:
+            graph = run_step = None                       # the headline's contexts and graph make room first
+            hctx.close()
+            ds.close()
+            extras = []
+            for name, policy, srows, steps in EXTRAS:
+                try:
+                    extras.append(measure_extra(args, lib, name, policy, srows, steps, peaks["mix_peak"], flush))
+                except SystemExit:
+                    raise
+                except Exception as e:  # noqa: BLE001
+                    extras.append({"config": {"workload": name, "pred_policy": policy}, "error": f"{type(e).__name__}: {e}"})
+            line["other_workloads"] = extras
         print(json.dumps(line), flush=True)
     # Orderly exit through the interpreter (the driver records the loaded .so files at exit).  A captured graph
     # holds the step's kernels (and NCCL / symmetric-memory work): it goes first, then the contexts, every rank
@@ -668,6 +749,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed steps' output")
     ap.add_argument("--parity-seconds", type=float, default=20.0,
                     help="CPU time budget of the oracle comparison (whole frame if it fits, else spread rows)")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the short measurements of the other BASELINE configs")
+    ap.add_argument("--extra-parity-seconds", type=float, default=6.0, help="oracle time budget per extra workload")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-peer", "p2p-push", "nccl"],
                     help="N > 1: how the MV field is gathered: stores from the search kernels through the NVLS multicast "
