@@ -57,6 +57,7 @@ cudaError_t jmme_launch_push(const uint32_t *src, uint32_t *const *dst, int n_ds
 struct jmme_ctx {
     jmme_params p;
     int w16, h16, mb_w, mb_h, pad, pstride, pheight, lambda_factor, n_planes, ncols, ncand;
+    int max_pred, cmax;                   // |pred| limit of the host entry points; limit of the window centre (samples)
     int device, num_sms;
     int metric[3], lf[3], ext;            // per-stage JMME_DIST_* / lambda factor in the context's cost domain; ext: general kernels
     int cpad, cstride, cheight;           // chroma ME: padded integer chroma planes (w16/2 + 2 cpad) x (h16/2 + 2 cpad)
@@ -132,7 +133,9 @@ int fail(jmme_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
         if (e_ != cudaSuccess) return fail(c, JMME_ERR_CUDA, #call, e_);   \
     } while (0)
 
-int pad_for(int R) { return (2 * R + 16 + 15) & ~15; }
+// replication border: the window centre moves up to cmax samples from the MB, the window R more, 16 for the MB and
+// the sub-pel / 6-tap margin (cmax = R unless jm_center lets the centre follow the predictor)
+int pad_for(int R, int cmax) { return (cmax + R + 16 + 15) & ~15; }
 
 // jmme_tuning with every 0 replaced by the measured default
 void resolve_tuning(const jmme_tuning *in, jmme_tuning *out)
@@ -201,7 +204,8 @@ int validate(const jmme_params *p)
         p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 3 || p->satd_round < 0 ||
         p->satd_round > 1 || p->n_gpus < 0 || p->n_gpus > JMME_MAX_GPUS || p->slice_rows < 0 || p->cost_domain < 0 ||
         p->cost_domain > 1 || p->me_distortion < 0 || p->me_distortion > 1 || p->transform8x8 < 0 || p->transform8x8 > 1 ||
-        p->chroma_me < 0 || p->chroma_me > 1)
+        p->chroma_me < 0 || p->chroma_me > 1 || p->jm_center < 0 || p->jm_center > 1 ||
+        (p->max_pred_qpel && (p->max_pred_qpel < 4 || p->max_pred_qpel > JMME_MAX_PRED_QPEL)))
         return JMME_ERR_PARAM;
     if (p->me_distortion &&
         (p->me_distortion_fpel < 0 || p->me_distortion_fpel > 2 || p->me_distortion_hpel < 0 || p->me_distortion_hpel > 2 ||
@@ -230,7 +234,10 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         const int k = p->slice_rows ? p->slice_rows : c->mb_h;
         if (c->p.mb_row_begin % k || (c->p.mb_row_end % k && c->p.mb_row_end != c->mb_h)) { delete c; return JMME_ERR_PARAM; }
     }
-    c->pad = pad_for(p->search_range);
+    c->max_pred = p->max_pred_qpel ? p->max_pred_qpel : JMME_MAX_PRED_QPEL;
+    // centre limit: +-R, or (JM: rdopt = 1 does not clamp) as far as the largest accepted predictor reaches
+    c->cmax = std::max((p->jm_center && p->rdopt) ? c->max_pred / 4 : p->search_range, p->search_range);
+    c->pad = pad_for(p->search_range, c->cmax);
     c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
     {
         // per-stage metric and lambda factor: an SSE stage works with lambda^2; cost domain 1 scales
@@ -375,7 +382,7 @@ void fill_search_params(const jmme_ctx *c, SearchParams &P, const uint8_t *cur, 
     P.pstride = c->pstride; P.pheight = c->pheight; P.pad = c->pad;
     P.mb_w = c->mb_w; P.mb_h = c->mb_h; P.mb_row_begin = c->p.mb_row_begin; P.mb_row_end = c->p.mb_row_end;
     P.R = c->p.search_range; P.ncols = c->ncols; P.num_refs = c->p.num_refs;
-    P.lambda_factor = c->lambda_factor; P.rdopt = c->p.rdopt; P.search_mode = c->p.search_mode;
+    P.lambda_factor = c->lambda_factor; P.rdopt = c->p.rdopt; P.search_mode = c->p.search_mode; P.cmax = c->cmax;
     P.pred_policy = c->p.pred_policy; P.blocktype_mask = c->p.blocktype_mask;
     P.use_hadamard = c->metric[1] == JMME_DIST_HADAMARD; P.satd_round = c->p.satd_round; P.subpel = c->p.subpel;
     P.pred = c->p.pred_policy == JMME_PRED_ZERO ? nullptr : d_pred;
@@ -539,7 +546,7 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
         c->n_sub++;
     }
     jmme_ctx *s0 = c->sub[0];
-    c->w16 = s0->w16; c->h16 = s0->h16; c->mb_w = s0->mb_w; c->mb_h = s0->mb_h; c->pad = s0->pad;
+    c->w16 = s0->w16; c->h16 = s0->h16; c->mb_w = s0->mb_w; c->mb_h = s0->mb_h; c->pad = s0->pad; c->max_pred = s0->max_pred; c->cmax = s0->cmax;
     c->pstride = s0->pstride; c->pheight = s0->pheight; c->lambda_factor = s0->lambda_factor;
     c->p.mb_row_begin = rb; c->p.mb_row_end = re;
     for (int g = 1; g < c->n_sub; g++) {         // NVLink peer access towards the gathering device
@@ -802,7 +809,7 @@ int jmme_search_frame_bipred(jmme_ctx *c, const uint8_t *cur, int stride, const 
         for (int r = 0; pr && r < (k ? 1 : c->p.num_refs); r++) {
             const int16_t *q = pr + ((size_t)r * n_mb + off) * npb * 2;
             for (size_t i = 0; i < cnt * npb * 2; i++)
-                if (q[i] > JMME_MAX_PRED_QPEL || q[i] < -JMME_MAX_PRED_QPEL) return fail(c, JMME_ERR_PARAM, "pred out of range");
+                if (q[i] > c->max_pred || q[i] < -c->max_pred) return fail(c, JMME_ERR_PARAM, "pred out of range");
         }
     }
     // spiral of the refinement range
@@ -1044,7 +1051,7 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
             const int16_t *q = pred + ((size_t)r * n_mb + (size_t)c->p.mb_row_begin * c->mb_w) * per_mb;
             const size_t n = (size_t)(c->p.mb_row_end - c->p.mb_row_begin) * c->mb_w * per_mb;
             for (size_t i = 0; i < n; i++)
-                if (q[i] > JMME_MAX_PRED_QPEL || q[i] < -JMME_MAX_PRED_QPEL) return fail(c, JMME_ERR_PARAM, "pred out of range");
+                if (q[i] > c->max_pred || q[i] < -c->max_pred) return fail(c, JMME_ERR_PARAM, "pred out of range");
         }
     auto upload_pred = [&](jmme_ctx *s, cudaStream_t st) -> cudaError_t {      // the stripe rows of every reference
         for (int r = 0; pred && r < c->p.num_refs; r++) {

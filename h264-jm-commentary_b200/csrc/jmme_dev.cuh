@@ -51,6 +51,7 @@ struct SearchParams {
     int8_t *field_ref;                   //           MB to the 4x4-granular field [4 mb_h][4 mb_w]([2])
     const WaveTab *wave_tab;             // non-null: the search kernel predicts its MB's 41 vectors itself from the
     int slice_rows;                      //           field (and writes them to `pred`) instead of reading `pred`
+    int cmax;                            // the window centre pred/4 is limited to +-cmax samples (R, or jm_center: max_pred/4)
     int tune_group, tune_cluster;        // host-side launch knobs (jmme_tuning.group / .cluster, defaults resolved)
     int tune_lin;                        // 0 (jmme_tuning.table_rate): per-block rate always from the table
     int tune_split;                      // zero-predictor search with balanced task ranges (jmme_tuning.no_balance = 0)

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
         if (!((P.blocktype_mask >> c_blk_type[b]) & 1)) continue;
         const int bx = c_blk_x[b], by = c_blk_y[b], bw4 = c_blk_w[b] >> 2, bh = c_blk_h[b];
         const int px = pr ? d_pred(pr[2 * (npb == 1 ? 0 : b)]) : 0, py = pr ? d_pred(pr[2 * (npb == 1 ? 0 : b) + 1]) : 0;
-        const int cx = d_clamp(px / 4, -R, R), cy = d_clamp(py / 4, -R, R);
+        const int cx = d_clamp(px / 4, -P.cmax, P.cmax), cy = d_clamp(py / 4, -P.cmax, P.cmax);
         const int bonus = b == 0 ? bonus16 : 0;
         unsigned long long best = ~0ull;
         for (int idx = tid; idx < ncand; idx += 128) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) me_full_kernel(const SearchParams P)
         const unsigned long long v = s_best[tid];
         const unsigned key = (unsigned)v;
         const int px = pr ? d_pred(pr[2 * (npb == 1 ? 0 : tid)]) : 0, py = pr ? d_pred(pr[2 * (npb == 1 ? 0 : tid) + 1]) : 0;
-        const int cx = d_clamp(px / 4, -R, R), cy = d_clamp(py / 4, -R, R);
+        const int cx = d_clamp(px / 4, -P.cmax, P.cmax), cy = d_clamp(py / 4, -P.cmax, P.cmax);
         BlkRes r;
         r.mvx = (int16_t)(4 * (cx + P.spiral_xy[2 * (key - 1)]));
         r.mvy = (int16_t)(4 * (cy + P.spiral_xy[2 * (key - 1) + 1]));

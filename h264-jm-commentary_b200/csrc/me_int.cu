@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_kernel(const SearchParam
         it.mbx = it.mb - it.mby * P.mb_w;
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
         const int p16x = pr ? d_pred(pr[0]) : 0, p16y = pr ? d_pred(pr[1]) : 0;
-        it.cx = d_clamp(p16x / 4, -R, R);
-        it.cy = d_clamp(p16y / 4, -R, R);
+        it.cx = d_clamp(p16x / 4, -P.cmax, P.cmax);
+        it.cy = d_clamp(p16y / 4, -P.cmax, P.cmax);
     };
     // asynchronous fetch of the raw window rows (16-byte chunks) and the current MB of an item
     auto prefetch = [&](const Item &it, int buf) {

@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             pr = s_wpred;
         }
         const int p16x = pr ? d_pred(pr[0]) : 0, p16y = pr ? d_pred(pr[1]) : 0;
-        it.cx = d_clamp(p16x / 4, -R, R);
-        it.cy = d_clamp(p16y / 4, -R, R);
+        it.cx = d_clamp(p16x / 4, -P.cmax, P.cmax);
+        it.cy = d_clamp(p16y / 4, -P.cmax, P.cmax);
     };
     auto prefetch = [&](const Item &it, int buf) {
         const uint8_t *plane = P.planes[it.ref];

@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-ABI_VERSION = 5          # JMME_ABI_VERSION of include/jmme.h
+ABI_VERSION = 6          # JMME_ABI_VERSION of include/jmme.h
 BLOCKS_PER_MB = 41
 MAX_REFS = 4
 MAX_GPUS = 8
@@ -46,7 +46,7 @@ class Params(C.Structure):
         "mb_row_begin", "mb_row_end", "n_gpus")] + [("device_ids", C.c_int32 * MAX_GPUS),
                                                      ("async_reference", C.c_int32), ("slice_rows", C.c_int32)] + \
         [(n, C.c_int32) for n in ("me_distortion", "me_distortion_fpel", "me_distortion_hpel", "me_distortion_qpel",
-                                  "transform8x8", "chroma_me")]
+                                  "transform8x8", "chroma_me", "jm_center", "max_pred_qpel")]
 
 
 class Tuning(C.Structure):

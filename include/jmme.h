@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define JMME_ABI_VERSION     5
+#define JMME_ABI_VERSION     6
 #define JMME_BLOCKS_PER_MB   41   /* 1 + 2 + 2 + 4 + 8 + 8 + 16 */
 #define JMME_MAX_REFS        4
 #define JMME_MAX_SEARCH_RANGE 64
@@ -114,6 +114,14 @@ typedef struct jmme_params {
     int32_t chroma_me;           /* 1: the sub-pel stages add the distortion of both chroma blocks (4:2:0,       */
                                  /* 1/8-pel bilinear samples, H.264 8.4.2.2.2); needs jmme_set_reference_chroma  */
                                  /* and jmme_set_current_chroma                                                  */
+    /* ---- ABI 6: JM's rule for the search-window centre ----------------------------- */
+    int32_t jm_center;           /* 0: centre = pred/4 clamped to +-R always (every window inside the default    */
+                                 /*    replication border);  1: JM's BlockMotionSearch — clamped to +-R only     */
+                                 /*    when !rdopt; with rdopt = 1 the centre follows the predictor, limited to  */
+                                 /*    +-max_pred_qpel/4, and the planes get a border of max_pred_qpel/4 + R +   */
+                                 /*    16 samples (jmme_pad) so that every window still lies inside them         */
+    int32_t max_pred_qpel;       /* |predictor component| the host entry points accept, quarter-pel;             */
+                                 /* 0 = JMME_MAX_PRED_QPEL (2048); 4..2048                                       */
 } jmme_params;
 
 /* distortion metrics (JM MEDistortion*: 0 SAD, 1 SSE, 2 Hadamard SAD) */

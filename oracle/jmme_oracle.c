@@ -44,6 +44,7 @@ struct jmme_ctx {
     int n_planes;                    /* 16 with subpel, else 1 */
     int metric[3];                   /* JMME_DIST_* of the integer, half-pel and quarter-pel stage */
     int lf[3];                       /* lambda factor of each stage in the context's cost domain (SSE: lambda^2) */
+    int max_pred, cmax;              /* |pred| limit of this context; limit of the window centre (samples)  */
     int cpad, cstride, cheight;      /* chroma_me: padded integer chroma planes (w16/2 + 2 cpad) x (h16/2 + 2 cpad) */
     uint8_t *cplanes[JMME_MAX_REFS][2];
     int cref_set[JMME_MAX_REFS];
@@ -366,7 +367,9 @@ void jmme_default_params(jmme_params *p)
     p->qp = 28; p->rdopt = 0; p->use_hadamard = 1; p->subpel = 0;
     p->search_mode = JMME_SEARCH_FASTFULL; p->pred_policy = JMME_PRED_ZERO;
 }
-static int pad_for(int R) { return (2 * R + 16 + 15) & ~15; }
+/* replication border: the window centre moves up to cmax samples from the MB, the window R more, 16 for the MB
+ * and the sub-pel / 6-tap margin */
+static int pad_for(int R, int cmax) { return (cmax + R + 16 + 15) & ~15; }
 
 int jmme_create(jmme_ctx **out, const jmme_params *p)
 {
@@ -381,7 +384,8 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
         p->search_mode < 0 || p->search_mode > 1 || p->pred_policy < 0 || p->pred_policy > 3 ||
         p->satd_round < 0 || p->satd_round > 1 || p->slice_rows < 0 || p->cost_domain < 0 || p->cost_domain > 1 ||
         p->me_distortion < 0 || p->me_distortion > 1 || p->transform8x8 < 0 || p->transform8x8 > 1 ||
-        p->chroma_me < 0 || p->chroma_me > 1)
+        p->chroma_me < 0 || p->chroma_me > 1 || p->jm_center < 0 || p->jm_center > 1 ||
+        (p->max_pred_qpel && (p->max_pred_qpel < 4 || p->max_pred_qpel > JMME_MAX_PRED_QPEL)))
         return JMME_ERR_PARAM;
     if (p->me_distortion &&
         (p->me_distortion_fpel < 0 || p->me_distortion_fpel > 2 || p->me_distortion_hpel < 0 || p->me_distortion_hpel > 2 ||
@@ -405,7 +409,11 @@ int jmme_create(jmme_ctx **out, const jmme_params *p)
             free(c); return JMME_ERR_PARAM;
         }
     }
-    c->pad = pad_for(p->search_range);
+    c->max_pred = p->max_pred_qpel ? p->max_pred_qpel : MAX_PRED;
+    /* centre limit: +-R, or (JM: rdopt = 1 does not clamp) as far as the largest predictor reaches */
+    c->cmax = (p->jm_center && p->rdopt) ? c->max_pred / 4 : p->search_range;
+    if (c->cmax < p->search_range) c->cmax = p->search_range;
+    c->pad = pad_for(p->search_range, c->cmax);
     c->pstride = c->w16 + 2 * c->pad; c->pheight = c->h16 + 2 * c->pad;
     {
         const int lf16 = p->lambda_factor ? p->lambda_factor : jmme_lambda_factor(p->qp, p->rdopt);
@@ -962,7 +970,7 @@ int jmme_commit_field(jmme_ctx *c, const jmme_mbresult *res, int16_t *mv4, int8_
 static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred, jmme_mbresult *out,
                       jmme_mbresult *out_per_ref, int mbx, int mby, int32_t *bsad)
 {
-    const int R = c->p.search_range, nmb = c->mb_w * c->mb_h, mb = mby * c->mb_w + mbx;
+    const int nmb = c->mb_w * c->mb_h, mb = mby * c->mb_w + mbx;
     const int npb = c->p.pred_policy >= JMME_PRED_PER_BLOCK ? JMME_BLOCKS_PER_MB : 1;
     const int dom = c->p.cost_domain;
     jmme_mbresult *o = &out[mb];
@@ -982,7 +990,7 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
         const int has_bonus = !c->p.rdopt && r == 0;       /* 16x16 (0,0) bias: !rdopt, reference 0 */
         jmme_mbresult *opr = out_per_ref ? &out_per_ref[(size_t)r * nmb + mb] : NULL;
         const int p16x = pr ? pr[0] : 0, p16y = pr ? pr[1] : 0;
-        const int cx = clampi(p16x / 4, -R, R), cy = clampi(p16y / 4, -R, R);
+        const int cx = clampi(p16x / 4, -c->cmax, c->cmax), cy = clampi(p16y / 4, -c->cmax, c->cmax);
         g.cplane[0] = c->cplanes[r][0]; g.cplane[1] = c->cplanes[r][1];
         if (opr) {
             for (b = 0; b < JMME_BLOCKS_PER_MB; b++) {
@@ -1011,7 +1019,7 @@ static void search_mb(const jmme_ctx *c, const uint8_t *cur, const int16_t *pred
                                        c->lf[0], cx, cy, px, py, !c->p.rdopt, g.bonus[0], &bp, &cost);
                         mvx = cx + c->spx[bp]; mvy = cy + c->spy[bp];
                     } else {
-                        const int bcx = clampi(px / 4, -R, R), bcy = clampi(py / 4, -R, R);
+                        const int bcx = clampi(px / 4, -c->cmax, c->cmax), bcy = clampi(py / 4, -c->cmax, c->cmax);
                         full_block(cur, c->w16, ref00, c->pstride, bx, by, bw, bh, bcx, bcy, px, py, c->ncand,
                                    c->spx, c->spy, c->mvbits, dom, c->metric[0], c->lf[0], g.bonus[0], &mvx, &mvy, &cost);
                     }
@@ -1062,7 +1070,7 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur_in, int stride, const int1
         for (r = 0; r < c->p.num_refs; r++) {
             const int16_t *q = pred + ((size_t)r * nmb + (size_t)c->p.mb_row_begin * c->mb_w) * per_mb;
             for (i = 0; i < n; i++)
-                if (q[i] > MAX_PRED || q[i] < -MAX_PRED) return set_err(c, JMME_ERR_PARAM, "pred out of range");
+                if (q[i] > c->max_pred || q[i] < -c->max_pred) return set_err(c, JMME_ERR_PARAM, "pred out of range");
         }
     }
     if (c->p.pred_policy == JMME_PRED_ZERO) pred = NULL;

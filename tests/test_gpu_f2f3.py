@@ -260,3 +260,46 @@ def test_bipred_stripes_virtual_devices_and_errors(cuda, oracle):
             with pytest.raises(abi.JmmeError) as e:
                 c.search_frame_bipred(cur, bad, bad, search_range=2, iterations=1)
             assert e.value.code == abi.ERR_PARAM
+
+
+@pytest.mark.parametrize("policy,mode,R,extra", [
+    (abi.PRED_PER_BLOCK, abi.SEARCH_FASTFULL, 8, dict(subpel=1)),
+    (abi.PRED_PER_BLOCK, abi.SEARCH_FULL, 6, dict(subpel=1, num_refs=2)),
+    (abi.PRED_PER_MB, abi.SEARCH_FASTFULL, 32, dict(subpel=1)),
+    (abi.PRED_PER_BLOCK, abi.SEARCH_FASTFULL, 40, dict(subpel=0)),                       # R > 32: me_int.cu
+    (abi.PRED_PER_BLOCK, abi.SEARCH_FASTFULL, 8, dict(subpel=1, cost_domain=1, chroma_me=1)),
+    (abi.PRED_MEDIAN, abi.SEARCH_FASTFULL, 8, dict(subpel=1, slice_rows=0)),
+])
+def test_jm_center_rule_matches_oracle(cuda, oracle, policy, mode, R, extra):
+    """jm_center = 1 with rdopt = 1: window centres that follow predictors of several R (not clamped to +-R), planes
+    with the wider replication border — every kernel family against the oracle, and the default rule differs."""
+    w, h = 112, 80
+    nref = extra.get("num_refs", 1)
+    cur, refs = synth.frame_pair(w, h, seed=12, search_range=R, num_refs=nref)
+    n_mb = 7 * 5
+    nb = {abi.PRED_PER_MB: 1, abi.PRED_PER_BLOCK: 41}.get(policy)
+    pred = synth.random_pred(nref, n_mb, nb, seed=8, max_qpel=200) if nb else None
+    kw = dict(width=w, height=h, search_range=R, pred_policy=policy, search_mode=mode, qp=29, rdopt=1, jm_center=1,
+              max_pred_qpel=200, **extra)
+    cc = [synth.gen_luma(w // 2, h // 2, 31 + k, "texture") for k in range(2)]
+    outs = []
+    for lib in (cuda, oracle):
+        with lib.context(**kw) as ctx:
+            assert ctx.pad == (200 // 4 + R + 16 + 15) & ~15
+            for i, r in enumerate(refs):
+                ctx.set_reference(i, r)
+                if extra.get("chroma_me"):
+                    ctx.set_reference_chroma(i, *cc)
+            if extra.get("chroma_me"):
+                ctx.set_current_chroma(*cc)
+            outs.append(ctx.search_frame(cur, pred))
+    assert outs[0].tobytes() == outs[1].tobytes()
+    if pred is not None:
+        with cuda.context(**dict(kw, jm_center=0)) as ctx:
+            for i, r in enumerate(refs):
+                ctx.set_reference(i, r)
+                if extra.get("chroma_me"):
+                    ctx.set_reference_chroma(i, *cc)
+            if extra.get("chroma_me"):
+                ctx.set_current_chroma(*cc)
+            assert ctx.search_frame(cur, pred).tobytes() != outs[0].tobytes()

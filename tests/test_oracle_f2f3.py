@@ -192,3 +192,44 @@ def test_bipred_errors_and_masks(oracle):
             for b in on:
                 bits = refimpl.se_bits(int(l0[mb]["mv"][b][0])) + refimpl.se_bits(int(l0[mb]["mv"][b][1]))
                 assert out[mb]["cost"][b] <= l0[mb]["cost"][b] + refimpl.weighted_cost(lf, bits) + 1
+
+
+@pytest.mark.parametrize("mode", [abi.SEARCH_FASTFULL, abi.SEARCH_FULL])
+@pytest.mark.parametrize("rdopt", [1, 0])
+def test_jm_center_rule_against_the_restatement(oracle, mode, rdopt):
+    """jm_center = 1 (JM's BlockMotionSearch): with rdopt the window centre is pred/4
+    truncated, NOT clamped to +-R — predictors of up to 7 R here, windows far outside the picture (unbounded edge
+    replication); without rdopt the clamp stays.  Checked block by block against the per-sample restatement, and
+    the replication border grows with max_pred_qpel."""
+    w, h, R = 32, 16, 2
+    cur, refs = synth.frame_pair(w, h, seed=9, search_range=R)
+    pred = synth.random_pred(1, 2, 41, seed=4, max_qpel=56)
+    assert np.abs(pred).max() > 4 * 3 * R
+    kw = dict(width=w, height=h, search_range=R, pred_policy=abi.PRED_PER_BLOCK, search_mode=mode, subpel=1, qp=30, rdopt=rdopt)
+    with oracle.context(jm_center=1, max_pred_qpel=64, **kw) as ctx:
+        assert ctx.pad == ((64 // 4 + R + 16 + 15) & ~15 if rdopt else (2 * R + 16 + 15) & ~15)
+        ctx.set_reference(0, refs[0])
+        res = ctx.search_frame(cur, pred)
+        with pytest.raises(abi.JmmeError):                       # beyond max_pred_qpel
+            ctx.search_frame(cur, np.full_like(pred, 65))
+    with oracle.context(**kw) as ctx:                             # the default rule: clamped always
+        ctx.set_reference(0, refs[0])
+        clamped = ctx.search_frame(cur, pred)
+    assert (res.tobytes() == clamped.tobytes()) == (not rdopt)
+    spec = refimpl.StageSpec(lam_of(30, rdopt))
+    refc = spec.rate(2, 1) if rdopt else 0
+    for mb in range(2):
+        p16 = pred[0, mb, 0]
+        for b, (t, x0, y0, bw, bh) in enumerate(BLOCKS):
+            if b not in (0, 2, 3, 7, 11, 22, 31):
+                continue
+            px, py = int(pred[0, mb, b, 0]), int(pred[0, mb, b, 1])
+            own = (px, py) if mode == abi.SEARCH_FULL else (int(p16[0]), int(p16[1]))
+            cx, cy = int(own[0] / 4), int(own[1] / 4)            # C truncation toward zero
+            if not rdopt:
+                cx, cy = int(np.clip(cx, -R, R)), int(np.clip(cy, -R, R))
+            mvx, mvy, c = refimpl.block_search(spec, cur, refs[0], 16 * mb + x0, y0, bw, bh, cx, cy, px, py, R,
+                                               bonus16=(t == 1 and not rdopt),
+                                               pretest=(not rdopt and mode == abi.SEARCH_FASTFULL), subpel=1)
+            assert tuple(res[mb]["mv"][b]) == (mvx, mvy), (mb, b)
+            assert res[mb]["cost"][b] == c + refc, (mb, b)
