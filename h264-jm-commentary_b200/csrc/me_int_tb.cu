@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int R = P.R, ncols = P.ncols, ncand = ncols * ncols;
     const int RS = RS_CT ? RS_CT : L.RS;
     const int rows = L.rows, RAWW = L.RAWW;
-    const int n_mb_stripe = (P.mb_row_end - P.mb_row_begin) * P.mb_w;
     const int n_mb = P.mb_w * P.mb_h;
     const int ppr = (P.mb_w + NM - 1) / NM;              // items per MB row
     const int n_it_stripe = P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ppr;   // a list: one MB per item
