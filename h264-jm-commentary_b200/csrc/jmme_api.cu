@@ -79,6 +79,14 @@ struct jmme_ctx {
     cudaEvent_t ev_copy;
     cudaStream_t part_stream[4];          // the pipelined host path searches the stripe in up to 4 parts
     cudaEvent_t ev_ref;
+    // async_reference + pipelined host path: jmme_set_reference queues only the first chunk of the picture (the rows
+    // the first part of the search needs); the other chunks are uploaded and interpolated by jmme_search_frame,
+    // interleaved with the parts of the current picture, so the first search kernel waits for a fraction of both
+    // pictures instead of the whole reference
+    const uint8_t *pend_luma[JMME_MAX_REFS];
+    int pend_stride[JMME_MAX_REFS];
+    int pend_next[JMME_MAX_REFS];         // first chunk not queued yet; 0 = nothing pending
+    cudaEvent_t ev_chunk[4];
     cudaEvent_t ev_search;                // end of the last in-frame median search (orders jmme_get_predictors)
     uint8_t *d_raw;                       // staging for the raw current picture (width x height)
     uint8_t *d_raw_ref[JMME_MAX_REFS];    // staging for the raw reference pictures
@@ -189,6 +197,8 @@ void free_device(jmme_ctx *c)
             if (c->ev_prof[i][j]) cudaEventDestroy(c->ev_prof[i][j]);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_ref) cudaEventDestroy(c->ev_ref);
+    for (int i = 0; i < 4; i++)
+        if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_search) cudaEventDestroy(c->ev_search);
     for (int i = 0; i < 4; i++)
         if (c->part_stream[i]) cudaStreamDestroy(c->part_stream[i]);
@@ -286,6 +296,7 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
         CUC(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
         for (int i = 0; i < 4; i++) CUC(cudaStreamCreateWithFlags(&c->part_stream[i], cudaStreamNonBlocking));
         CUC(cudaEventCreateWithFlags(&c->ev_ref, cudaEventDisableTiming));
+        for (int i = 0; i < 4; i++) CUC(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_search, cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         CUC(cudaMalloc(&c->d_raw, (size_t)p->width * p->height));
@@ -599,11 +610,17 @@ int64_t jmme_launch_count(const jmme_ctx *c)
     return n;
 }
 
+static int flush_pending_refs(jmme_ctx *c);
 int jmme_set_tuning(jmme_ctx *c, const jmme_tuning *t)
 {
     if (!c || !t) return JMME_ERR_PARAM;
     if (t->variant < 0 || t->group < 0 || t->group > 4 || t->cluster < 0 || t->cluster > 4 || t->pipe_parts < 0)
         return fail(c, JMME_ERR_PARAM, "tuning out of range");
+    if (!c->n_sub) {                              // reference chunks still pending were cut for the old pipe_parts
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, JMME_ERR_CUDA, "cudaSetDevice");
+        int rcf = flush_pending_refs(c);
+        if (rcf != JMME_OK) return rcf;
+    }
     resolve_tuning(t, &c->tune);
     for (int g = 0; g < c->n_sub; g++) resolve_tuning(t, &c->sub[g]->tune);
     return JMME_OK;
@@ -625,9 +642,9 @@ int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d_luma, int stride, v
     // 16 rows of the MB, one more sample for the sub-pel candidates (rounded out to 4)
     const int R = c->p.search_range;
     // (a stripe that touches the top / bottom of the picture produces the whole border)
-    const int y_begin = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - 2 * R - 4);
+    const int y_begin = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - c->cmax - R - 4);
     const int y_end = c->p.mb_row_end == c->mb_h ? c->pheight
-                                                 : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
+                                                 : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + c->cmax + R + 4);
     c->prof_valid[0] = false;
     if (c->profiling) CU(c, cudaEventRecord(c->ev_prof[0][0], (cudaStream_t)stream));
     CU(c, jmme_launch_interp((const uint8_t *)d_luma, c->p.width, c->p.height, stride, c->pad, c->pstride, c->pheight,
@@ -635,6 +652,74 @@ int jmme_set_reference_dev(jmme_ctx *c, int r, const void *d_luma, int stride, v
     if (c->profiling) { CU(c, cudaEventRecord(c->ev_prof[0][1], (cudaStream_t)stream)); c->prof_valid[0] = true; }
     c->launches++;
     c->ref_set[r] = true;
+    return JMME_OK;
+}
+
+// First MB row of part k of np of the pipelined host path (k = np: the end).  The first part is small, so that the
+// first search kernel waits for few rows of both pictures, and the last one is smaller than the middle ones,
+// because its download is not hidden behind any kernel.
+static int part_begin(const jmme_ctx *c, int k, int np)
+{
+    static const int kCut[5][5] = {{0, 0, 0, 0, 0}, {0, 100, 0, 0, 0}, {0, 40, 100, 0, 0}, {0, 20, 64, 100, 0}, {0, 12, 42, 75, 100}};
+    const int rows = c->p.mb_row_end - c->p.mb_row_begin;
+    if (k <= 0) return c->p.mb_row_begin;
+    if (k >= np) return c->p.mb_row_end;
+    const int cut = c->tune.even_parts ? 100 * k / np : kCut[np][k];
+    return c->p.mb_row_begin + std::min(std::max(rows * cut / 100, k), rows - (np - k));
+}
+
+// ---- reference upload in chunks (host path) -----------------------------------------------------------------
+// Can jmme_search_frame take its pipelined form for this context?  (The properties of the current-picture buffer
+// are checked there; if they fail, the pending chunks are flushed first.)
+static bool pipelined_ctx(const jmme_ctx *c)
+{
+    return !c->n_sub && !c->profiling && c->tune.pipe_parts > 1 && c->p.pred_policy != JMME_PRED_MEDIAN &&
+           c->w16 == c->p.width && c->p.mb_row_end - c->p.mb_row_begin >= 4 * c->tune.pipe_parts;
+}
+// plane rows [*pb, *pe) and picture rows [*sb, *se) of chunk k of np: chunk k ends where part k of the search can
+// reach (its MB rows + window + centre excursion + sub-pel margin); a plane row needs picture rows -2 .. +3
+static void ref_chunk(const jmme_ctx *c, int k, int np, int *pb, int *pe, int *sb, int *se)
+{
+    const int R = c->p.search_range;
+    const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - c->cmax - R - 4);
+    const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + c->cmax + R + 4);
+    auto end_of = [&](int j) {
+        if (j < 0) return yb;
+        if (j >= np - 1) return ye;
+        const int re = part_begin(c, j + 1, np);
+        return std::min(ye, c->pad + 16 * re + c->cmax + R + 4);
+    };
+    auto src_end = [&](int y) { return std::min(std::max(y - c->pad + 3, 1), c->p.height); };     // exclusive
+    *pb = end_of(k - 1); *pe = end_of(k);
+    *sb = k == 0 ? std::min(std::max(yb - c->pad - 3, 0), c->p.height - 1) : src_end(*pb);
+    *se = src_end(*pe);
+}
+// queue chunks [from, to) of reference r on the context's stream: picture rows up, their plane rows interpolated
+static int queue_ref_chunks(jmme_ctx *c, int r, const uint8_t *luma, int stride, int from, int to, int np)
+{
+    for (int k = from; k < to; k++) {
+        int pb, pe, sb, se;
+        ref_chunk(c, k, np, &pb, &pe, &sb, &se);
+        if (se > sb)
+            CU(c, upload_rows(c->d_raw_ref[r] + (size_t)sb * c->p.width, luma + (size_t)sb * stride, stride, c->p.width, se - sb,
+                              c->stream));
+        if (pe > pb) {
+            CU(c, jmme_launch_interp(c->d_raw_ref[r], c->p.width, c->p.height, c->p.width, c->pad, c->pstride, c->pheight,
+                                     c->n_planes, c->d_planes[r], pb, pe, c->stream));
+            c->launches++;
+        }
+    }
+    return JMME_OK;
+}
+// everything still pending goes out now (a call that reads the planes outside the pipelined search)
+static int flush_pending_refs(jmme_ctx *c)
+{
+    for (int r = 0; r < c->p.num_refs; r++)
+        if (c->pend_next[r]) {
+            int rc = queue_ref_chunks(c, r, c->pend_luma[r], c->pend_stride[r], c->pend_next[r], c->tune.pipe_parts, c->tune.pipe_parts);
+            c->pend_next[r] = 0;
+            if (rc != JMME_OK) return rc;
+        }
     return JMME_OK;
 }
 
@@ -649,11 +734,21 @@ int jmme_set_reference(jmme_ctx *c, int r, const uint8_t *luma, int stride)
         return JMME_OK;
     }
     CU(c, cudaSetDevice(c->device));
+    c->pend_next[r] = 0;
+    if (c->p.async_reference && pipelined_ctx(c)) {
+        // first chunk now, the others with the parts of the next jmme_search_frame (the caller keeps `luma` unchanged
+        // until that call returns: the contract of async_reference)
+        int rc = queue_ref_chunks(c, r, luma, stride, 0, 1, c->tune.pipe_parts);
+        if (rc != JMME_OK) return rc;
+        c->pend_luma[r] = luma; c->pend_stride[r] = stride; c->pend_next[r] = 1;
+        c->ref_set[r] = true;
+        return JMME_OK;
+    }
     {
         // upload only the picture rows the stripe's planes are built from (plane rows +-3 filter taps)
         const int R = c->p.search_range;
-        const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - 2 * R - 4);
-        const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
+        const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - c->cmax - R - 4);
+        const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + c->cmax + R + 4);
         const int s0 = std::min(std::max(yb - c->pad - 3, 0), c->p.height - 1);
         const int s1 = std::min(std::max(ye - c->pad + 3, 1), c->p.height);          // exclusive; clamps hit row h-1
         CU(c, upload_rows(c->d_raw_ref[r] + (size_t)s0 * c->p.width, luma + (size_t)s0 * stride, stride, c->p.width, s1 - s0,
@@ -784,6 +879,7 @@ int jmme_search_frame_bipred(jmme_ctx *c, const uint8_t *cur, int stride, const 
         return JMME_OK;
     }
     if (!c->l1_set) return fail(c, JMME_ERR_STATE, "list-1 reference not set");
+    { int rcf = flush_pending_refs(c); if (rcf != JMME_OK) return rcf; }
     for (int r = 0; r < c->p.num_refs; r++)
         if (!c->ref_set[r]) return fail(c, JMME_ERR_STATE, "reference not set");
     // list-0 planes of a stripe context cover only the rows its own search reaches: the refinement needs the same
@@ -793,9 +889,9 @@ int jmme_search_frame_bipred(jmme_ctx *c, const uint8_t *cur, int stride, const 
         const int R = c->p.search_range;
         // quarter-pel, worst case: a uni-directional vector reaches R around the window centre, the centre R around
         // (0,0) when predictors are given; each iteration of a list moves it by up to `range`
-        const int reach = 4 * (c->p.pred_policy == JMME_PRED_ZERO ? R : 2 * R) + 3 + 4 * range * ((iterations + 1) / 2);
-        const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - 2 * R - 4);
-        const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + 2 * R + 4);
+        const int reach = 4 * (c->p.pred_policy == JMME_PRED_ZERO ? R : c->cmax + R) + 3 + 4 * range * ((iterations + 1) / 2);
+        const int yb = c->p.mb_row_begin == 0 ? 0 : std::max(0, c->pad + 16 * c->p.mb_row_begin - c->cmax - R - 4);
+        const int ye = c->p.mb_row_end == c->mb_h ? c->pheight : std::min(c->pheight, c->pad + 16 * c->p.mb_row_end + c->cmax + R + 4);
         const int need_b = c->pad + 16 * c->p.mb_row_begin - std::min((reach >> 2) + 1, c->pad - 1);
         const int need_e = c->pad + 16 * c->p.mb_row_end + std::min((reach >> 2) + 1, c->pad - 1);
         if (need_b < yb || need_e > ye) return fail(c, JMME_ERR_UNSUPPORTED, "bi-pred refinement on a stripe context: range * iterations exceeds the halo");
@@ -918,6 +1014,7 @@ int jmme_get_subimage(jmme_ctx *c, int r, int xf, int yf, uint8_t *dst, int dst_
     if (!c->ref_set[r]) return JMME_ERR_STATE;
     if ((xf || yf) && c->n_planes != 16) return JMME_ERR_STATE;
     CU(c, cudaSetDevice(c->device));
+    { int rc = flush_pending_refs(c); if (rc != JMME_OK) return rc; }
     const uint8_t *src = c->d_planes[r] + (size_t)c->pstride * c->pheight * (yf * 4 + xf);
     CU(c, cudaMemcpy2DAsync(dst, dst_stride, src, c->pstride, c->pstride, c->pheight, cudaMemcpyDeviceToHost,
                             c->stream));
@@ -933,6 +1030,16 @@ int jmme_search_frame_dev(jmme_ctx *c, const void *d_cur, int stride, const void
     if (c->p.pred_policy != JMME_PRED_ZERO && c->p.pred_policy != JMME_PRED_MEDIAN && !d_pred)
         return fail(c, JMME_ERR_PARAM, "pred required");
     CU(c, cudaSetDevice(c->device));
+    {
+        bool pending = false;                                 // a host-path reference still in chunks (async_reference)
+        for (int r = 0; r < c->p.num_refs; r++) pending |= c->pend_next[r] != 0;
+        int rcf = flush_pending_refs(c);
+        if (rcf != JMME_OK) return rcf;
+        if (pending) {                                        // its planes are built on the internal stream
+            CU(c, cudaEventRecord(c->ev_ref, c->stream));
+            CU(c, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_ref, 0));
+        }
+    }
     c->dev_call = true;
     const int rc = enqueue_search(c, (const uint8_t *)d_cur, stride, (const int16_t *)d_pred, (jmme_mbresult *)d_out,
                                   (jmme_mbresult *)d_out_per_ref, (cudaStream_t)stream);
@@ -1071,8 +1178,8 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
         jmme_ctx *s = c;
         CU(c, cudaSetDevice(s->device));
         CU(c, upload_pred(s, s->stream));
-        CU(c, cudaEventRecord(s->ev_ref, s->stream));          // planes (and predictors) are ready after this
-        const int np = s->tune.pipe_parts, rows = s->p.mb_row_end - s->p.mb_row_begin;
+        CU(c, cudaEventRecord(s->ev_chunk[0], s->stream));     // first chunk of the planes (and predictors) ready after this
+        const int np = s->tune.pipe_parts;
         int rc = JMME_OK, used = 0;
         // a failure in part k must not return while parts 0..k-1 still write into the caller's buffers
 #define CUP(call)                                                                              \
@@ -1081,13 +1188,23 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
         if (e_ != cudaSuccess) { rc = fail(c, JMME_ERR_CUDA, #call, e_); goto parts_done; }    \
     } while (0)
         for (int pt = 0; pt < np; pt++) {
-            const int rb = s->p.mb_row_begin + rows * pt / np, re = s->p.mb_row_begin + rows * (pt + 1) / np;
+            const int rb = part_begin(s, pt, np), re = part_begin(s, pt + 1, np);
             cudaStream_t st = s->part_stream[pt];
             const int y0 = std::min(16 * rb, s->p.height - 1), y1 = std::min(16 * re, s->p.height);
             used = pt + 1;
             CUP(upload_rows(s->d_raw + (size_t)y0 * s->p.width, cur + (size_t)y0 * stride, stride, s->p.width,
                             std::max(y1 - y0, 1), st));
-            CUP(cudaStreamWaitEvent(st, s->ev_ref, 0));
+            if (pt > 0) {
+                // the reference chunks of this part, queued behind the part's current-picture rows (copy-engine order)
+                for (int r = 0; r < s->p.num_refs; r++)
+                    if (s->pend_next[r] && s->pend_next[r] <= pt) {
+                        rc = queue_ref_chunks(s, r, s->pend_luma[r], s->pend_stride[r], pt, pt + 1, np);
+                        if (rc != JMME_OK) goto parts_done;
+                        s->pend_next[r] = pt + 1 < np ? pt + 1 : 0;
+                    }
+                CUP(cudaEventRecord(s->ev_chunk[pt], s->stream));
+            }
+            CUP(cudaStreamWaitEvent(st, s->ev_chunk[pt], 0));
             rc = enqueue_search(s, s->d_raw, s->p.width, s->d_pred, s->d_out, out_per_ref ? s->d_out_per_ref : nullptr,
                                 st, rb, re);
             if (rc != JMME_OK) goto parts_done;
@@ -1100,6 +1217,11 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
         }
 #undef CUP
     parts_done:
+        if (rc != JMME_OK) flush_pending_refs(s);              // (keeps the planes whole for the next call)
+        {
+            cudaError_t e = cudaStreamSynchronize(s->stream);   // the chunk uploads read the caller's reference buffers
+            if (e != cudaSuccess && rc == JMME_OK) rc = fail(c, JMME_ERR_CUDA, "cudaStreamSynchronize(stream)", e);
+        }
         for (int pt = 0; pt < used; pt++) {
             cudaError_t e = cudaStreamSynchronize(s->part_stream[pt]);
             if (e != cudaSuccess && rc == JMME_OK) rc = fail(c, JMME_ERR_CUDA, "cudaStreamSynchronize(part)", e);
@@ -1111,6 +1233,7 @@ int jmme_search_frame(jmme_ctx *c, const uint8_t *cur, int stride, const int16_t
     for (int g = 0; g < ns; g++) {
         jmme_ctx *s = subs[g];
         CU(c, cudaSetDevice(s->device));
+        { int rcf = flush_pending_refs(s); if (rcf != JMME_OK) return fail(c, rcf, s->err); }
         {
             // only the current-picture rows of this stripe (row h-1 stands in for the replicated rows below it)
             const int s0 = std::min(16 * s->p.mb_row_begin, s->p.height - 1);

@@ -257,7 +257,8 @@ typedef struct jmme_tuning {
     int32_t pipe_parts;      /* host path: the stripe is searched in this many parts on separate streams (1..4)      */
     int32_t balance;         /* zero-predictor search, R = 32: 0 = balanced task ranges when the stripe has two or   */
                              /* more rounds of items, 1 = always, 2 = never (whole MB items per CTA)                 */
-    int32_t reserved[8];
+    int32_t even_parts;      /* host path: 1 = parts of equal size (default: a small first and a smaller last part)  */
+    int32_t reserved[7];
 } jmme_tuning;
 int jmme_set_tuning(jmme_ctx *ctx, const jmme_tuning *t);
 int jmme_get_tuning(const jmme_ctx *ctx, jmme_tuning *t);      /* the values in effect (defaults resolved)         */

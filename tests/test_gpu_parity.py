@@ -694,6 +694,49 @@ def test_async_reference_with_the_pipelined_host_path(cuda, oracle, h, stripe):
                 assert np.array_equal(pa, pb)
 
 
+@pytest.mark.parametrize("parts", [2, 3, 4])
+@pytest.mark.parametrize("extra", [dict(), dict(mb_row_begin=3, mb_row_end=19), dict(rdopt=1, jm_center=1, max_pred_qpel=160, pred_policy=abi.PRED_PER_MB)])
+def test_reference_chunks_of_the_pipelined_host_path(cuda, parts, extra):
+    """async_reference + the pipelined host path: jmme_set_reference queues the first chunk of the reference only, the
+    others go up with the parts of the search.  Three frames through one context (each frame a new reference and a
+    new current picture), two references, stripes, wider borders: the same fields as a context that uploads
+    synchronously; a tuning change, a plane read-back and a device-pointer search in between flush the pending
+    chunks."""
+    import torch
+    w, h, R = 160, 336, 8
+    frames = [synth.frame_pair(w, h, seed=40 + i, search_range=R, num_refs=2) for i in range(3)]
+    kw = dict(width=w, height=h, search_range=R, num_refs=2, qp=28, subpel=1, **extra)
+    n_mb = (w // 16) * (h // 16)
+    pred = synth.random_pred(2, n_mb, 1, seed=3, max_qpel=150) if "pred_policy" in extra else None
+    with cuda.context(async_reference=1, tuning=dict(pipe_parts=parts), **kw) as a, cuda.context(**kw) as b:
+        for i, (cur, refs) in enumerate(frames):
+            for r in range(2):
+                a.set_reference(r, refs[r]); b.set_reference(r, refs[r])
+            if i == 1:                                           # read a plane back while chunks are pending
+                assert np.array_equal(a.get_subimage(1, 2, 3), b.get_subimage(1, 2, 3)) or "mb_row_begin" in extra
+                for r in range(2):
+                    a.set_reference(r, refs[r])
+            if i == 2:                                           # a tuning change while chunks are pending
+                a.set_tuning(pipe_parts=parts % 3 + 2)
+            ga, gb = a.search_frame(cur, pred), b.search_frame(cur, pred)
+            assert ga.tobytes() == gb.tobytes(), (i, parts, extra)
+        # pending chunks and a device-pointer search
+        cur, refs = frames[0]
+        for r in range(2):
+            a.set_reference(r, refs[r]); b.set_reference(r, refs[r])
+        dcur = torch.from_numpy(cur).cuda()
+        outs = []
+        for ctx in (a, b):
+            out = torch.zeros(n_mb * abi.MBRESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+            dp = torch.from_numpy(pred).cuda() if pred is not None else None
+            cuda.check(cuda.dll.jmme_search_frame_dev(ctx.handle, ctypes.c_void_p(dcur.data_ptr()), w,
+                                                      ctypes.c_void_p(dp.data_ptr()) if dp is not None else None,
+                                                      ctypes.c_void_p(out.data_ptr()), None, None), ctx.handle)
+            torch.cuda.synchronize()
+            outs.append(out.cpu().numpy().tobytes())
+        assert outs[0] == outs[1]
+
+
 @pytest.mark.parametrize("nref,subpel,median", [(1, 1, False), (2, 1, False), (1, 0, False), (1, 1, True), (2, 1, True)])
 def test_fused_peer_stores(cuda, nref, subpel, median):
     """jmme_set_peer_fields_dev: the kernel that writes a record also stores it into the peer buffers (here two more
