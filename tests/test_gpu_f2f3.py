@@ -303,3 +303,53 @@ def test_jm_center_rule_matches_oracle(cuda, oracle, policy, mode, R, extra):
             if extra.get("chroma_me"):
                 ctx.set_current_chroma(*cc)
             assert ctx.search_frame(cur, pred).tobytes() != outs[0].tobytes()
+
+
+def test_randomised_round2_parameter_space(cuda, oracle):
+    """Seeded random sweep over everything round 2 added, combined freely with the older parameters: cost domain,
+    per-stage metrics, 8x8 Hadamard, chroma ME, JM's centre rule with a predictor limit, predictor policies incl. the
+    in-frame median, stripes, and for the product library the launch shape (balanced task ranges, item groups, parts
+    of the host path).  Even frame sizes (4:2:0 chroma)."""
+    rng = np.random.default_rng(20262)
+    kernels = set()
+    for case in range(40):
+        w, h = 2 * int(rng.integers(9, 72)), 2 * int(rng.integers(9, 56))
+        R = int(rng.choice([2, 4, 7, 12, 16, 32, 32, 32, 36]))
+        nref = int(rng.integers(1, 3))
+        policy = int(rng.choice([0, 0, 1, 2, 3]))
+        rdopt = int(rng.integers(0, 2))
+        subpel = int(rng.integers(0, 2))
+        kw = dict(search_range=R, qp=int(rng.integers(8, 48)), rdopt=rdopt, subpel=subpel, pred_policy=policy,
+                  search_mode=int(rng.integers(0, 2)), satd_round=int(rng.integers(0, 2)), cost_domain=int(rng.integers(0, 2)),
+                  blocktype_mask=int(rng.choice([0xFE, 0xFE, 0x92, 0x1E])))
+        if rng.integers(0, 2):
+            kw.update(me_distortion=1, me_distortion_fpel=int(rng.integers(0, 2)), me_distortion_hpel=int(rng.integers(0, 3)),
+                      me_distortion_qpel=int(rng.integers(0, 3)), transform8x8=int(rng.integers(0, 2)))
+        else:
+            kw.update(use_hadamard=int(rng.integers(0, 2)))
+        chroma = None
+        if subpel and rng.integers(0, 2):
+            kw["chroma_me"] = 1
+            chroma = (chroma_pair(w, h, 100 + case), [chroma_pair(w, h, 200 + case + 7 * r) for r in range(nref)])
+        maxp = 4 * R + 40
+        if rdopt and rng.integers(0, 2):
+            maxp = int(rng.choice([4 * R + 40, 240]))
+            kw.update(jm_center=1, max_pred_qpel=maxp)
+        mb_w, mb_h = (w + 15) // 16, (h + 15) // 16
+        if policy == 3:
+            kw["slice_rows"] = int(rng.choice([0, 1, 2]))
+            if kw["slice_rows"] == 1 and mb_h >= 3 and rng.integers(0, 2):
+                kw.update(mb_row_begin=1, mb_row_end=mb_h - 1)
+        elif mb_h >= 3 and rng.integers(0, 3) == 0:
+            kw.update(mb_row_begin=int(rng.integers(0, 2)), mb_row_end=mb_h - int(rng.integers(0, 2)))
+        tuning = dict(balance=int(rng.integers(0, 3)), group=int(rng.choice([0, 1, 2, 4])), pipe_parts=int(rng.integers(1, 5)),
+                      even_parts=int(rng.integers(0, 2)))
+        cur, refs = synth.frame_pair(w, h, seed=300 + case, search_range=R, kind=str(rng.choice(["texture", "noise"])), num_refs=nref)
+        pred = None if policy in (0, 3) else synth.random_pred(nref, mb_w * mb_h, 1 if policy == 1 else 41, case, maxp)
+        g, k = run(cuda, cur, refs, pred, chroma=chroma, tuning=tuning, **kw)
+        o, _ = run(oracle, cur, refs, pred, chroma=chroma, **kw)
+        rb, re = kw.get("mb_row_begin", 0), kw.get("mb_row_end", mb_h)
+        sl = slice(rb * mb_w, re * mb_w)
+        assert_same(g[sl], o[sl], f"case {case}: {w}x{h} refs {nref} {kw} {tuning} {k}")
+        kernels.add(k.split("<")[0] + ("BAL=1" if "BAL=1" in k else ""))
+    assert len(kernels) >= 3, kernels
