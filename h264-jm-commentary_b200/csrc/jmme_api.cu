@@ -28,6 +28,7 @@ char *jmme_kernel_name_buf()
 cudaError_t jmme_launch_me_int(const SearchParams &P, int num_sms, int variant, cudaStream_t st);
 cudaError_t jmme_launch_me_full(const SearchParams &P, cudaStream_t st);
 bool jmme_me_int_balanced(const SearchParams &P, int variant, int num_sms, bool forced);      // me_int_tb.cu
+bool jmme_me_int_raises_flags(const SearchParams &P, int variant);                            // me_int_tb.cu
 cudaError_t jmme_launch_interp(const uint8_t *src, int w_in, int h_in, int stride, int pad, int ps, int ph,
                                int n_planes, uint8_t *out, int y_begin, int y_end, cudaStream_t st);
 cudaError_t jmme_launch_pad_cur(const uint8_t *src, int w_in, int h_in, int stride, int w16, int h16, uint8_t *dst,
@@ -97,7 +98,9 @@ struct jmme_ctx {
     uint16_t *d_spiral_key;
     int16_t *d_spiral_xy;
     uint32_t *d_kr0;                      // zero-predictor rate + key table of the context (SearchParams::kr0)
+    int *d_ready;                         // per-(ref, MB) flags of the early sub-pel start (SearchParams::ready), all 0
     uint32_t *d_gbest;                    // packed minima of a balanced integer search (SearchParams::gbest), all 0xFFFFFFFF
+    bool ready_dirty;                     // the same for d_ready
     bool gbest_dirty;                     // a failed search may have left words behind: cleared before the next one
     BlkRes *d_res;
     jmme_mbresult *d_out, *d_out_per_ref;
@@ -187,7 +190,7 @@ void free_device(jmme_ctx *c)
     cudaFree(c->d_cur_c[0]); cudaFree(c->d_cur_c[1]); cudaFree(c->d_craw);
     cudaFree(c->d_planes_l1); cudaFree(c->d_raw_l1); cudaFree(c->d_bi_l0); cudaFree(c->d_bi_l1); cudaFree(c->d_bi_pred0);
     cudaFree(c->d_bi_pred1); cudaFree(c->d_bi_spiral); cudaFree(c->d_bi_out); cudaFree(c->d_bi_err);
-    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy); cudaFree(c->d_kr0); cudaFree(c->d_gbest);
+    cudaFree(c->d_cur16); cudaFree(c->d_pred); cudaFree(c->d_spiral_key); cudaFree(c->d_spiral_xy); cudaFree(c->d_kr0); cudaFree(c->d_gbest); cudaFree(c->d_ready);
     cudaFree(c->d_res); cudaFree(c->d_out); cudaFree(c->d_out_per_ref);
     cudaFree(c->d_fmv); cudaFree(c->d_fref); cudaFree(c->d_wave); cudaFree(c->d_wave_tab);
     free(c->wave_off);
@@ -347,6 +350,8 @@ int create_single(jmme_ctx **out, const jmme_params *p, int device)
             const size_t gb = sizeof(uint32_t) * JMME_NBLK * n_mb * p->num_refs;
             CUC(cudaMalloc(&c->d_gbest, gb));
             CUC(cudaMemset(c->d_gbest, 0xFF, gb));
+            CUC(cudaMalloc(&c->d_ready, sizeof(int) * n_mb * p->num_refs));
+            CUC(cudaMemset(c->d_ready, 0, sizeof(int) * n_mb * p->num_refs));
         }
         if (p->pred_policy == JMME_PRED_MEDIAN) {
             // 2:1 wavefront inside every slice: MB (x, y) of a slice that starts at row y0 is decided in step
@@ -477,7 +482,29 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
     // (me_int_tb.cu BAL); a search that failed half-way may have left words behind
     const bool full_pb = c->p.search_mode == JMME_SEARCH_FULL && c->p.pred_policy == JMME_PRED_PER_BLOCK;
     P.int_packed = !full_pb && jmme_me_int_balanced(P, c->tune.variant, c->num_sms, c->tune.balance == 1);
-    if (P.tune_group <= 0) P.tune_group = P.int_packed ? 4 : 2;      // MBs per item: measured best per mode
+    if (P.tune_group <= 0) {
+        // MBs per item of the zero-predictor kernel, measured: 4 once the launch has two or more rounds of MB pairs
+        // on the 3 x SMs resident CTAs (fewer window stagings per MB), else pairs (a short stripe needs the items)
+        const long long pairs = (long long)(P.mb_row_end - P.mb_row_begin) * ((P.mb_w + 1) / 2) * P.num_refs;
+        P.tune_group = (P.int_packed || pairs >= 6LL * c->num_sms) ? 4 : 2;
+        if (P.tune_group == 4 && !P.int_packed && P.num_refs == 1 && !c->tune.no_pair_tail) {
+            // whole rounds of 4-MB items on the 3 x SMs resident CTAs, the remaining rows as pairs: the launch ends with a
+            // short round of short items instead of a long round of long ones
+            const int cap = 3 * c->num_sms, ppr4 = (P.mb_w + 3) / 4, rows = P.mb_row_end - P.mb_row_begin;
+            const int rounds = rows * ppr4 / cap;                       // full rounds of 4-MB items available
+            const int r4 = std::min(rows, rounds * cap / ppr4);          // rows that fill whole rounds
+            if (rounds >= 1 && r4 < rows) P.pair_row = P.mb_row_begin + r4;
+        }
+    }
+    // early start of the sub-pel kernel behind a whole-item search (per-MB ready flags); not while per-kernel event
+    // brackets separate the two launches
+    P.ready = (c->p.subpel && !full_pb && !c->profiling && c->tune.early_subpel != 2 &&
+               jmme_me_int_raises_flags(P, c->tune.variant)) ? c->d_ready : nullptr;
+    if (P.ready && c->ready_dirty) {
+        CU(c, cudaMemsetAsync(c->d_ready, 0, sizeof(int) * (size_t)c->mb_w * c->mb_h * c->p.num_refs, st));
+        c->ready_dirty = false;
+    }
+    if (P.ready) c->ready_dirty = true;
     if (P.int_packed && c->gbest_dirty) {
         CU(c, cudaMemsetAsync(c->d_gbest, 0xFF, sizeof(uint32_t) * JMME_NBLK * (size_t)c->mb_w * c->mb_h * c->p.num_refs, st));
         c->gbest_dirty = false;
@@ -504,6 +531,7 @@ int enqueue_search(jmme_ctx *c, const uint8_t *d_cur, int stride, const int16_t 
         c->launches++;
     }
     c->gbest_dirty = false;
+    c->ready_dirty = false;
     return JMME_OK;
 }
 

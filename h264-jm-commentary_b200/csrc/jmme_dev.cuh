@@ -60,6 +60,11 @@ struct SearchParams {
     uint32_t *gbest;                     // [ref][mb][41] packed (cost + bias) << 15 | key minima, 0xFFFFFFFF between searches
     int int_packed;                      // 1: the integer search leaves its result in gbest (not in res); the first kernel
                                          //    that consumes it — sub-pel, else reference selection — decodes and resets
+    // early start of the sub-pel kernel (me_int_tb.cu / me_subpel.cu): the search kernel raises ready[ref][mb] when the
+    // integer result of an MB is in `res`, the sub-pel kernel — a programmatic dependent that starts while the search
+    // kernel's last round is still running — waits for its MB's flag instead of the kernel boundary and lowers it again
+    int *ready;
+    int pair_row;                        // > 0 (items of 4 MBs): MB rows from here on are dealt out as items of 2 MBs
     jmme_mbresult *peer_out[JMME_MAX_GPUS];  // fused gather: the kernel that writes a record of `out` also stores it into
     int n_peer_out;                      //               the same offset of these (peer-mapped) buffers
     jmme_mbresult *mc_out;               // non-null (then n_peer_out = -1: "fused gather on", no peer list): one multimem.st per

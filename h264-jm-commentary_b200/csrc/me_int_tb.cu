@@ -123,7 +123,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     const int rows = L.rows, RAWW = L.RAWW;
     const int n_mb = P.mb_w * P.mb_h;
     const int ppr = (P.mb_w + NM - 1) / NM;              // items per MB row
-    const int n_it_stripe = P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ppr;   // a list: one MB per item
+    // P.pair_row (NM = 4 only): the stripe's rows from pair_row on are dealt out as items of 2 MBs, so that the launch
+    // is whole rounds of 4-MB items plus a short tail of pairs (see d_n_items_stripe)
+    const int ppr2 = (P.mb_w + 1) / 2;
+    const int row_split = (NM == 4 && P.pair_row > 0 && !P.mb_list) ? min(max(P.pair_row, P.mb_row_begin), P.mb_row_end) : P.mb_row_end;
+    const int n_it4 = (row_split - P.mb_row_begin) * ppr;
+    const int n_it_stripe = P.mb_list ? P.n_list : n_it4 + (P.mb_row_end - row_split) * ppr2;   // a list: one MB per item
     const int n_items = n_it_stripe * P.num_refs;
     constexpr int NPB = PER_BLOCK ? JMME_NBLK : 1;
 
@@ -183,9 +188,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             it.mbx = it.mb - it.mby * P.mb_w;
             it.nmb = 1;
         } else {
-            it.mby = P.mb_row_begin + idx / ppr;
-            it.mbx = (idx % ppr) * NM;
-            it.nmb = min(NM, P.mb_w - it.mbx);
+            if (idx < n_it4) {
+                it.mby = P.mb_row_begin + idx / ppr;
+                it.mbx = (idx % ppr) * NM;
+                it.nmb = min(NM, P.mb_w - it.mbx);
+            } else {                                     // the tail rows in pairs
+                const int i2 = idx - n_it4;
+                it.mby = row_split + i2 / ppr2;
+                it.mbx = (i2 % ppr2) * 2;
+                it.nmb = min(2, P.mb_w - it.mbx);
+            }
             it.mb = it.mby * P.mb_w + it.mbx;
         }
         const int16_t *pr = P.pred ? P.pred + ((size_t)it.ref * n_mb + it.mb) * NPB * 2 : nullptr;
@@ -308,6 +320,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
     Item cur_it, nxt_it;
     int item = blockIdx.x / CL, buf = 0;
     int item_stride = gridDim.x / CL, item_end = n_items;
+    // the sub-pel kernel may start as soon as SMs are free: it waits per MB (P.ready), not for this kernel's end
+    if (P.ready) pdl_trigger();
     const int TPI = n_tasks * NM;                        // tasks of an item
     int g0 = 0, g1 = 0;                                  // BAL: this CTA's range of the stripe's tasks
     if constexpr (BAL) {
@@ -556,6 +570,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) me_int_tb_kernel(const SearchPa
             r.cost = (int)(v >> JMME_KEY_BITS) - (int)bias;
             P.res[((size_t)cur_it.ref * n_mb + cur_it.mb + m) * JMME_NBLK + b] = r;
         }
+        if (P.ready) {                                   // the integer result of this item's MBs is complete: raise their flags
+            __threadfence();
+            __syncthreads();
+            if (crank == 0 && tid < cur_it.nmb) {
+                __threadfence();
+                *(volatile int *)(P.ready + (size_t)cur_it.ref * n_mb + cur_it.mb + tid) = 1;
+            }
+        }
         if (!has_next) break;
         __syncthreads();
         expand(nxt_it);
@@ -580,6 +602,10 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
              "me_int_tb_kernel<K=%d,NW=%d,MINB=%d,PER_BLOCK=%d,RS_CT=%d,KEYG=%d,KRTAB=%d,NMB=%d,CL=%d,WP=%d,LIN=%d,BAL=%d>", K, NW, MINB,
              (int)PER_BLOCK, RS_CT, (int)KEYG, (int)KRTAB, NMB, CL, (int)WP, (int)LIN, (int)BAL);
     int n_items = (P.mb_list ? P.n_list : (P.mb_row_end - P.mb_row_begin) * ((P.mb_w + NMB - 1) / NMB)) * P.num_refs;
+    if (NMB == 4 && P.pair_row > 0 && !P.mb_list) {
+        const int rs = std::min(std::max(P.pair_row, P.mb_row_begin), P.mb_row_end);
+        n_items = ((rs - P.mb_row_begin) * ((P.mb_w + 3) / 4) + (P.mb_row_end - rs) * ((P.mb_w + 1) / 2)) * P.num_refs;
+    }
     if (n_items <= 0) return cudaSuccess;
     if (BAL) {
         // every resident CTA slot gets an equal share of the tasks; at least 8 tasks per CTA (a tiny stripe must not
@@ -678,14 +704,26 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
 bool jmme_me_int_balanced(const SearchParams &P, int variant, int num_sms, bool forced)
 {
     if (!P.tune_split || !P.gbest || !P.kr0) return false;
-    // measured (tools/sweep_split.py, 1080p): with two or more rounds of MB-pair items on the 3 x SMs resident CTAs the
-    // balanced ranges in groups of 4 MBs win 2-6 %; below that a CTA's extra partial item (one more window staging)
-    // costs more than the balance returns — a lone CTA on an SM runs much faster than one of three, so a short last
-    // round is cheap anyway
-    if (!forced && (long long)(P.mb_row_end - P.mb_row_begin) * ((P.mb_w + 1) / 2) * P.num_refs < 6LL * num_sms) return false;
+    // measured (tools/sweep_split.py, 1080p, search + sub-pel): whole items with the early sub-pel start beat the
+    // balanced ranges at every stripe size (68 rows 0.412 vs 0.433 ms, 17 rows 0.111 vs 0.125 ms), so balance is
+    // opt-in (jmme_tuning.balance = 1)
+    (void)num_sms;
+    if (!forced) return false;
     if (P.metric[0] == JMME_DIST_SSE || P.cost_domain || P.R != 32 || P.pred || P.mb_list) return false;
     if (P.blocktype_mask == JMME_MASK_16x16) return false;
     if (variant <= 0) variant = 68;
     const int K = variant / 10, c = variant % 10;
     return c >= 4 && c != 9 && K <= P.ncols;
+}
+
+// Does the integer search of P go to a me_int_tb_kernel launch that raises the per-MB ready flags (SearchParams::ready:
+// the sub-pel kernel then starts early)?  Mirrors jmme_launch_me_int: the two-thread kernel on a whole stripe (no MB
+// list, no balanced ranges: an MB has one writer).
+bool jmme_me_int_raises_flags(const SearchParams &P, int variant)
+{
+    if (P.int_packed || P.mb_list || P.metric[0] == JMME_DIST_SSE || P.cost_domain) return false;
+    if (P.blocktype_mask == JMME_MASK_16x16) return false;
+    if (variant <= 0) variant = P.R <= 32 ? 68 : 51;
+    const int K = variant / 10, c = variant % 10;
+    return c >= 4 && K <= P.ncols;
 }

@@ -95,10 +95,36 @@ __global__ void __launch_bounds__(128 * NG) me_subpel_kernel(const SearchParams 
         pdl_trigger();
         pdl_wait();
     }
+    if (P.ready) {
+        // early start: this kernel runs beside the last round of the search kernel; wait for this MB's integer result
+        // (bounded: a flag that never comes must not hang the GPU — the parity tests would show it), lower the flag for
+        // the next search, and read the result past the L1 (a neighbour's line may have been cached before it was final)
+        if (tid == 0) {
+            volatile int *f = P.ready + (size_t)ref * n_mb + mb;
+            unsigned long long t0 = 0, t1 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (*f == 0) {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 200000000ull) break;           // 0.2 s
+            }
+            __threadfence();
+            *f = 0;
+        }
+        __syncthreads();
+    }
     int mvx, mvy, mn, px = 0, py = 0;
     {
         // (a balanced integer search leaves packed minima: decoded here, reset by the block's owner lane below)
-        const BlkRes r = P.int_packed ? d_unpack_int(P, P.gbest[((size_t)ref * n_mb + mb) * JMME_NBLK + b]) : res[b];
+        BlkRes r;
+        if (P.int_packed) {
+            r = d_unpack_int(P, P.gbest[((size_t)ref * n_mb + mb) * JMME_NBLK + b]);
+        } else if (P.ready) {
+            const uint2 v = __ldcg((const uint2 *)(res + b));
+            r.mvx = (int16_t)(v.x & 0xFFFF); r.mvy = (int16_t)(v.x >> 16); r.cost = (int)v.y;
+        } else {
+            r = res[b];
+        }
         mvx = r.mvx; mvy = r.mvy;
         mn = r.cost;
         if (P.pred) {
@@ -439,6 +465,16 @@ cudaError_t jmme_launch_subpel(const SearchParams &P, cudaStream_t st)
                      : cudaLaunchKernelEx(&cfg, me_subpel_kernel<true, 3, false>, P);
     }
     // (the wide form on whole stripes was measured: 2.6x slower on a 9-row stripe, 2x on the frame)
+    if (P.ready && !P.mb_list) {                          // early start behind the search kernel (programmatic dependent)
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.gridDim = dim3((unsigned)n_items); cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+        return P.ext ? cudaLaunchKernelEx(&cfg, me_subpel_kernel<false, 1, true>, P)
+                     : cudaLaunchKernelEx(&cfg, me_subpel_kernel<false, 1, false>, P);
+    }
     if (P.mb_list) {
         if (P.ext) me_subpel_kernel<true, 3, true><<<n_items, 384, 0, st>>>(P);
         else me_subpel_kernel<true, 3, false><<<n_items, 384, 0, st>>>(P);

@@ -52,8 +52,8 @@ class Params(C.Structure):
 class Tuning(C.Structure):
     """jmme_tuning: launch knobs of the product library, 0 = default."""
     _fields_ = [(n, C.c_int32) for n in ("variant", "group", "cluster", "table_rate", "wave_step", "no_pdl",
-                                         "pipe_parts", "balance", "even_parts")] + \
-        [("reserved", C.c_int32 * 7)]
+                                         "pipe_parts", "balance", "even_parts", "early_subpel", "no_pair_tail")] + \
+        [("reserved", C.c_int32 * 5)]
 
 
 MBRESULT_DTYPE = np.dtype([("mv", np.int16, (BLOCKS_PER_MB, 2)), ("cost", np.int32, (BLOCKS_PER_MB,)),

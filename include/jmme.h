@@ -255,15 +255,19 @@ typedef struct jmme_tuning {
     int32_t wave_step;       /* 1: in-frame median predictors always by the separate wave_step kernel                */
     int32_t no_pdl;          /* 1: no programmatic dependent launch between the kernels of a wavefront step         */
     int32_t pipe_parts;      /* host path: the stripe is searched in this many parts on separate streams (1..4)      */
-    int32_t balance;         /* zero-predictor search, R = 32: 0 = balanced task ranges when the stripe has two or   */
-                             /* more rounds of items, 1 = always, 2 = never (whole MB items per CTA)                 */
+    int32_t balance;         /* zero-predictor search, R = 32: 1 = balanced task ranges (every CTA an equal range of */
+                             /* the stripe's tasks); 0 / 2 = whole MB items per CTA (the measured default)           */
     int32_t even_parts;      /* host path: 1 = parts of equal size (default: a small first and a smaller last part)  */
-    int32_t reserved[7];
+    int32_t early_subpel;    /* sub-pel kernel as a programmatic dependent that waits per MB for the integer result  */
+                             /* (runs beside the last round of the search kernel): 0 = when the search deals whole   */
+                             /* items, 2 = never                                                                     */
+    int32_t no_pair_tail;    /* 1: items of 4 MBs to the last row (default: whole rounds of them, then rows of pairs) */
+    int32_t reserved[5];
 } jmme_tuning;
 int jmme_set_tuning(jmme_ctx *ctx, const jmme_tuning *t);
 int jmme_get_tuning(const jmme_ctx *ctx, jmme_tuning *t);      /* the values in effect (defaults resolved)         */
 /* Name and template arguments of the integer-search kernel the last search of this context launched, e.g.
- * "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0,BAL=1>" ("" before the
+ * "me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=126,KEYG=0,KRTAB=1,NMB=4,CL=1,WP=0,LIN=0,BAL=0>" ("" before the
  * first search; the oracle returns "cpu-oracle").  The parity tests assert it so that a test of a BASELINE
  * config provably ran the kernel the bench times. */
 const char *jmme_last_kernel(const jmme_ctx *ctx);

@@ -37,10 +37,10 @@ def oracle_threads(oracle, n):
 # regular expressions of the integer-search instantiation each BASELINE config launches by default (whole frame)
 DEFAULT_KERNELS = {
     "config1": r"me_int_kernel<K=3,NW=4,MINB=3,PER_BLOCK=0,ONLY16=1,RS_CT=0,MODE=0>$",
-    # zero predictors, R = 32: whole MB-pair items while a launch has less than two rounds of them (720p through the host
-    # path: three parts of 15 MB rows), else balanced task ranges over items of 4 MBs (BAL)
+    # zero predictors, R = 32: whole items of MB pairs while a launch has less than two rounds of them (720p through
+    # the host path: parts of 9 / 20 / 16 MB rows), else of 4 MBs
     "config2": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=94,KEYG=0,KRTAB=1,NMB=2,CL=1,WP=0,LIN=0,BAL=0>$",
-    "config3": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=126,KEYG=0,KRTAB=1,NMB=4,CL=1,WP=0,LIN=0,BAL=1>$",
+    "config3": r"me_int_tb_kernel<K=6,NW=4,MINB=3,PER_BLOCK=0,RS_CT=126,KEYG=0,KRTAB=1,NMB=4,CL=1,WP=0,LIN=0,BAL=0>$",
     "config4": r"me_int_kernel<K=5,NW=8,MINB=1,PER_BLOCK=0,ONLY16=0,RS_CT=144,MODE=0>$",
 }
 
@@ -380,8 +380,10 @@ def test_balanced_task_ranges_reproduce_whole_items(cuda, oracle, tuning, w, h, 
     kw = dict(search_range=R, qp=28, subpel=subpel)
     if rows:
         kw.update(mb_row_begin=rows[0], mb_row_end=rows[1])
-    ref = run(cuda, cur, refs, tuning=dict(balance=2, group=2), **kw)
+    ref = run(cuda, cur, refs, tuning=dict(balance=2, group=2, early_subpel=2), **kw)
     assert "BAL=0" in LAST["kernel"], LAST
+    dflt = run(cuda, cur, refs, **kw)                            # the default: whole items + early sub-pel start
+    assert "BAL=0" in LAST["kernel"] and dflt.tobytes() == ref.tobytes(), LAST
     with cuda.context(width=w, height=h, num_refs=nref, tuning=tuning, **kw) as ctx:
         for i, r in enumerate(refs):
             ctx.set_reference(i, r)

@@ -13,7 +13,7 @@ from jmme import synth  # noqa: E402
 from jmme.torch_api import DeviceSearch  # noqa: E402
 
 W, H, R = 1920, 1080, 32
-TUNINGS = [dict(balance=2), dict(), dict(balance=1), dict(balance=1, group=2)]
+TUNINGS = [dict(), dict(no_pair_tail=1), dict(group=2), dict(early_subpel=2), dict(balance=1)]
 lib = jmme.load()
 cur, refs = synth.frame_pair(W, H, seed=1, search_range=R)
 dcur, dref = torch.from_numpy(cur).cuda(), torch.from_numpy(refs[0]).cuda()

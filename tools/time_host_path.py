@@ -37,8 +37,8 @@ print("H2D 2.07 MB pinned  %.1f us" % t(lambda: (dbuf[: w * h].copy_(hc.view(-1)
 print("D2H 3.04 MB pinned  %.1f us" % t(lambda: (ho.copy_(dbuf[: n_mb * 372], non_blocking=True), torch.cuda.synchronize())))
 print("empty sync          %.1f us" % t(lambda: torch.cuda.synchronize()))
 pu8 = C.POINTER(C.c_uint8)
-for asyncref, ng, tn in ((0, 1, {}), (1, 1, {}), (1, 1, dict(even_parts=1)), (1, 1, dict(pipe_parts=4)), (1, 1, dict(pipe_parts=4, even_parts=1)),
-                         (1, 1, dict(pipe_parts=2))):
+for asyncref, ng, tn in ((0, 1, {}), (1, 1, {}), (1, 1, dict(early_subpel=2)), (1, 1, dict(even_parts=1)), (1, 1, dict(balance=1)),
+                         (1, 1, dict(pipe_parts=4)), (1, 1, dict(pipe_parts=2)), (1, 1, dict(pipe_parts=1)), (1, 1, {})):
     ctx = lib.context(width=w, height=h, search_range=R, subpel=1, qp=28, async_reference=asyncref, n_gpus=ng,
                       device_ids=[0] * ng, tuning=tn)
 
