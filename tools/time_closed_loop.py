@@ -24,8 +24,12 @@ print(f"MBs whose 41 median predictors are all equal: {100 * uniform:.1f} %; mod
       f"{[int((mode[:, 0] == m).sum()) for m in (1, 2, 3, 8)]}")
 dcur, dref = torch.from_numpy(cur).cuda(), torch.from_numpy(refs[0]).cuda()
 dpred = torch.from_numpy(pred).cuda()
-for name, kw, p in (("pass 1 zero predictors", dict(), None), ("pass 2 median predictors", dict(pred_policy=abi.PRED_PER_BLOCK), dpred)):
-    s = DeviceSearch(lib, width=w, height=h, search_range=R, subpel=1, qp=28, **kw)
+for name, kw, p in (("pass 1 zero predictors", dict(), None), ("pass 2 median predictors", dict(pred_policy=abi.PRED_PER_BLOCK), dpred),
+                    ("pass 2, rdopt lambda (rate from the table)", dict(pred_policy=abi.PRED_PER_BLOCK, rdopt=1), dpred),
+                    ("pass 2, integer only", dict(pred_policy=abi.PRED_PER_BLOCK, subpel=0), dpred),
+                    ("FullPelBlockMotionSearch: a window per block (me_full.cu), integer only",
+                     dict(pred_policy=abi.PRED_PER_BLOCK, search_mode=abi.SEARCH_FULL, subpel=0), dpred)):
+    s = DeviceSearch(lib, width=w, height=h, search_range=R, qp=28, **dict(dict(subpel=1), **kw))
     s.set_reference(0, dref)
     for _ in range(3):
         s.search(dcur, p)
