@@ -640,6 +640,14 @@ cudaError_t launch_tb(const SearchParams &P, int num_sms, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// balanced-range launch of a shape that has one (else the launch is refused: jmme_me_int_balanced never asks for it)
+template <int K, int NW, int MINB, int RS, int NMB, bool OK>
+cudaError_t launch_bal(const SearchParams &P, int num_sms, cudaStream_t st)
+{
+    if constexpr (OK) return launch_tb<K, NW, MINB, false, RS, false, true, NMB, 1, false, false, true>(P, num_sms, st);
+    else return cudaErrorInvalidValue;
+}
+
 }  // namespace
 
 // shape 7: 4 warps, >= 4 CTAs/SM (<= 128 registers)   shape 8: 4 warps, >= 3 CTAs/SM (<= 168 registers)
@@ -671,15 +679,15 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
         if (cmax >= 2 && 2 * n_items <= num_sms) return launch_tb<6, 12, 1, true, 0, false, false, 1, 2>(P, num_sms, st);
     }
     if (P.wave_tab) return cudaErrorInvalidValue;            // the host asks for in-kernel prediction only with this shape
-#define TB(KK, SH, NWW, MB, KG)                                                            \
+#define TB(KK, SH, NWW, MB, KG, BALOK)                                                          \
     if (K == KK && shape == SH) {                                                          \
         if (pb) return launch_tb<KK, NWW, MB, true, 0, KG>(P, num_sms, st);                \
         if (P.R == 32 && !P.pred && !KG) {                                                                     \
             const int grp = P.tune_group;                           /* MBs per item, default 2 */             \
             if (P.int_packed) {                                     /* balanced task ranges (BAL) */           \
-                if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4, 1, false, false, true>(P, num_sms, st);  \
-                if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2, 1, false, false, true>(P, num_sms, st);   \
-                return launch_tb<KK, NWW, MB, false, 78, false, true, 1, 1, false, false, true>(P, num_sms, st);                 \
+                if (grp >= 4) return launch_bal<KK, NWW, MB, 126, 4, BALOK>(P, num_sms, st);                    \
+                if (grp >= 2) return launch_bal<KK, NWW, MB, 94, 2, BALOK>(P, num_sms, st);                     \
+                return launch_bal<KK, NWW, MB, 78, 1, BALOK>(P, num_sms, st);                                   \
             }                                                                                                   \
             if (grp >= 4) return launch_tb<KK, NWW, MB, false, 126, false, true, 4>(P, num_sms, st);            \
             if (grp >= 2) return launch_tb<KK, NWW, MB, false, 94, false, true, 2>(P, num_sms, st);             \
@@ -689,11 +697,12 @@ cudaError_t jmme_launch_me_int_tb(const SearchParams &P, int num_sms, int K, int
         if (P.R == 64) return launch_tb<KK, NWW, MB, false, 142, KG>(P, num_sms, st);      \
         return launch_tb<KK, NWW, MB, false, 0, KG>(P, num_sms, st);                       \
     }
-    TB(4, 7, 4, 4, false)
-    TB(4, 8, 4, 3, false) TB(6, 8, 4, 3, false) TB(8, 8, 4, 3, false)
-    TB(6, 9, 6, 2, true)
-    TB(6, 6, 3, 4, false)
-    TB(6, 5, 6, 2, false) TB(6, 4, 12, 1, false)
+    // (BALOK: the shapes that have balanced-range instantiations — the default and the two the tests sweep)
+    TB(4, 7, 4, 4, false, false)
+    TB(4, 8, 4, 3, false, true) TB(6, 8, 4, 3, false, true) TB(8, 8, 4, 3, false, false)
+    TB(6, 9, 6, 2, true, false)
+    TB(6, 6, 3, 4, false, false)
+    TB(6, 5, 6, 2, false, true) TB(6, 4, 12, 1, false, false)
 #undef TB
     return cudaErrorInvalidValue;
 }
@@ -712,8 +721,7 @@ bool jmme_me_int_balanced(const SearchParams &P, int variant, int num_sms, bool 
     if (P.metric[0] == JMME_DIST_SSE || P.cost_domain || P.R != 32 || P.pred || P.mb_list) return false;
     if (P.blocktype_mask == JMME_MASK_16x16) return false;
     if (variant <= 0) variant = 68;
-    const int K = variant / 10, c = variant % 10;
-    return c >= 4 && c != 9 && K <= P.ncols;
+    return variant == 68 || variant == 65 || variant == 48;      // the shapes with BAL instantiations (TB(..., true))
 }
 
 // Does the integer search of P go to a me_int_tb_kernel launch that raises the per-MB ready flags (SearchParams::ready:
