@@ -343,7 +343,7 @@ def test_randomised_round2_parameter_space(cuda, oracle):
         elif mb_h >= 3 and rng.integers(0, 3) == 0:
             kw.update(mb_row_begin=int(rng.integers(0, 2)), mb_row_end=mb_h - int(rng.integers(0, 2)))
         tuning = dict(balance=int(rng.integers(0, 3)), group=int(rng.choice([0, 1, 2, 4])), pipe_parts=int(rng.integers(1, 5)),
-                      even_parts=int(rng.integers(0, 2)))
+                      even_parts=int(rng.integers(0, 2)), early_subpel=int(rng.choice([0, 0, 2])), no_pair_tail=int(rng.integers(0, 2)))
         cur, refs = synth.frame_pair(w, h, seed=300 + case, search_range=R, kind=str(rng.choice(["texture", "noise"])), num_refs=nref)
         pred = None if policy in (0, 3) else synth.random_pred(nref, mb_w * mb_h, 1 if policy == 1 else 41, case, maxp)
         g, k = run(cuda, cur, refs, pred, chroma=chroma, tuning=tuning, **kw)

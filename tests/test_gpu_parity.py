@@ -395,6 +395,35 @@ def test_balanced_task_ranges_reproduce_whole_items(cuda, oracle, tuning, w, h, 
         assert_same(got, run(oracle, cur, refs, **kw), f"{w}x{h} {tuning}")
 
 
+@pytest.mark.parametrize("tuning", [dict(), dict(early_subpel=2), dict(no_pair_tail=1), dict(group=2), dict(group=4, early_subpel=2),
+                                    dict(even_parts=1, pipe_parts=4)])
+@pytest.mark.parametrize("nref", [1, 2])
+def test_early_subpel_start_and_item_shapes(cuda, tuning, nref):
+    """The whole-item search with the early sub-pel start (per-MB ready flags, programmatic dependent launch), items of
+    4 MBs with a tail of pairs, through the host path and the device path, twice in a row in one context (the sub-pel
+    kernel lowers the flags): every launch shape gives the same field as the plain serial form."""
+    import torch
+    from jmme.torch_api import DeviceSearch
+    w, h, R = 1920, 400, 32                                   # 25 MB rows: 4-MB items in whole rounds + pair rows
+    cur, refs = synth.frame_pair(w, h, seed=17, search_range=R, num_refs=nref)
+    kw = dict(search_range=R, qp=28, subpel=1)
+    ref = run(cuda, cur, refs, tuning=dict(early_subpel=2, no_pair_tail=1, group=2, balance=2, pipe_parts=1), **kw)
+    with cuda.context(width=w, height=h, num_refs=nref, tuning=tuning, **kw) as ctx:
+        for i, r in enumerate(refs):
+            ctx.set_reference(i, r)
+        for rep in range(2):
+            assert ctx.search_frame(cur).tobytes() == ref.tobytes(), (tuning, rep, ctx.last_kernel())
+    ds = DeviceSearch(cuda, width=w, height=h, num_refs=nref, tuning=tuning, **kw)
+    dcur = torch.from_numpy(cur).cuda()
+    for i, r in enumerate(refs):
+        ds.set_reference(i, torch.from_numpy(r).cuda())
+    for rep in range(3):
+        out = ds.search(dcur)
+        torch.cuda.synchronize()
+        assert ds.to_numpy(out).tobytes() == ref.tobytes(), (tuning, rep)
+    ds.close()
+
+
 def test_launch_counter_counts_kernels(cuda):
     cur, refs = synth.frame_pair(64, 48, seed=1, search_range=4)
     with cuda.context(width=64, height=48, search_range=4, subpel=1) as ctx:
