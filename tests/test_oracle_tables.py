@@ -81,3 +81,27 @@ def test_search_before_reference_is_state_error(oracle):
         with pytest.raises(abi.JmmeError) as e:
             ctx.search_frame(np.zeros((32, 32), np.uint8))
         assert e.value.code == abi.ERR_STATE
+
+
+def test_spiral_inverse_closed_form():
+    """The arithmetic inverse of the spiral order that the CUDA kernels use at their result write (jmme_dev.cuh
+    d_spiral_xy: ring from an integer square root, top/bottom rows interleaved, then left/right columns), restated
+    here and checked against the generated order for every position of a +-64 window."""
+    import math
+
+    def inverse(k):
+        if k == 0:
+            return 0, 0
+        s = math.isqrt(k)
+        l = (s + 1) >> 1
+        w = 2 * l - 1
+        off = k - w * w
+        if off < 2 * w:
+            return (off >> 1) - l + 1, (l if off & 1 else -l)
+        o2 = off - 2 * w
+        return (l if o2 & 1 else -l), (o2 >> 1) - l
+
+    order = refimpl.spiral(64)
+    assert len(order) == 129 * 129
+    for k, xy in enumerate(order):
+        assert inverse(k) == tuple(xy), (k, xy)
